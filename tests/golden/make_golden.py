@@ -1,0 +1,138 @@
+"""Generate golden vectors by running the UNMODIFIED reference (/root/reference) in this container.
+
+The reference cannot travel to the GPU box, so its outputs are committed as small .npz fixtures
+next to this script.  Run from the repo root:
+
+    python tests/golden/make_golden.py
+
+Every configuration runs in a FRESH interpreter because the reference seeds the global NumPy RNG
+at import (phi.py:2) and consumes it in OneGroup.__init__ / Zone.__init__ (group.py:18, zone.py:11);
+the reference's own goldens were produced one configuration per process.
+Nothing is written under /root/reference (PYTHONDONTWRITEBYTECODE=1, h5py stub in /tmp).
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+STUBS = "/tmp/ae_golden_stubs"
+
+WORKER = r'''
+import sys, warnings, json
+warnings.filterwarnings("ignore")
+import numpy as np
+mode, out = sys.argv[1], sys.argv[2]
+from alpha_eigen_modules.slab import SymmetricHeterogeneousSlab
+from alpha_eigen_modules.group import OneGroup
+from alpha_eigen_modules.material import SimpleMaterial
+from alpha_eigen_modules.time_unit import TimeUnit
+
+def build(length, cpm, A):
+    fuel = SimpleMaterial('fuel', num_groups=1)
+    moderator = SimpleMaterial('moderator', num_groups=1)
+    absorber = SimpleMaterial('absorber', num_groups=1)
+    slab = SymmetricHeterogeneousSlab(length, cpm, A, moderator, fuel_mat=fuel, abs_mat=absorber)
+    g = OneGroup(slab=slab)
+    g.create_zones()
+    return slab, g
+
+if mode == "k":
+    length, cpm, A = map(int, sys.argv[3:6])
+    slab, g = build(length, cpm, A)
+    phi0_new, phi0_old = g.phi.new.copy(), g.phi.old.copy()
+    counts = {"sweeps": 0, "si": []}
+    orig_si = OneGroup.source_iteration_for_scalar_flux
+    orig_sw = OneGroup.sweep1D
+    def sw(self, angle, source, sigT=None):
+        counts["sweeps"] += 1
+        return orig_sw(self, angle, source, sigT)
+    def si(self, *a, **k):
+        before = counts["sweeps"]
+        r = orig_si(self, *a, **k)
+        counts["si"].append((counts["sweeps"] - before) // self.slab.num_angles)
+        return r
+    OneGroup.sweep1D = sw
+    OneGroup.source_iteration_for_scalar_flux = si
+    k = g.perform_power_iteration(quiet=True)
+    psi = np.stack([a.psi_midpoint[:, 0] for a in g.angle], axis=1)   # (Z, A)
+    np.savez_compressed(out, length=length, cells_per_mfp=cpm, num_angles=A,
+             k_new=k.new, k_old=k.old, phi0=phi0_old, phi_new=g.phi.new, phi_old=g.phi.old,
+             psi_midpoint=psi, si_hist=np.array(counts["si"], dtype=np.int32),
+             total_xs=g.total_xs, scatter_xs=g.scatter_xs, chi=g.chi, nu_sigmaf=g.nu_sigmaf,
+             mu=slab.mu, weight=slab.weight, hx=slab.hx)
+elif mode == "sweep":
+    # single sweeps + one source iteration on the K-P slab with a seeded arbitrary source
+    length, cpm, A = map(int, sys.argv[3:6])
+    slab, g = build(length, cpm, A)
+    rs = np.random.RandomState(7)
+    src = rs.rand(slab.num_zones, 1) + 0.1
+    psis = np.stack([g.sweep1D(g.angle[n], src) for n in range(A)], axis=1)       # (Z, A)
+    g.source = src.copy()
+    g.source_iteration_for_scalar_flux()
+    psi_after = np.stack([a.psi_midpoint[:, 0] for a in g.angle], axis=1)
+    np.savez_compressed(out, length=length, cells_per_mfp=cpm, num_angles=A, source=src, psi=psis,
+             phi_si=g.phi.new, psi_si=psi_after, total_xs=g.total_xs, scatter_xs=g.scatter_xs,
+             mu=slab.mu, weight=slab.weight, hx=slab.hx)
+elif mode == "dmd":
+    # unmodified TimeUnit.compute_alpha_eigenvalues on seeded snapshot arrays (SURVEY appendix A)
+    kind, Z, A, steps = sys.argv[3], int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
+    dt = 0.1
+    class S: pass
+    s = S(); s.num_zones, s.num_angles, s.num_groups = Z, A, 1
+    tu = TimeUnit(s, None, steps, dt)
+    rs = np.random.RandomState(11)
+    if kind == "modes":
+        # psi(t) = sum_j c_j v_j / (1 - alpha_j dt)^step : exact backward-Euler modes + decaying noise floor
+        alphas = np.array([-0.05, -0.3, -1.0, -2.5, 0.2])
+        V = rs.rand(Z * A, len(alphas)) + 0.1
+        lam = 1.0 / (1.0 - alphas * dt)
+        for st in range(steps):
+            col = V @ (np.array([1.0, 0.7, 0.5, 0.3, 1e-3]) * lam ** (st + 1))
+            tu.psi[:, :, 0, st] = col.reshape(Z, A)
+    else:
+        snap = np.load(sys.argv[7])["psi_snap"]           # (Z, A, 1, steps) from the repaired oracle march
+        tu.psi[...] = snap
+    al = tu.compute_alpha_eigenvalues()
+    np.savez_compressed(out, Z=Z, A=A, steps=steps, dt=dt, psi=tu.psi, alphas=np.asarray(al, dtype=complex))
+'''
+
+
+def run(args):
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1", PYTHONPATH=f"{STUBS}:/root/reference")
+    subprocess.check_call([sys.executable, "-W", "ignore", "-c", WORKER] + [str(a) for a in args],
+                          env=env, cwd="/tmp")
+
+
+def main():
+    os.makedirs(STUBS, exist_ok=True)
+    with open(os.path.join(STUBS, "h5py.py"), "w") as f:        # material.py:2 imports h5py unconditionally
+        f.write('class File:\n    def __init__(self,*a,**k): raise RuntimeError("h5py stub")\n')
+    for length, cpm, A in [(9, 5, 2), (9, 10, 4), (9, 20, 8), (9, 50, 4), (9, 100, 16)]:
+        out = os.path.join(HERE, f"kp_k_{length}_{cpm}_{A}.npz")
+        print("k golden", length, cpm, A, flush=True)
+        run(["k", out, length, cpm, A])
+    for length, cpm, A in [(9, 10, 4), (9, 37, 6)]:
+        out = os.path.join(HERE, f"kp_sweep_{length}_{cpm}_{A}.npz")
+        print("sweep golden", length, cpm, A, flush=True)
+        run(["sweep", out, length, cpm, A])
+    print("dmd golden (modes)", flush=True)
+    run(["dmd", os.path.join(HERE, "dmd_modes_64_4_50.npz"), "modes", 64, 4, 50])
+    run(["dmd", os.path.join(HERE, "dmd_modes_40_2_200.npz"), "modes", 40, 2, 200])
+    # DMD of a real (repaired) time march: snapshots come from the oracle, alphas from the reference routine
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from tests.kp import kp_problem, kp_psi0
+    from oracle import ae_oracle as orc
+    import numpy as np
+    for cpm, A, steps in [(10, 4, 50)]:
+        p = kp_problem(9, cpm, A)
+        res = orc.time_march(p["mu"], p["weight"], p["hx"], p["tables"], np.zeros((p["Z"], 1)),
+                             kp_psi0(p), 0.1, steps)
+        assert res["status"] == 0
+        tmp = f"/tmp/ae_march_{cpm}_{A}_{steps}.npz"
+        np.savez(tmp, psi_snap=res["psi_snap"])
+        print("dmd golden (march)", cpm, A, steps, flush=True)
+        run(["dmd", os.path.join(HERE, f"dmd_march_{cpm}_{A}_{steps}.npz"), "march", p["Z"], A, steps, tmp])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+"""Pin the CPU oracle against the reference: golden k values from the reference's own tests and
+phi / psi / alpha vectors produced by the unmodified reference (tests/golden/make_golden.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ae_oracle as orc
+from tests.kp import kp_problem, kp_psi0
+
+# reference goldens: tests/test_short_kornreich_parsons.py:39-42, tests/long_kornreich_parsons.py:35-36
+REF_GOLDEN_K = {(50, 4): 0.9358157950764868, (100, 16): 0.9885264464200719, (200, 196): 0.9900590623010896}
+
+
+@pytest.mark.parametrize("cpm,A", [(50, 4), (100, 16), (200, 196)])
+def test_reference_golden_k(cpm, A):
+    p = kp_problem(9, cpm, A)
+    r = orc.power_iteration(p["mu"], p["weight"], p["hx"], p["tables"], p["phi0"])
+    assert r["status"] == 0
+    assert abs(r["k_old"] - REF_GOLDEN_K[(cpm, A)]) < 1e-8      # the reference's own tolerance
+    assert abs(r["k_old"] - REF_GOLDEN_K[(cpm, A)]) < 1e-13     # what the restatement actually achieves
+
+
+def test_k_fixtures_bit_level(golden_dir):
+    files = sorted(glob.glob(os.path.join(golden_dir, "kp_k_*.npz")))
+    assert len(files) >= 5
+    for f in files:
+        g = np.load(f)
+        p = kp_problem(int(g["length"]), int(g["cells_per_mfp"]), int(g["num_angles"]))
+        np.testing.assert_array_equal(p["phi0"], g["phi0"])             # same RNG draw as phi.py:2,10-11
+        np.testing.assert_array_equal(p["total_xs"], g["total_xs"])     # same material map as slab.py:41-56
+        np.testing.assert_array_equal(p["scatter_xs"], g["scatter_xs"])
+        np.testing.assert_array_equal(p["nu_sigmaf"], g["nu_sigmaf"])
+        r = orc.power_iteration(p["mu"], p["weight"], p["hx"], p["tables"], p["phi0"], want_psi=True)
+        assert r["status"] == 0
+        assert list(r["si_hist"]) == list(g["si_hist"])                 # same iteration counts
+        assert abs(r["k_new"] - float(g["k_new"])) < 1e-14
+        np.testing.assert_allclose(r["phi_new"], g["phi_new"], rtol=1e-13, atol=0)
+        np.testing.assert_allclose(r["phi_old"], g["phi_old"], rtol=1e-13, atol=0)
+        np.testing.assert_allclose(r["psi"][:, :, 0], g["psi_midpoint"], rtol=1e-13, atol=1e-300)
+
+
+def test_sweep_fixtures_bit_exact(golden_dir):
+    for f in sorted(glob.glob(os.path.join(golden_dir, "kp_sweep_*.npz"))):
+        g = np.load(f)
+        mu, hx = g["mu"], float(g["hx"])
+        for n in range(len(mu)):
+            psi = orc.sweep(mu[n], hx, g["source"], g["total_xs"])
+            np.testing.assert_array_equal(psi, g["psi"][:, n])          # bit-exact single sweep, group.py:41-60
+        p = kp_problem(int(g["length"]), int(g["cells_per_mfp"]), int(g["num_angles"]))
+        st, phi, it, psi = orc.source_iteration(mu, g["weight"], hx, p["tables"], g["source"], want_psi=True)
+        assert st == 0
+        np.testing.assert_allclose(phi, g["phi_si"], rtol=1e-14, atol=0)
+        np.testing.assert_allclose(psi[:, :, 0], g["psi_si"], rtol=1e-14, atol=0)
+
+
+def _sorted_c(a):
+    a = np.asarray(a, dtype=complex)
+    return a[np.lexsort((a.imag, -a.real))]
+
+
+def test_dmd_fixtures(golden_dir):
+    files = sorted(glob.glob(os.path.join(golden_dir, "dmd_*.npz")))
+    assert len(files) >= 3
+    for f in files:
+        g = np.load(f)
+        al = orc.dmd_alpha_from_psi(g["psi"], int(g["steps"]), float(g["dt"]))
+        ref = g["alphas"]
+        assert len(al) == len(ref)                                      # same rank decision (time_unit.py:75-76)
+        # same LAPACK, same memory layout as time_unit.py:68-72 -> identical to rounding
+        np.testing.assert_allclose(_sorted_c(al), _sorted_c(ref), rtol=1e-12, atol=1e-13)
+
+
+def test_dmd_march_matches_oracle_march(golden_dir):
+    """The march fixture's snapshots came from the oracle's repaired time march: regenerate and compare."""
+    g = np.load(os.path.join(golden_dir, "dmd_march_10_4_50.npz"))
+    p = kp_problem(9, 10, 4)
+    res = orc.time_march(p["mu"], p["weight"], p["hx"], p["tables"], np.zeros((p["Z"], 1)), kp_psi0(p), 0.1, 50)
+    assert res["status"] == 0
+    np.testing.assert_array_equal(res["psi_snap"], g["psi"])
+    al = orc.dmd_alpha_from_psi(res["psi_snap"], 50, 0.1)
+    dom = _sorted_c(al)[0]
+    assert abs(dom - _sorted_c(g["alphas"])[0]) < 1e-10 * abs(dom)
+
+
+def test_multigroup_reduces_to_one_group():
+    """G=2 with two uncoupled identical groups must reproduce the one-group answer group by group."""
+    p = kp_problem(9, 10, 4)
+    t1 = p["tables"]
+    M = t1.M
+    scat = np.zeros((M, 2, 2))
+    scat[:, 0, 0] = t1.scat[:, 0, 0]
+    scat[:, 1, 1] = t1.scat[:, 0, 0]
+    t2 = orc.Tables(t1.mat, np.repeat(t1.total, 2, 1), scat, np.repeat(t1.chi, 2, 1), np.repeat(t1.nusf, 2, 1),
+                    np.repeat(t1.invspeed, 2, 1))
+    src = np.random.RandomState(3).rand(p["Z"], 1) + 0.1
+    st1, phi1, it1 = orc.source_iteration(p["mu"], p["weight"], p["hx"], t1, src)
+    st2, phi2, it2 = orc.source_iteration(p["mu"], p["weight"], p["hx"], t2, np.repeat(src, 2, 1))
+    assert st1 == st2 == 0 and it1 == it2
+    np.testing.assert_array_equal(phi2[:, 0:1], phi1)
+    np.testing.assert_array_equal(phi2[:, 1:2], phi1)
+
+
+def test_not_converged_status():
+    p = kp_problem(9, 5, 2)
+    st, phi, it = orc.source_iteration(p["mu"], p["weight"], p["hx"], p["tables"], np.ones((p["Z"], 1)),
+                                       max_iterations=5)
+    assert st == 1 and it == 4          # `assert iteration < max_iterations` (group.py:72): 4 iterations run
