@@ -1,0 +1,113 @@
+// Error reporting, ABI introspection and the cell storage map.
+#include <stdarg.h>
+#include <string.h>
+#include "ae_common.cuh"
+
+namespace ae {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    set_error("%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+    return AE_CUDA_ERROR;
+}
+
+}  // namespace ae
+
+extern "C" int ae_abi_version(void) { return AE_ABI_VERSION; }
+extern "C" const char *ae_last_error(void) { return ae::g_err; }
+extern "C" int64_t ae_padded_cells(int64_t Z) { return (Z + AE_TILE - 1) / AE_TILE * AE_TILE; }
+extern "C" int64_t ae_cell_offset(int64_t z)
+{
+    const int64_t tile = z / AE_TILE;
+    const int r = (int)(z % AE_TILE);
+    return tile * AE_TILE + ae::tile_offset(r / AE_LANE_CELLS, r % AE_LANE_CELLS);
+}
+
+// ---- layout conversion kernels (boundary only; not on the iteration path) -------------------
+namespace ae {
+
+__global__ void pack_cells_kernel(const double *__restrict__ logical, int64_t Z, int64_t Zp, int G, double *__restrict__ storage)
+{
+    const int64_t n = (int64_t)G * Zp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i / Zp);
+        const int64_t z = logical_cell(i % Zp);
+        storage[i] = z < Z ? logical[z * G + g] : 0.0;
+    }
+}
+
+__global__ void unpack_cells_kernel(const double *__restrict__ storage, int64_t Z, int64_t Zp, int G, double *__restrict__ logical)
+{
+    const int64_t n = (int64_t)G * Zp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i / Zp);
+        const int64_t z = logical_cell(i % Zp);
+        if (z < Z) logical[z * G + g] = storage[i];
+    }
+}
+
+__global__ void pack_psi_kernel(const double *__restrict__ logical, int64_t Z, int64_t Zp, int At, int G,
+                                const int32_t *__restrict__ aidx, int A, double *__restrict__ storage, int unpack)
+{
+    const int64_t n = (int64_t)G * A * Zp;
+    double *lw = const_cast<double *>(logical);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / Zp;
+        const int g = (int)(row / A), a = (int)(row % A);
+        const int64_t z = logical_cell(i % Zp);
+        const int64_t j = (z * At + aidx[a]) * G + g;
+        if (unpack) { if (z < Z) lw[j] = storage[i]; }
+        else storage[i] = z < Z ? logical[j] : 0.0;
+    }
+}
+
+static int grid_for(int64_t n) { int64_t b = (n + 255) / 256; return (int)(b < 148 * 32 ? b : 148 * 32); }
+
+}  // namespace ae
+
+extern "C" int ae_pack_cells(const double *logical, int64_t Z, int32_t G, double *storage, void *stream)
+{
+    const int64_t Zp = ae_padded_cells(Z);
+    ae::pack_cells_kernel<<<ae::grid_for(G * Zp), 256, 0, (cudaStream_t)stream>>>(logical, Z, Zp, G, storage);
+    AE_CUDA(cudaGetLastError());
+    return AE_OK;
+}
+
+extern "C" int ae_unpack_cells(const double *storage, int64_t Z, int32_t G, double *logical, void *stream)
+{
+    const int64_t Zp = ae_padded_cells(Z);
+    ae::unpack_cells_kernel<<<ae::grid_for(G * Zp), 256, 0, (cudaStream_t)stream>>>(storage, Z, Zp, G, logical);
+    AE_CUDA(cudaGetLastError());
+    return AE_OK;
+}
+
+extern "C" int ae_pack_psi(const double *logical, int64_t Z, int32_t A_total, int32_t G, const int32_t *angle_index,
+                           int32_t A, double *storage, void *stream)
+{
+    const int64_t Zp = ae_padded_cells(Z);
+    ae::pack_psi_kernel<<<ae::grid_for((int64_t)G * A * Zp), 256, 0, (cudaStream_t)stream>>>(logical, Z, Zp, A_total, G,
+                                                                                            angle_index, A, storage, 0);
+    AE_CUDA(cudaGetLastError());
+    return AE_OK;
+}
+
+extern "C" int ae_unpack_psi(const double *storage, int64_t Z, int32_t A_total, int32_t G, const int32_t *angle_index,
+                             int32_t A, double *logical, void *stream)
+{
+    const int64_t Zp = ae_padded_cells(Z);
+    ae::pack_psi_kernel<<<ae::grid_for((int64_t)G * A * Zp), 256, 0, (cudaStream_t)stream>>>(logical, Z, Zp, A_total, G,
+                                                                                            angle_index, A,
+                                                                                            const_cast<double *>(storage), 1);
+    AE_CUDA(cudaGetLastError());
+    return AE_OK;
+}

@@ -1,0 +1,239 @@
+// DMD on the device: tall-skinny Gram contraction + small dense eigen-solve.
+//
+// Replaces TimeUnit.compute_alpha_eigenvalues (reference time_unit.py:61-92).  With snapshot rows
+// s_0..s_K (K+1 consecutive steps, each a vector of length M in HBM), X = [s_0..s_{K-1}]^T,
+// Y = [s_1..s_K]^T.  Everything the reference needs from the thin SVD X = U S V^T follows from
+// the (K+1)x(K+1) Gram matrix C = S S^T:   X^T X = C[0:K,0:K] = V S^2 V^T,
+//   Atilde = U^T Y V S^-1 = S^-1 V^T (X^T Y) V S^-1,   X^T Y = C[0:K,1:K+1],
+// so U (M x K) is never formed.  The Gram contraction is the only O(M)
+// step; it is done with FP64 tensor-core DMMA (mma.sync.m8n8k4.f64 -- tcgen05 has no FP64 kind)
+// and reduced deterministically.  The K x K symmetric and non-symmetric eigenproblems go to
+// cuSOLVER (plain library calls on tiny matrices).
+#include <cusolverDn.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "ae_common.cuh"
+
+namespace ae {
+
+constexpr int kGN = 128;            // padded snapshot count handled by one CTA (n <= 128)
+constexpr int kGK = 32;             // columns (cells) staged per smem stage
+constexpr int kGStride = kGK + 4;   // padded row stride in doubles: conflict-free DMMA fragment loads
+
+__device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Each CTA (8 warps) owns a contiguous range of columns and accumulates the full n x n Gram of it.
+// Warp w computes output rows [16w, 16w+16) x all 128 columns as 2 x 16 DMMA tiles of 8x8
+// (64 accumulator doubles per lane).  The A fragment (row i0+lane/4, k0+lane%4) and the B fragment
+// (col j0+lane/4, k0+lane%4) are the same access pattern on the staged tile, because B = S^T.
+__global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ snap, int64_t ld, int64_t len, int n,
+                                                   int64_t cols_per_cta, double *__restrict__ partial)
+{
+    __shared__ double tile[kGN * kGStride];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t c_begin = (int64_t)blockIdx.x * cols_per_cta;
+    const int64_t c_end = min(len, c_begin + cols_per_cta);
+    double acc[2][16][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 16; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    for (int64_t c0 = c_begin; c0 < c_end; c0 += kGK) {
+        __syncthreads();
+        // stage rows 0..127 x kGK columns (zero beyond n / c_end); 32 consecutive doubles per row
+        for (int idx = tid; idx < kGN * kGK; idx += 256) {
+            const int r = idx / kGK, k = idx % kGK;
+            const int64_t c = c0 + k;
+            tile[r * kGStride + k] = (r < n && c < c_end) ? snap[(int64_t)r * ld + c] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k0 = 0; k0 < kGK; k0 += 4) {
+            double af[2];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) af[a] = tile[(warp * 16 + a * 8 + (lane >> 2)) * kGStride + k0 + (lane & 3)];
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                const double bf = tile[(b * 8 + (lane >> 2)) * kGStride + k0 + (lane & 3)];
+#pragma unroll
+                for (int a = 0; a < 2; ++a) dmma_8x8x4(acc[a][b][0], acc[a][b][1], af[a], bf);
+            }
+        }
+    }
+    // C fragment: row = lane/4, cols = 2*(lane%4) + {0,1}
+    double *out = partial + (size_t)blockIdx.x * kGN * kGN;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            const int r = warp * 16 + a * 8 + (lane >> 2), c = b * 8 + 2 * (lane & 3);
+            out[r * kGN + c] = acc[a][b][0];
+            out[r * kGN + c + 1] = acc[a][b][1];
+        }
+}
+
+__global__ void gram_reduce_kernel(const double *__restrict__ partial, int nparts, int n, double *__restrict__ gram)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    const int r = idx / n, c = idx % n;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * kGN * kGN + r * kGN + c];
+    gram[idx] = s;
+}
+
+// Atilde = S^-1 V^T Cxy V S^-1 for the r retained modes (column-major output for cuSOLVER).
+// V: eigenvectors of Cxx as returned by syevd (column-major K x K, eigenvalues ascending), so
+// retained mode j (descending sigma) is column K-1-j.
+__global__ void atilde_kernel(const double *__restrict__ gram, int n /*K+1*/, const double *__restrict__ V,
+                              const double *__restrict__ inv_sigma, int K, int r, double *__restrict__ T /*K x r*/,
+                              double *__restrict__ At /* r x r col-major */)
+{
+    // T = Cxy V_r   (K x r):  T[i][j] = sum_k C[i][k+1] V[k][col(j)]
+    for (int idx = threadIdx.x + blockIdx.x * blockDim.x; idx < K * r; idx += blockDim.x * gridDim.x) {
+        const int i = idx / r, j = idx % r, col = K - 1 - j;
+        double s = 0.0;
+        for (int k = 0; k < K; ++k) s = fma(gram[i * n + k + 1], V[(size_t)col * K + k], s);
+        T[idx] = s;
+    }
+    __threadfence();
+    __syncthreads();    // single-block launch: T complete
+    for (int idx = threadIdx.x; idx < r * r; idx += blockDim.x) {
+        const int i = idx % r, j = idx / r, coli = K - 1 - i;
+        double s = 0.0;
+        for (int k = 0; k < K; ++k) s = fma(V[(size_t)coli * K + k], T[k * r + j], s);
+        At[idx] = inv_sigma[i] * s * inv_sigma[j];
+    }
+}
+
+static int cusolver_fail(cusolverStatus_t st, const char *what)
+{
+    set_error("%s failed with cusolver status %d", what, (int)st);
+    return AE_CUDA_ERROR;
+}
+#define AE_CUSOLVER(call)                                              \
+    do {                                                               \
+        cusolverStatus_t s_ = (call);                                  \
+        if (s_ != CUSOLVER_STATUS_SUCCESS) { status = cusolver_fail(s_, #call); goto done; } \
+    } while (0)
+#define AE_CUDA_G(call)                                                \
+    do {                                                               \
+        cudaError_t e_ = (call);                                       \
+        if (e_ != cudaSuccess) { status = cuda_fail(e_, #call, __FILE__, __LINE__); goto done; } \
+    } while (0)
+
+}  // namespace ae
+
+using namespace ae;
+
+extern "C" int ae_gram(const double *snap, int64_t ld, int64_t len, int32_t n, double *gram, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!snap || !gram || n < 1 || n > kGN || len < 1 || ld < len) {
+        set_error("ae_gram: bad argument (n=%d must be <= %d)", n, kGN);
+        return AE_BAD_ARG;
+    }
+    int nparts = 148 * 2;
+    int64_t cols = (len + nparts - 1) / nparts;
+    cols = (cols + kGK - 1) / kGK * kGK;
+    nparts = (int)((len + cols - 1) / cols);
+    double *partial = nullptr;
+    AE_CUDA(cudaMallocAsync((void **)&partial, (size_t)nparts * kGN * kGN * sizeof(double), st));
+    gram_kernel<<<nparts, 256, 0, st>>>(snap, ld, len, n, cols, partial);
+    gram_reduce_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(partial, nparts, n, gram);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(partial, st);
+    AE_CUDA(e);
+    return AE_OK;
+}
+
+extern "C" int ae_dmd_from_gram(const double *gram_dev, int32_t K, double dt, double rank_tol, double *alpha_re,
+                                double *alpha_im, double *sigma_out, int32_t *rank, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!gram_dev || K < 1 || K + 1 > kGN || !alpha_re || !alpha_im || !rank) {
+        set_error("ae_dmd_from_gram: bad argument");
+        return AE_BAD_ARG;
+    }
+    int status = AE_OK;
+    const int n = K + 1;
+    cusolverDnHandle_t h = nullptr;
+    cusolverDnParams_t params = nullptr;
+    double *dV = nullptr, *dW = nullptr, *dwork = nullptr, *dT = nullptr, *dAt = nullptr, *dInv = nullptr;
+    double *dEig = nullptr;
+    void *dbuf = nullptr, *hbuf = nullptr;
+    int *dinfo = nullptr;
+    int lwork = 0, info = 0, r = 0;
+    size_t dbytes = 0, hbytes = 0;
+    double *lam = (double *)malloc(sizeof(double) * K), *sig = (double *)malloc(sizeof(double) * K),
+           *inv = (double *)malloc(sizeof(double) * K), *W = (double *)malloc(sizeof(double) * 2 * K);
+
+    AE_CUSOLVER(cusolverDnCreate(&h));
+    AE_CUSOLVER(cusolverDnSetStream(h, st));
+    AE_CUDA_G(cudaMalloc((void **)&dV, sizeof(double) * K * K));
+    AE_CUDA_G(cudaMalloc((void **)&dW, sizeof(double) * K));
+    AE_CUDA_G(cudaMalloc((void **)&dinfo, sizeof(int)));
+    // Cxx = gram[0:K,0:K] (symmetric, so row/column-major agree)
+    AE_CUDA_G(cudaMemcpy2DAsync(dV, sizeof(double) * K, gram_dev, sizeof(double) * n, sizeof(double) * K, K,
+                                cudaMemcpyDeviceToDevice, st));
+    AE_CUSOLVER(cusolverDnDsyevd_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, K, dV, K, dW, &lwork));
+    AE_CUDA_G(cudaMalloc((void **)&dwork, sizeof(double) * (size_t)lwork));
+    AE_CUSOLVER(cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, K, dV, K, dW, dwork, lwork, dinfo));
+    AE_CUDA_G(cudaMemcpyAsync(lam, dW, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
+    AE_CUDA_G(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AE_CUDA_G(cudaStreamSynchronize(st));
+    if (info != 0) { set_error("syevd info=%d", info); status = AE_CUDA_ERROR; goto done; }
+    {
+        // singular values of X, descending; rank rule of time_unit.py:75-76
+        double total = 0.0, run = 0.0;
+        for (int j = 0; j < K; ++j) { sig[j] = sqrt(fmax(lam[K - 1 - j], 0.0)); total += sig[j]; }
+        for (int j = 0; j < K; ++j) {
+            run += sig[j];
+            if (1.0 - run / total > rank_tol && sig[j] > 0.0) r = j + 1; else break;
+        }
+        if (r < 1) { set_error("ae_dmd_from_gram: no singular value survives the rank rule"); status = AE_BAD_ARG; goto done; }
+        for (int j = 0; j < r; ++j) inv[j] = 1.0 / sig[j];
+        if (sigma_out) memcpy(sigma_out, sig, sizeof(double) * K);
+    }
+    AE_CUDA_G(cudaMalloc((void **)&dT, sizeof(double) * K * r));
+    AE_CUDA_G(cudaMalloc((void **)&dAt, sizeof(double) * r * r));
+    AE_CUDA_G(cudaMalloc((void **)&dInv, sizeof(double) * r));
+    AE_CUDA_G(cudaMalloc((void **)&dEig, sizeof(double) * 2 * r));
+    AE_CUDA_G(cudaMemcpyAsync(dInv, inv, sizeof(double) * r, cudaMemcpyHostToDevice, st));
+    atilde_kernel<<<1, 1024, 0, st>>>(gram_dev, n, dV, dInv, K, r, dT, dAt);
+    AE_CUDA_G(cudaGetLastError());
+    // eigenvalues of the real non-symmetric r x r matrix (time_unit.py:90)
+    AE_CUSOLVER(cusolverDnCreateParams(&params));
+    AE_CUSOLVER(cusolverDnXgeev_bufferSize(h, params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, r, CUDA_R_64F,
+                                           dAt, r, CUDA_C_64F, dEig, CUDA_R_64F, nullptr, 1, CUDA_R_64F, nullptr, 1,
+                                           CUDA_R_64F, &dbytes, &hbytes));
+    AE_CUDA_G(cudaMalloc(&dbuf, dbytes ? dbytes : 8));
+    hbuf = malloc(hbytes ? hbytes : 8);
+    AE_CUSOLVER(cusolverDnXgeev(h, params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, r, CUDA_R_64F, dAt, r,
+                                CUDA_C_64F, dEig, CUDA_R_64F, nullptr, 1, CUDA_R_64F, nullptr, 1, CUDA_R_64F, dbuf,
+                                dbytes, hbuf, hbytes, dinfo));
+    AE_CUDA_G(cudaMemcpyAsync(W, dEig, sizeof(double) * 2 * r, cudaMemcpyDeviceToHost, st));
+    AE_CUDA_G(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AE_CUDA_G(cudaStreamSynchronize(st));
+    if (info != 0) { set_error("geev info=%d", info); status = AE_CUDA_ERROR; goto done; }
+    for (int j = 0; j < r; ++j) {
+        // alpha = (1 - 1/lambda)/dt  (time_unit.py:91), complex arithmetic
+        const double re = W[2 * j], im = W[2 * j + 1], d = re * re + im * im;
+        alpha_re[j] = (1.0 - re / d) / dt;
+        alpha_im[j] = (im / d) / dt;
+    }
+    *rank = r;
+done:
+    if (params) cusolverDnDestroyParams(params);
+    if (h) cusolverDnDestroy(h);
+    cudaFree(dV); cudaFree(dW); cudaFree(dwork); cudaFree(dT); cudaFree(dAt); cudaFree(dInv); cudaFree(dEig);
+    cudaFree(dbuf); cudaFree(dinfo);
+    free(hbuf); free(lam); free(sig); free(inv); free(W);
+    return status;
+}

@@ -1,0 +1,197 @@
+// Host-side iteration drivers behind the C ABI: source iteration, power iteration, time stepping.
+//
+// The loops of the reference (group.py:62-81, 97-116; time_unit.py:17-59) run here as streams of
+// kernel launches.  Convergence is decided ON THE DEVICE by the finalize / k-update / outer-check
+// kernels with the reference's formulas and tolerances; the host only polls a small control block
+// (one pinned-memory read per `batch` source iterations) so that iteration counts -- and therefore
+// results -- are identical to the reference's, which stops on the first iterate that passes.
+#include "ae_common.cuh"
+
+namespace ae {
+int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double *psi_out, double *partial,
+                 const ae_ctrl *ctrl, int gate, cudaStream_t st);
+int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, double *q_next, int init,
+                    double cold, double tol, int iteration, int gate, cudaStream_t st);
+int launch_fission_base(const ae_slab *s, const double *phi, double *base, cudaStream_t st);
+int launch_k_update(const ae_slab *s, ae_work *w, double tol, int iteration, cudaStream_t st);
+int launch_outer_check(const ae_slab *s, ae_work *w, cudaStream_t st);
+int launch_ctrl_init(ae_work *w, cudaStream_t st);
+
+static int poll_ctrl(ae_work *w, cudaStream_t st)
+{
+    AE_CUDA(cudaMemcpyAsync(w->ctrl_host, w->ctrl, sizeof(ae_ctrl), cudaMemcpyDeviceToHost, st));
+    AE_CUDA(cudaStreamSynchronize(st));
+    return AE_OK;
+}
+
+static int check_work(const ae_slab *s, const ae_work *w, const char *who)
+{
+    if (!s || !w || !w->phi || !w->phi_outer || !w->base || !w->q0 || !w->q1 || !w->partial || !w->norm_scratch ||
+        !w->ctrl || !w->ctrl_host || w->P != ae_partial_count(s->A, s->n_neg)) {
+        set_error("%s: incomplete ae_work / ae_slab", who);
+        return AE_BAD_ARG;
+    }
+    return AE_OK;
+}
+
+// group.py:62-81 / time_unit.py:44-59
+static int source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, double cold, double tol,
+                            int max_iterations, int *iters, int *last_q, cudaStream_t st)
+{
+    double *q[2] = {w->q0, w->q1};
+    const int batch = w->batch > 0 ? w->batch : 1;
+    // phi_old = cold (group.py:66 / time_unit.py:45); q0 = base + 0.5*sigma_s*phi_old (group.py:73)
+    AE_TRY(launch_finalize(s, w, nullptr, 0, q[0], 1, cold, tol, 0, 0, st));
+    int it = 0;         // iterations launched so far
+    for (;;) {
+        // `assert iteration < max_iterations` (group.py:72) fires when iteration reaches the cap
+        const int room = (max_iterations - 1) - it;
+        if (room <= 0) {
+            if (iters) *iters = it;
+            if (last_q) *last_q = (it - 1) & 1;
+            return AE_NOT_CONVERGED;
+        }
+        const int nb = batch < room ? batch : room;
+        for (int b = 0; b < nb; ++b) {
+            const int i = it + b;                       // 0-based; reference iteration number is i+1
+            const int gate = b > 0;                     // first of a batch always runs
+            AE_TRY(launch_sweep(s, q[i & 1], psi_in, nullptr, w->partial, w->ctrl, gate, st));
+            if (w->comm) {
+                // angle-sharded ranks: local partial sum -> NCCL sum over ranks -> same finalize on every rank
+                AE_TRY(ae_reduce_partials(s, w->partial, w->P, w->partial, st));
+                AE_TRY(ae_comm_allreduce_sum(w->comm, w->partial, (int64_t)s->G * s->Zp, st));
+                AE_TRY(launch_finalize(s, w, w->partial, 1, q[(i + 1) & 1], 0, cold, tol, i + 1, gate, st));
+            } else {
+                AE_TRY(launch_finalize(s, w, w->partial, w->P, q[(i + 1) & 1], 0, cold, tol, i + 1, gate, st));
+            }
+        }
+        AE_TRY(poll_ctrl(w, st));
+        if (w->ctrl_host->inner_done) {
+            const int n = w->ctrl_host->inner_iters;
+            if (iters) *iters = n;
+            if (last_q) *last_q = (n - 1) & 1;          // the sweep of iteration n read q[(n-1)&1]
+            return AE_OK;
+        }
+        it += nb;
+    }
+}
+
+}  // namespace ae
+
+using namespace ae;
+
+extern "C" int ae_flux_update(const ae_slab *s, ae_work *w, const double *partial, int32_t P, double *q_next, double tol,
+                              int32_t iteration, void *stream)
+{
+    AE_TRY(check_work(s, w, "ae_flux_update"));
+    if (!partial || !q_next || P < 1) { set_error("ae_flux_update: bad argument"); return AE_BAD_ARG; }
+    return launch_finalize(s, w, partial, P, q_next, 0, 0.0, tol, iteration, 0, (cudaStream_t)stream);
+}
+
+extern "C" int ae_source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, double cold_start, double tol,
+                                   int32_t max_iterations, int32_t *iters, int32_t *last_q_index, void *stream)
+{
+    AE_TRY(check_work(s, w, "ae_source_iteration"));
+    return source_iteration(s, w, psi_in, cold_start, tol, max_iterations, iters, last_q_index, (cudaStream_t)stream);
+}
+
+// group.py:97-116
+extern "C" int ae_power_iteration(const ae_slab *s, ae_work *w, double tol, int32_t max_iterations, double si_tol,
+                                  int32_t si_max_iterations, double *psi_out, double *k_new, double *k_old,
+                                  int32_t *iters, double *k_hist, int32_t *si_hist, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    AE_TRY(check_work(s, w, "ae_power_iteration"));
+    AE_TRY(launch_ctrl_init(w, st));                    // k.new = 1, k.old = 1.1 (eigenvalue.py:3-4)
+    int iteration = 0, status = AE_OK, last_q = 0;
+    double kn = 1.0, ko = 1.1;
+    for (;;) {
+        iteration += 1;
+        if (!(iteration < max_iterations)) { status = AE_NOT_CONVERGED; iteration -= 1; break; }   // group.py:102
+        ae_slab steady = *s;
+        steady.s_ext = nullptr;                          // group.py:104: source = zeros + fission
+        AE_TRY(launch_fission_base(&steady, w->phi_outer, w->base, st));
+        int si = 0;
+        status = source_iteration(s, w, nullptr, 1e-12, si_tol, si_max_iterations, &si, &last_q, st);
+        if (si_hist) si_hist[iteration - 1] = si;
+        if (status != AE_OK) { iteration -= 1; break; }     // *iters = completed power iterations
+        AE_TRY(launch_k_update(s, w, tol, iteration, st));
+        AE_TRY(poll_ctrl(w, st));
+        kn = w->ctrl_host->k_new;
+        ko = w->ctrl_host->k_old;
+        if (k_hist) k_hist[iteration - 1] = kn;
+        if (w->ctrl_host->power_done) break;
+    }
+    if (status == AE_OK && psi_out) {
+        // angle.psi_midpoint of the last sweep executed (group.py:59): replay it with the same source
+        const double *q = last_q ? w->q1 : w->q0;
+        AE_TRY(launch_sweep(s, q, nullptr, psi_out, w->partial, w->ctrl, 0, st));
+        AE_CUDA(cudaStreamSynchronize(st));
+    }
+    if (k_new) *k_new = kn;
+    if (k_old) *k_old = ko;
+    if (iters) *iters = iteration;
+    return status;
+}
+
+// time_unit.py:29-42 (+R3, R4): one backward-Euler step
+extern "C" int ae_time_step(const ae_slab *s, ae_work *w, const double *psi_prev, double *psi_next, double tol,
+                            int32_t *outer_iters, int32_t *inner_iters, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    AE_TRY(check_work(s, w, "ae_time_step"));
+    if (!psi_prev || !psi_next || !s->cdt) { set_error("ae_time_step: psi / cdt missing"); return AE_BAD_ARG; }
+    const size_t nbytes = (size_t)s->G * s->Zp * sizeof(double);
+    AE_CUDA(cudaMemsetAsync(w->phi_outer, 0, nbytes, st));      // time_unit.py:30 phi = zeros
+    int outer = 0, inner_total = 0, last_q = 0, status = AE_OK;
+    for (;;) {
+        outer += 1;
+        if (!(outer < 100)) { status = AE_NOT_CONVERGED; break; }               // time_unit.py:35
+        AE_TRY(launch_fission_base(s, w->phi_outer, w->base, st));              // time_unit.py:37-39
+        int si = 0;
+        status = source_iteration(s, w, psi_prev, 0.0, tol, 100, &si, &last_q, st);     // time_unit.py:40
+        inner_total += si;
+        if (status != AE_OK) break;
+        AE_TRY(launch_outer_check(s, w, st));                                   // time_unit.py:41 (+R4)
+        AE_TRY(poll_ctrl(w, st));
+        if (w->ctrl_host->outer_change < tol) break;                            // time_unit.py:42
+    }
+    if (outer_iters) *outer_iters = outer;
+    if (inner_iters) *inner_iters = inner_total;
+    if (status != AE_OK) return status;
+    // commit: replay the last sweep with its own source, now writing psi (time_unit.py:26-27)
+    const double *q = last_q ? w->q1 : w->q0;
+    AE_TRY(launch_sweep(s, q, psi_prev, psi_next, w->partial, w->ctrl, 0, st));
+    return AE_OK;
+}
+
+// time_unit.py:17-27 (+R2)
+extern "C" int ae_time_march(const ae_slab *s, ae_work *w, double *psi, double *psi_snap, double *phi_snap,
+                             int32_t num_steps, double tol, int32_t *outer_hist, int32_t *inner_hist, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    AE_TRY(check_work(s, w, "ae_time_march"));
+    if (!psi) { set_error("ae_time_march: psi missing"); return AE_BAD_ARG; }
+    const size_t n_phi = (size_t)s->G * s->Zp, n_psi = n_phi * s->A;
+    for (int step = 0; step < num_steps; ++step) {
+        const double *prev = psi;
+        double *next = psi;
+        if (psi_snap) {
+            prev = step == 0 ? psi : psi_snap + (size_t)(step - 1) * n_psi;
+            next = psi_snap + (size_t)step * n_psi;
+        }
+        int outer = 0, inner = 0;
+        const int status = ae_time_step(s, w, prev, next, tol, &outer, &inner, stream);
+        if (outer_hist) outer_hist[step] = outer;
+        if (inner_hist) inner_hist[step] = inner;
+        if (status != AE_OK) return status;
+        if (phi_snap)                                                            // time_unit.py:25
+            AE_CUDA(cudaMemcpyAsync(phi_snap + (size_t)step * n_phi, w->phi, n_phi * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, st));
+    }
+    if (psi_snap && num_steps > 0)
+        AE_CUDA(cudaMemcpyAsync(psi, psi_snap + (size_t)(num_steps - 1) * n_psi, n_psi * sizeof(double),
+                                cudaMemcpyDeviceToDevice, st));
+    AE_CUDA(cudaStreamSynchronize(st));
+    return AE_OK;
+}

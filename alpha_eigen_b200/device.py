@@ -1,0 +1,287 @@
+"""Device-resident slab problem: torch owns HBM and streams, the C ABI does the arithmetic.
+
+`SlabDevice` is the single place where the Python classes that mirror the reference
+(group.py / time_unit.py) meet libalpha_eigen_b200.so.  It uploads the cross-section tables
+and per-cell arrays in the lane-blocked storage order once, allocates the work buffers, and
+exposes one method per C entry point.  There is no CPU path: every method needs CUDA.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, layout
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.AlphaEigenError("alpha_eigen_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch
+
+
+def shard_angles(mu: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """Reference-angle indices owned by `rank`: negatives first, dealt round-robin so every rank
+    gets the same mix of directions (the rows of one sweep set are independent, group.py:74-77)."""
+    order = np.concatenate([np.flatnonzero(mu < 0), np.flatnonzero(mu >= 0)])
+    mine = order[rank::world]
+    return np.concatenate([mine[mu[mine] < 0], mine[mu[mine] >= 0]])
+
+
+class Comm:
+    """NCCL communicator created from a torch.distributed rendezvous (one process per GPU)."""
+
+    def __init__(self, rank: int, world: int):
+        import torch
+        import torch.distributed as dist
+        lib = _lib.load()
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            _lib.check(lib.ae_comm_unique_id(ident))
+        t = torch.tensor(list(bytes(ident)), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, 0)
+        ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+        self.handle = C.c_void_p()
+        _lib.check(lib.ae_comm_init(C.byref(self.handle), rank, world, ident))
+        self.rank, self.world = rank, world
+
+    def allreduce_(self, tensor):
+        torch = _torch()
+        _lib.check(_lib.load().ae_comm_allreduce_sum(self.handle, tensor.data_ptr(), tensor.numel(),
+                                                    torch.cuda.current_stream().cuda_stream))
+        return tensor
+
+    def close(self):
+        if self.handle:
+            _lib.load().ae_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+class SlabDevice:
+    """One (slab, cross-sections, dt) problem resident in HBM.
+
+    mu, weight ... all quadrature angles of the problem (slab.py:11); `angles` selects the
+                   reference-angle indices this rank owns (default: all)
+    mat .......... (Z,) material index per cell
+    total/chi/nusf/invspeed (M,G), scat (M,G,G) with scat[m][g'][g] = sigma_s(g'->g)
+    dt ........... None for steady state; otherwise sigT = total + inv_speed/dt (time_unit.py:24)
+    s_ext ........ (Z,G) fixed external source or None
+    """
+
+    def __init__(self, Z, hx, mu, weight, mat, total, scat, chi, nusf, invspeed, dt=None, s_ext=None,
+                 angles=None, comm: Comm | None = None, device=None, batch=None):
+        torch = _torch()
+        self.torch = torch
+        self.lib = _lib.load()
+        self.dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        mu = np.asarray(mu, dtype=np.float64)
+        weight = np.asarray(weight, dtype=np.float64)
+        if np.any(np.abs(mu) <= 1e-10):
+            raise AssertionError("abs(mu) must exceed 1e-10")          # group.py:44
+        if angles is None:
+            angles = shard_angles(mu, 0, 1)
+        self.angles = np.asarray(angles, dtype=np.int64)              # device angle a <-> reference angle angles[a]
+        self.Z, self.hx = int(Z), float(hx)
+        self.Zp = layout.padded_cells(self.Z)
+        self.A_total = len(mu)
+        self.A = len(self.angles)
+        total = np.asarray(total, dtype=np.float64)
+        self.M, self.G = total.shape
+        self.dt = dt
+        self.comm = comm
+        mu_loc, w_loc = mu[self.angles], weight[self.angles]
+        self.n_neg = int(np.sum(mu_loc < 0))
+        assert np.all(mu_loc[:self.n_neg] < 0) and np.all(mu_loc[self.n_neg:] > 0)
+        ihx = 1 / self.hx                                             # group.py:46
+        mat = np.asarray(mat, dtype=np.int64)
+        sigT = total[mat]                                             # (Z,G)
+        inv_cell = np.asarray(invspeed, dtype=np.float64)[mat]
+        if dt is not None:
+            sigT = sigT + 1 / dt * inv_cell                           # time_unit.py:24
+        up = self._upload
+        self.t_mu = up(mu_loc * ihx)
+        self.t_w = up(w_loc)
+        self.t_aidx = up(self.angles.astype(np.int32))
+        self.t_mat = up(layout.to_storage(mat.astype(np.int32), self.Z))
+        self.t_scat = up(np.asarray(scat, dtype=np.float64).reshape(self.M, self.G, self.G))
+        self.t_chi = up(np.asarray(chi, dtype=np.float64).reshape(self.M, self.G))
+        self.t_nusf = up(np.asarray(nusf, dtype=np.float64).reshape(self.M, self.G))
+        self.t_hs = self.cells_to_device(0.5 * sigT)                  # [G][Zp]
+        self.t_cdt = self.cells_to_device(inv_cell / dt) if dt is not None else None
+        self.t_sext = self.cells_to_device(s_ext) if s_ext is not None else None
+        del sigT, inv_cell
+        self.P = int(self.lib.ae_partial_count(self.A, self.n_neg))
+        n = self.G * self.Zp
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        self.phi = torch.zeros(n, **f64)
+        self.phi_outer = torch.zeros(n, **f64)
+        self.base = torch.zeros(n, **f64)
+        self.q0 = torch.zeros(n, **f64)
+        self.q1 = torch.zeros(n, **f64)
+        self.partial = torch.zeros(self.P * n, **f64)
+        self.scratch = torch.zeros(4 * int(self.lib.ae_norm_blocks(self.Zp)), **f64)
+        self.ctrl = torch.zeros(C.sizeof(_lib.AeCtrl), dtype=torch.uint8, device=self.dev)
+        self.ctrl_host = torch.zeros(C.sizeof(_lib.AeCtrl), dtype=torch.uint8).pin_memory()
+        if batch is None:       # small problems are launch-latency bound: poll the flag less often
+            batch = 1 if (comm is not None or self.Z * self.A * self.G > (1 << 24)) else 8
+        self.slab = _lib.AeSlab(self.Z, self.Zp, self.A, self.n_neg, self.G, self.M, self.t_mu.data_ptr(),
+                                self.t_w.data_ptr(), self.t_mat.data_ptr(), self.t_scat.data_ptr(),
+                                self.t_chi.data_ptr(), self.t_nusf.data_ptr(), self.t_hs.data_ptr(),
+                                self.t_cdt.data_ptr() if self.t_cdt is not None else None,
+                                self.t_sext.data_ptr() if self.t_sext is not None else None)
+        self.work = _lib.AeWork(self.phi.data_ptr(), self.phi_outer.data_ptr(), self.base.data_ptr(),
+                                self.q0.data_ptr(), self.q1.data_ptr(), self.partial.data_ptr(),
+                                self.scratch.data_ptr(), self.ctrl.data_ptr(), self.ctrl_host.data_ptr(),
+                                comm.handle.value if comm is not None else None, self.P, int(batch))
+        self.last_q_index = 0
+
+    @classmethod
+    def for_sweep(cls, Z, hx, mu, weight, sigT):
+        """Bare problem for single sweeps with an explicit per-cell sigT (Z,G) (group.py:41-43)."""
+        sigT = np.asarray(sigT, dtype=np.float64)
+        G = sigT.shape[1]
+        dev = cls(Z, hx, mu, weight, np.zeros(Z, dtype=np.int64), np.zeros((1, G)), np.zeros((1, G, G)),
+                  np.zeros((1, G)), np.zeros((1, G)), np.zeros((1, G)))
+        dev.t_hs = dev._upload(layout.to_storage((0.5 * sigT).T, dev.Z))
+        dev.slab.hs = dev.t_hs.data_ptr()
+        return dev
+
+    # ---- plumbing ------------------------------------------------------------------------
+    def _upload(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+
+    @property
+    def stream(self):
+        return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def cells_to_device(self, a, out=None):
+        """(Z,G) logical ndarray / host tensor -> [G][Zp] storage tensor (packed on the device)."""
+        torch = self.torch
+        if not torch.is_tensor(a):
+            a = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(self.Z, self.G)))
+        d = a.to(self.dev, non_blocking=True)
+        if out is None:
+            out = torch.empty(self.G * self.Zp, dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.ae_pack_cells(d.data_ptr(), self.Z, self.G, out.data_ptr(), self.stream))
+        return out
+
+    def cells_to_host(self, t, out=None):
+        """[G][Zp] storage tensor -> (Z,G) logical ndarray (or into the pinned host tensor `out`)."""
+        torch = self.torch
+        d = torch.empty(self.Z * self.G, dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.ae_unpack_cells(t.data_ptr(), self.Z, self.G, d.data_ptr(), self.stream))
+        if out is not None:
+            out.copy_(d.view(out.shape), non_blocking=True)
+            torch.cuda.current_stream(self.dev).synchronize()
+            return out
+        return d.cpu().numpy().reshape(self.Z, self.G)
+
+    def psi_to_device(self, psi):
+        """(Z, A_total, G) logical, reference angle order -> [G][A][Zp] for the local angles."""
+        torch = self.torch
+        h = torch.from_numpy(np.ascontiguousarray(np.asarray(psi, dtype=np.float64).reshape(self.Z, self.A_total, self.G)))
+        d = h.to(self.dev)
+        out = torch.empty(self.G * self.A * self.Zp, dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.ae_pack_psi(d.data_ptr(), self.Z, self.A_total, self.G, self.t_aidx.data_ptr(), self.A,
+                                        out.data_ptr(), self.stream))
+        return out
+
+    def psi_to_host(self, t):
+        """[G][A][Zp] -> (Z, A, G) for the local angles (device angle order)."""
+        torch = self.torch
+        d = torch.zeros(self.Z * self.A_total * self.G, dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.ae_unpack_psi(t.data_ptr(), self.Z, self.A_total, self.G, self.t_aidx.data_ptr(), self.A,
+                                          d.data_ptr(), self.stream))
+        full = d.cpu().numpy().reshape(self.Z, self.A_total, self.G)
+        return np.ascontiguousarray(full[:, self.angles, :])
+
+    def new_psi(self):
+        return self.torch.zeros(self.G * self.A * self.Zp, dtype=self.torch.float64, device=self.dev)
+
+    # ---- C entry points --------------------------------------------------------------------
+    def sweep_set(self, q, psi_in=None, psi_out=None):
+        """ae_sweep_set + ae_reduce_partials: returns the [G][Zp] scalar flux of the local angles
+        (summed over ranks when a communicator is attached)."""
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        _lib.check(self.lib.ae_sweep_set(C.byref(self.slab), q.data_ptr(), ptr(psi_in), ptr(psi_out),
+                                         self.partial.data_ptr(), self.stream))
+        phi = self.torch.empty(self.G * self.Zp, dtype=self.torch.float64, device=self.dev)
+        _lib.check(self.lib.ae_reduce_partials(C.byref(self.slab), self.partial.data_ptr(), self.P, phi.data_ptr(),
+                                               self.stream))
+        if self.comm is not None:
+            self.comm.allreduce_(phi)
+        return phi
+
+    def flux_update(self, partial, P, q_next, tol=0.0, iteration=0):
+        """ae_flux_update: phi assembly + norm + next scatter source (w->base must be set)."""
+        _lib.check(self.lib.ae_flux_update(C.byref(self.slab), C.byref(self.work), partial.data_ptr(), P,
+                                           q_next.data_ptr(), tol, iteration, self.stream))
+
+    def read_ctrl(self):
+        """Copy the device control block to the host (synchronises the stream)."""
+        self.ctrl_host.copy_(self.ctrl, non_blocking=True)
+        self.torch.cuda.current_stream(self.dev).synchronize()
+        return _lib.AeCtrl.from_buffer_copy(bytes(self.ctrl_host.numpy()))
+
+    def source_iteration(self, base, psi_in=None, cold_start=1e-12, tol=1e-8, max_iterations=100):
+        """ae_source_iteration.  `base` [G][Zp] tensor is the fixed source.  Returns (status, iterations)."""
+        self.base.copy_(base)
+        it, lq = C.c_int32(0), C.c_int32(0)
+        st = self.lib.ae_source_iteration(C.byref(self.slab), C.byref(self.work),
+                                          psi_in.data_ptr() if psi_in is not None else None, cold_start, tol,
+                                          max_iterations, C.byref(it), C.byref(lq), self.stream)
+        self.last_q_index = lq.value
+        return st, it.value
+
+    def power_iteration(self, phi_old, tol=1e-8, max_iterations=100, si_tol=1e-8, si_max_iterations=100,
+                        psi_out=None):
+        """ae_power_iteration.  phi_old: (Z,G) ndarray (phi.old).  Returns dict like the oracle's."""
+        self.phi_outer.copy_(self.cells_to_device(phi_old))
+        k_new, k_old, it = C.c_double(0), C.c_double(0), C.c_int32(0)
+        k_hist = (C.c_double * max_iterations)()
+        si_hist = (C.c_int32 * max_iterations)()
+        st = self.lib.ae_power_iteration(C.byref(self.slab), C.byref(self.work), tol, max_iterations, si_tol,
+                                         si_max_iterations, psi_out.data_ptr() if psi_out is not None else None,
+                                         C.byref(k_new), C.byref(k_old), C.byref(it), k_hist, si_hist, self.stream)
+        n = it.value
+        return dict(status=st, k_new=k_new.value, k_old=k_old.value, iterations=n,
+                    phi_new=self.cells_to_host(self.phi), phi_old=self.cells_to_host(self.phi_outer),
+                    k_hist=np.array(k_hist[:n]), si_hist=np.array(si_hist[:n], dtype=np.int32))
+
+    def time_step(self, psi_prev, psi_next, tol=1e-10):
+        outer, inner = C.c_int32(0), C.c_int32(0)
+        st = self.lib.ae_time_step(C.byref(self.slab), C.byref(self.work), psi_prev.data_ptr(), psi_next.data_ptr(),
+                                   tol, C.byref(outer), C.byref(inner), self.stream)
+        return st, outer.value, inner.value
+
+    def time_march(self, psi, num_steps, tol=1e-10, psi_snap=None, phi_snap=None):
+        """ae_time_march.  psi: [G][A][Zp] tensor (psi0 in, last psi out)."""
+        outer = (C.c_int32 * num_steps)()
+        inner = (C.c_int32 * num_steps)()
+        st = self.lib.ae_time_march(C.byref(self.slab), C.byref(self.work), psi.data_ptr(),
+                                    psi_snap.data_ptr() if psi_snap is not None else None,
+                                    phi_snap.data_ptr() if phi_snap is not None else None, num_steps, tol,
+                                    outer, inner, self.stream)
+        return st, np.array(outer[:], dtype=np.int32), np.array(inner[:], dtype=np.int32)
+
+    # ---- DMD ---------------------------------------------------------------------------------
+    def gram(self, snap, row_len, first, count):
+        """Gram matrix [count][count] of snapshot rows first..first+count-1 of `snap` [steps][row_len];
+        summed over ranks when the rows are sharded."""
+        g = self.torch.empty(count * count, dtype=self.torch.float64, device=self.dev)
+        _lib.check(self.lib.ae_gram(snap.data_ptr() + 8 * first * row_len, row_len, row_len, count, g.data_ptr(),
+                                    self.stream))
+        if self.comm is not None:
+            self.comm.allreduce_(g)
+        return g
+
+    def dmd_from_gram(self, gram, K, dt, rank_tol=1e-13):
+        are, aim, sig = (C.c_double * K)(), (C.c_double * K)(), (C.c_double * K)()
+        r = C.c_int32(0)
+        _lib.check(self.lib.ae_dmd_from_gram(gram.data_ptr(), K, dt, rank_tol, are, aim, sig, C.byref(r), self.stream))
+        n = r.value
+        alphas = np.array(are[:n]) + 1j * np.array(aim[:n])
+        return alphas, np.array(sig[:]), n

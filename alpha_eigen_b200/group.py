@@ -1,0 +1,230 @@
+"""Transport solver container (mirror of reference group.py: OneGroup, MultiGroup).
+
+Same constructor, attributes, method names, return objects, prints and assertion messages as
+the reference; the method bodies hand the arithmetic to the sm_100a kernels through
+`SlabDevice` (C ABI in include/alpha_eigen_b200.h).  Nothing here computes a sweep on the host.
+"""
+import numpy as np
+
+from . import _lib, distributed
+from .device import SlabDevice, shard_angles
+from .eigenvalue import Eigenvalue
+from .material import material_row
+from .one_direction import OneDirection
+from .phi import Phi, ZoneFlux
+from .zone import Zone
+
+
+class _LazyZones:
+    """Sequence of Zone objects materialised on demand.
+
+    The reference appends one Zone per cell in a Python loop (group.py:26-27): minutes and GBs at
+    1e6 cells.  Region assignment and the per-zone RNG draw (zone.py:11) are done vectorised in
+    create_zones(); a Zone object is only built when somebody indexes the list.
+    """
+
+    def __init__(self, slab, midpoints, materials, names, index, draws):
+        self._slab, self._mid, self._mats, self._names, self._idx, self._draws = slab, midpoints, materials, names, index, draws
+        self._cache = {}
+
+    def __len__(self):
+        return len(self._mid)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        z = self._cache.get(i)
+        if z is None:
+            z = Zone(self._slab, self._mid[i], _draw=self._draws[i])
+            z.material, z.region_name = self._mats[self._idx[i]], self._names[self._idx[i]]
+            self._cache[i] = z
+        return z
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class OneGroup:
+    def __init__(self, slab, material=None):
+        self.slab = slab
+        self.material = material
+        Z, G = self.slab.num_zones, self.slab.num_groups
+        self.total_xs = np.zeros((Z, G))
+        self.scatter_xs = np.zeros((Z, G))          # in-group sigma_s(g->g); the full matrix lives in the materials
+        self.chi = np.zeros((Z, G))
+        self.nu_sigmaf = np.zeros((Z, G))
+        self.inv_speed = np.ones((Z, G))
+        self.source = np.zeros((Z, G))
+        self.phi = Phi(Z, G)                        # group.py:18: Z*G draws from the global RNG
+        self.angle = [OneDirection(number=n, slab=self.slab, group=self) for n in range(self.slab.num_angles)]
+        self.zone = []
+        self._materials = []                        # distinct material objects, first-appearance order
+        self._mat_index = None                      # (Z,) index into _materials
+        self._dev = {}                              # dt -> (fingerprint, SlabDevice)
+        self._psi_replay = None                     # (SlabDevice, psi_in tensor or None) of the last solve
+
+    # ------------------------------------------------------------------ problem set-up ----
+    def create_zones(self):
+        """group.py:24-35: one Zone per cell, material from the slab map, xs arrays filled per cell."""
+        s = self.slab
+        Z, G = s.num_zones, s.num_groups
+        mid = np.linspace(s.hx / 2, s.length - s.hx / 2, Z)
+        if self.material is None and hasattr(s, "assign_all"):
+            draws = np.random.rand(Z, G) * 2        # == Z successive rand(G)*2 draws (zone.py:11, phi.py:8)
+            mats, names, idx = s.assign_all(mid)
+            self.zone = _LazyZones(s, mid, mats, names, idx, draws)
+        else:
+            zones, mats, idx = [], [], np.empty(Z, dtype=np.int64)
+            for i in range(Z):
+                z = Zone(s, mid[i])
+                if self.material is None:
+                    s.assign_zone_material(z)
+                else:
+                    z.material = self.material
+                zones.append(z)
+                for j, m in enumerate(mats):
+                    if m is z.material:
+                        idx[i] = j
+                        break
+                else:
+                    mats.append(z.material)
+                    idx[i] = len(mats) - 1
+            self.zone = zones
+        self._materials, self._mat_index = mats, idx
+        rows = [material_row(m, G) for m in mats]
+        self.total_xs[:] = np.array([r[0] for r in rows])[idx]
+        self.scatter_xs[:] = np.array([np.diag(r[1]) for r in rows])[idx]
+        self.chi[:] = np.array([r[2] for r in rows])[idx]
+        self.nu_sigmaf[:] = np.array([r[3] for r in rows])[idx]
+        self.inv_speed[:] = np.array([r[4] for r in rows])[idx]
+
+    def reset(self):                                # group.py:37-39
+        self.source = np.zeros((self.slab.num_zones, self.slab.num_groups))
+        self.phi = Phi(self.slab.num_zones, self.slab.num_groups)
+
+    # ------------------------------------------------------------------ device plumbing ---
+    def _tables(self):
+        """(mat index, total, scat, chi, nusf, invspeed) tables for the device.
+
+        One group: the per-cell arrays are the source of truth, as in the reference, so edits to
+        group.total_xs etc. are honoured; distinct rows become materials.  G > 1: the scatter
+        matrix only exists on the material objects, so the tables come from them.
+        """
+        G = self.slab.num_groups
+        if G == 1:
+            cols = np.column_stack([np.ravel(x) for x in (self.total_xs, self.scatter_xs, self.chi, self.nu_sigmaf,
+                                                           self.inv_speed)])
+            uniq, inv = np.unique(cols, axis=0, return_inverse=True)
+            return (inv.reshape(-1), uniq[:, 0:1], uniq[:, 1:2].reshape(-1, 1, 1), uniq[:, 2:3], uniq[:, 3:4],
+                    uniq[:, 4:5])
+        assert self._mat_index is not None, "call create_zones() first"
+        rows = [material_row(m, G) for m in self._materials]
+        stack = lambda k: np.array([r[k] for r in rows])
+        return self._mat_index, stack(0), stack(1), stack(2), stack(3), stack(4)
+
+    def _device(self, dt=None, s_ext=None):
+        tabs = self._tables()
+        sx = None if s_ext is None else np.asarray(s_ext, dtype=np.float64)
+        key = (dt, self.slab.hx, tuple(np.asarray(self.slab.mu)), tuple(a.tobytes() if a.size < 4096 else (a.shape, float(a.sum()), float((a * a).sum()))
+                                                                        for a in map(np.asarray, tabs)),
+               None if sx is None else (sx.shape, float(sx.sum()), float((sx * sx).sum())))
+        hit = self._dev.get(dt)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        comm = distributed.communicator()
+        mu = np.asarray(self.slab.mu, dtype=np.float64)
+        angles = shard_angles(mu, comm.rank, comm.world) if comm is not None else None
+        dev = SlabDevice(self.slab.num_zones, self.slab.hx, mu, self.slab.weight, *tabs, dt=dt, s_ext=sx,
+                         angles=angles, comm=comm)
+        self._dev[dt] = (key, dev)
+        return dev
+
+    def _refresh_psi(self):
+        """Fill angle[n].psi_midpoint from the device by replaying the last sweep (group.py:59)."""
+        if self._psi_replay is None:
+            return
+        dev, psi_in = self._psi_replay
+        self._psi_replay = None
+        psi = dev.new_psi()
+        dev.sweep_set(dev.q1 if dev.last_q_index else dev.q0, psi_in=psi_in, psi_out=psi)
+        host = dev.psi_to_host(psi)                 # (Z, A_local, G)
+        for a, n in enumerate(dev.angles):
+            self.angle[n]._psi_midpoint = host[:, a, :].copy()
+
+    # ------------------------------------------------------------------ solver surface ----
+    def sweep1D(self, angle, source, sigT=None):
+        """group.py:41-60: one diamond-difference sweep of one angle; returns psi at cell centres
+        ((Z,) for one group, (Z,G) otherwise) and stores it in angle.psi_midpoint."""
+        if sigT is None:
+            sigT = self.total_xs
+        assert (np.abs(angle.mu) > 1e-10)
+        Z, G = self.slab.num_zones, self.slab.num_groups
+        sigT = np.asarray(sigT, dtype=np.float64).reshape(Z, G)
+        dev = SlabDevice.for_sweep(Z, self.slab.hx, [angle.mu], [angle.weight], sigT)
+        psi = dev.new_psi()
+        dev.sweep_set(dev.cells_to_device(np.asarray(source, dtype=np.float64).reshape(Z, G)), psi_out=psi)
+        out = dev.psi_to_host(psi)[:, 0, :]
+        angle._psi_midpoint = out.copy()
+        self._psi_replay = None
+        return out[:, 0] if G == 1 else out
+
+    def source_iteration_for_scalar_flux(self, tolerance=1.0e-8, max_iterations=100):
+        """group.py:62-81: iterate the scattering source to convergence for the fixed self.source."""
+        dev = self._device()
+        st, _ = dev.source_iteration(dev.cells_to_device(self.source), None, 1e-12, tolerance, max_iterations)
+        _lib.check(st, "Warning: source iteration did not converge")
+        self.phi.new = dev.cells_to_host(dev.phi)
+        self._psi_replay = (dev, None)
+
+    def perform_power_iteration(self, tolerance=1.0e-8, max_iterations=100, quiet=False):
+        """group.py:97-116: k-eigenvalue power iteration, entirely on the device."""
+        dev = self._device()
+        r = dev.power_iteration(self.phi.old, tolerance, max_iterations)
+        k = Eigenvalue()
+        for it, k_new in enumerate(r["k_hist"], start=1):
+            if not quiet:                           # group.py:110-113
+                print("*************************====================")
+                print("Power Iteration", it, ": k =", k_new, "Relative Change =", np.abs(k_new - k.old))
+                print("*************************====================")
+            k.new = float(k_new)
+            k.converged = bool(np.abs(k.new - k.old) < tolerance)
+            k.old = k.new
+        if r["status"] == _lib.AE_NOT_CONVERGED:
+            inner = r["iterations"] < max_iterations - 1
+            raise AssertionError("Warning: source iteration did not converge" if inner
+                                 else "Warning: power iteration did not converge")
+        _lib.check(r["status"])
+        self.source = dev.cells_to_host(dev.base)   # group.py:104-105 of the last iteration
+        self.phi.new = r["phi_new"]
+        self.phi.old = r["phi_old"]
+        self._psi_replay = (dev, None)
+        return k
+
+    def calculate_scalar_flux(self):
+        """group.py:83-95 is an infinite loop in the reference; kept as an explicit error."""
+        raise NotImplementedError("calculate_scalar_flux is dead code in the reference (group.py:88-89)")
+
+
+class MultiGroup(OneGroup):
+    """Multigroup driver.  The reference class (group.py:160-240) is non-functional scaffolding;
+    this one runs the same device path as OneGroup with G = slab.num_groups, using the source
+    formulas of zone.py:38-51 (fission chi_g * sum nu_sigma_f phi, scatter sigma_s(g'->g))."""
+
+    def __init__(self, slab):
+        super().__init__(slab)
+        self.Q = np.zeros((slab.num_zones, slab.num_groups))
+        self.group = [self] * slab.num_groups
+
+    def return_energy_based_flux(self):
+        """group.py:183-189 (needs materials that carry group_edges)."""
+        phi = ZoneFlux(self.slab.num_zones)
+        for i in range(self.slab.num_zones):
+            edges = self.zone[i].material.group_edges
+            phi.thermal[i] = np.sum(self.phi.old[i, edges[:-1] <= 0.55e-6])
+            phi.fast[i] = np.sum(self.phi.old[i, edges[1:] >= 1])
+            phi.epithermal[i] = np.sum(self.phi.old[i, :]) - phi.thermal[i] - phi.fast[i]
+        return phi

@@ -1,0 +1,170 @@
+/*
+ * alpha_eigen_b200.h -- C ABI of the B200 (sm_100a) slab S_N hot path.
+ *
+ * The reference (SoftwareDevEngResearch/alpha-eigen) is pure Python and has no FFI of its
+ * own; its boundary is the method surface of OneGroup / TimeUnit.  Each entry point below
+ * replaces the body of one reference method and is what a ctypes binding inside that
+ * method would call (INTEGRATION.md shows the stubs).  Plain pointers and sizes only: no
+ * torch, no C++ types.  Every `double*` / `int32_t*` inside ae_slab / ae_work is a DEVICE
+ * pointer unless its comment says host.  All functions return an ae_status.
+ *
+ * Cell storage order ("lane-blocked tiles")
+ *   Per-cell arrays are stored in tiles of AE_TILE = 256 cells; inside a tile logical cell
+ *   r = lane*8 + j (lane 0..31, j 0..7) lives at offset (j/2)*64 + lane*2 + (j%2), so that a
+ *   warp whose lane owns 8 consecutive cells reads them with four perfectly coalesced 16-byte
+ *   loads.  Z is padded to Zp = ae_padded_cells(Z); padding cells carry zeros in every input.
+ *   ae_cell_offset() gives the map; the Python host applies it once at upload / download.
+ *   Array shapes below are written [slow]...[fast] with the cell index always fastest.
+ */
+#ifndef ALPHA_EIGEN_B200_H
+#define ALPHA_EIGEN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AE_ABI_VERSION 1
+#define AE_TILE 256          /* cells per tile */
+#define AE_LANE_CELLS 8      /* consecutive cells owned by one lane */
+
+typedef enum ae_status {
+    AE_OK = 0,
+    AE_NOT_CONVERGED = 1,    /* the reference raises AssertionError (group.py:72,102; time_unit.py:35,51) */
+    AE_BAD_ARG = 2,          /* includes |mu| <= 1e-10 (group.py:44) */
+    AE_CUDA_ERROR = 3,       /* CUDA / NCCL / cuSOLVER failure; see ae_last_error() */
+} ae_status;
+
+/* Device-side control block (one per solver instance; also mirrored in pinned host memory). */
+typedef struct ae_ctrl {
+    double change;           /* last ||phi-phi_old||/||phi|| of the inner (scatter) iteration */
+    double outer_change;     /* same for the outer (fission) loop of a time step */
+    double k_new, k_old;     /* power iteration (group.py:108,114) */
+    double k_change;         /* |k_new - k_old| before k_old is overwritten */
+    int32_t inner_done, inner_iters;
+    int32_t power_done, power_iters;
+    uint32_t ticket;         /* last-block election counter */
+    int32_t reserved;
+} ae_ctrl;
+
+/* Read-only problem description.  Built once per (slab, dt). */
+typedef struct ae_slab {
+    int64_t Z;               /* logical cells  (slab.py:8 num_zones) */
+    int64_t Zp;              /* padded cells, multiple of AE_TILE */
+    int32_t A;               /* angles held by THIS rank (slab.py:10), negatives first */
+    int32_t n_neg;           /* how many of them have mu < 0 */
+    int32_t G;               /* energy groups (slab.py:12) */
+    int32_t M;               /* materials */
+    const double *mu_ihx;    /* [A] mu/hx, signed (group.py:46,50) */
+    const double *wgt;       /* [A] quadrature weights (slab.py:11) */
+    const int32_t *mat;      /* [Zp] material index per cell (slab.py:41-56) */
+    const double *scat;      /* [M][G][G] sigma_s(g'->g) at [m][g'][g] (material.py:38, zone.py:50) */
+    const double *chi;       /* [M][G] (material.py:10) */
+    const double *nusf;      /* [M][G] (material.py:13-19) */
+    const double *hs;        /* [G][Zp] 0.5*sigT seen by the sweep (group.py:50; time_unit.py:24 adds 1/(v dt)) */
+    const double *cdt;       /* [G][Zp] inv_speed/dt (time_unit.py:23) or NULL in steady state */
+    const double *s_ext;     /* [G][Zp] fixed external source (group.source at time_unit.py:19) or NULL */
+} ae_slab;
+
+/* Mutable buffers, all caller-allocated (torch owns the memory). */
+typedef struct ae_work {
+    double *phi;             /* [G][Zp] current scalar-flux iterate (phi_old of group.py:80) */
+    double *phi_outer;       /* [G][Zp] power-iteration phi.old / time-step outer phi */
+    double *base;            /* [G][Zp] source that is fixed during the inner iteration */
+    double *q0, *q1;         /* [G][Zp] ping-pong isotropic sweep source */
+    double *partial;         /* [P][G][Zp] per-angle-block partial scalar flux */
+    double *norm_scratch;    /* [4 * ae_norm_blocks(Zp)] */
+    ae_ctrl *ctrl;           /* device */
+    ae_ctrl *ctrl_host;      /* pinned host */
+    void *comm;              /* ae_comm handle for the phi allreduce, or NULL (single GPU) */
+    int32_t P;               /* ae_partial_count(A, n_neg) */
+    int32_t batch;           /* source iterations launched between host polls (>=1) */
+} ae_work;
+
+/* ---- introspection ---------------------------------------------------------------- */
+int ae_abi_version(void);
+const char *ae_last_error(void);
+int64_t ae_padded_cells(int64_t Z);
+int64_t ae_cell_offset(int64_t z);              /* storage offset of logical cell z */
+int32_t ae_partial_count(int32_t A, int32_t n_neg);
+int64_t ae_norm_blocks(int64_t Zp);
+
+/* ---- sweep: replaces the loop of OneGroup.sweep1D calls (group.py:41-60, 74-77) ------ */
+/* One sweep set over all local angles x groups with isotropic source q [G][Zp].
+ *   psi_in  != NULL : time-dependent source q + cdt*psi_in (time_unit.py:23,53); [G][A][Zp]
+ *   psi_out != NULL : angle.psi_midpoint (group.py:59) is written; may alias psi_in
+ *   partial         : [P][G][Zp] receives sum_a w_a psi_a per angle block (group.py:77)
+ */
+int ae_sweep_set(const ae_slab *s, const double *q, const double *psi_in, double *psi_out,
+                 double *partial, void *stream);
+/* phi[G][Zp] = sum_p partial[p] in block order; padding cells are zeroed. */
+int ae_reduce_partials(const ae_slab *s, const double *partial, int32_t P, double *phi, void *stream);
+
+/* Scalar-flux assembly after a sweep set (group.py:77-80 + group.py:73 for the next iterate):
+ *   phi_new = sum_p partial[p] (padding zeroed); change = ||phi_new - w->phi|| / ||phi_new||;
+ *   w->phi = phi_new; q_next = w->base + 0.5 * sum_g' sigma_s(g'->g) phi_new(g').
+ * ctrl.change / inner_iters / inner_done are updated on the device (done when change < tol).
+ * The solver loops below are this call alternated with ae_sweep_set. */
+int ae_flux_update(const ae_slab *s, ae_work *w, const double *partial, int32_t P, double *q_next,
+                   double tol, int32_t iteration, void *stream);
+
+/* ---- layout conversion at the boundary (device to device) ------------------------------- */
+/* cells: logical [Z][G] (phi.new of group.py:18) <-> storage [G][Zp] */
+int ae_pack_cells(const double *logical, int64_t Z, int32_t G, double *storage, void *stream);
+int ae_unpack_cells(const double *storage, int64_t Z, int32_t G, double *logical, void *stream);
+/* psi: logical [Z][A_total][G] (TimeUnit.psi[..., step], time_unit.py:14) <-> storage [G][A][Zp];
+ * angle_index [A] (device) maps local angle a to the reference angle number. */
+int ae_pack_psi(const double *logical, int64_t Z, int32_t A_total, int32_t G, const int32_t *angle_index,
+                int32_t A, double *storage, void *stream);
+int ae_unpack_psi(const double *storage, int64_t Z, int32_t A_total, int32_t G, const int32_t *angle_index,
+                  int32_t A, double *logical, void *stream);
+
+/* ---- source iteration: OneGroup.source_iteration_for_scalar_flux (group.py:62-81) and
+ *      TimeUnit.time_dependent_source_iteration (time_unit.py:44-59) ------------------------ */
+/* w->base holds the fixed source; cold_start is 1e-12 (group.py:66) or 0 (time_unit.py:45).
+ * On return w->phi is the converged flux and *last_q_index says which of q0/q1 fed the last sweep. */
+int ae_source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, double cold_start,
+                        double tol, int32_t max_iterations, int32_t *iters, int32_t *last_q_index,
+                        void *stream);
+
+/* ---- power iteration: OneGroup.perform_power_iteration (group.py:97-116) --------------- */
+/* w->phi_outer is phi.old (in/out); w->phi returns phi.new.  k_hist (host, may be NULL) receives
+ * k.new per iteration so the caller can print the reference's banner (group.py:110-113). */
+int ae_power_iteration(const ae_slab *s, ae_work *w, double tol, int32_t max_iterations,
+                       double si_tol, int32_t si_max_iterations, double *psi_out,
+                       double *k_new, double *k_old, int32_t *iters, double *k_hist, int32_t *si_hist,
+                       void *stream);
+
+/* ---- time stepping: TimeUnit.calculate_one_step_flux (time_unit.py:29-42) and
+ *      calculate_time_dependent_flux (time_unit.py:17-27), with repairs R2-R5 ---- */
+/* One backward-Euler step: reads psi_prev [G][A][Zp], writes psi_next (may alias psi_prev). */
+int ae_time_step(const ae_slab *s, ae_work *w, const double *psi_prev, double *psi_next, double tol,
+                 int32_t *outer_iters, int32_t *inner_iters, void *stream);
+/* num_steps steps.  psi [G][A][Zp] is psi0 on entry and the last step's psi on exit (in place)
+ * unless psi_snap != NULL, in which case step n reads slot n-1 and writes slot n of
+ * psi_snap [num_steps][G][A][Zp] (slot 0 reads `psi`).  phi_snap [num_steps][G][Zp] may be NULL. */
+int ae_time_march(const ae_slab *s, ae_work *w, double *psi, double *psi_snap, double *phi_snap,
+                  int32_t num_steps, double tol, int32_t *outer_hist, int32_t *inner_hist, void *stream);
+
+/* ---- DMD: TimeUnit.compute_alpha_eigenvalues (time_unit.py:61-92) ---------------------- */
+/* gram[n][n] (device, row-major) = S S^T for snapshot rows S [n][ld] restricted to len columns. */
+int ae_gram(const double *snap, int64_t ld, int64_t len, int32_t n, double *gram, void *stream);
+/* Small dense part from the (allreduced) Gram matrix of snapshots first..first+K (K+1 rows):
+ * rank rule of time_unit.py:75-76 (keep sigma_j while 1 - cumsum/sum > rank_tol), Atilde,
+ * eigenvalues, alpha = (1-1/lambda)/dt (time_unit.py:91).  gram is a DEVICE pointer
+ * [K+1][K+1]; alpha_re / alpha_im / sigma are HOST arrays of length K (sigma may be NULL);
+ * *rank is the number of alpha values written. */
+int ae_dmd_from_gram(const double *gram, int32_t K, double dt, double rank_tol,
+                     double *alpha_re, double *alpha_im, double *sigma, int32_t *rank, void *stream);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink ---------------------------------- */
+int ae_comm_unique_id(void *id128);                                     /* host, 128 bytes */
+int ae_comm_init(void **comm, int32_t rank, int32_t nranks, const void *id128);
+int ae_comm_allreduce_sum(void *comm, double *buf, int64_t count, void *stream);
+int ae_comm_destroy(void *comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
