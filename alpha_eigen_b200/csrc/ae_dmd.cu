@@ -112,6 +112,116 @@ __global__ void atilde_kernel(const double *__restrict__ gram, int n /*K+1*/, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// R-only TSQR.  The Gram route squares the condition number: singular values below ~1e-8 sigma_1
+// drown in rounding, while the reference's rank rule (time_unit.py:75-76) looks 1e-13 deep.  A
+// Householder QR of the tall matrix T = S^T (len x n) is backward stable, and only its n x n
+// triangular factor is needed (Q is never formed).
+//
+// Each CTA keeps a working matrix W[(n + B)][ldw] in shared memory: rows 0..n-1 hold the running
+// R, rows n.. hold the next block of B rows of T.  One "append" runs n Householder steps; step k
+// only touches row k of R and the B block rows (the rest of column k is already zero).  Thread j
+// owns column j: the reflector entries are warp-uniform smem broadcasts, the column entries are
+// stride-1 across threads, ldw is odd so column walks are conflict-free.
+__global__ void __launch_bounds__(128) tsqr_kernel(const double *__restrict__ in, int64_t ld, int64_t len, int n,
+                                                   int row_major, int64_t rows_per_cta, int B, double *__restrict__ r_out)
+{
+    extern __shared__ double W[];
+    __shared__ double hh[4];                        // tau, 1/(alpha-beta), beta
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ldw = n | 1;
+    const int64_t m_begin = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t m_end = min(len, m_begin + rows_per_cta);
+    for (int i = tid; i < n * ldw; i += blockDim.x) W[i] = 0.0;
+    for (int64_t m0 = m_begin; m0 < m_end; m0 += B) {
+        __syncthreads();
+        // load block rows: T[m0+b][i]
+        if (row_major) {
+            for (int idx = tid; idx < B * n; idx += blockDim.x) {
+                const int b = idx / n, i = idx % n;
+                const int64_t m = m0 + b;
+                W[(n + b) * ldw + i] = m < m_end ? in[m * ld + i] : 0.0;
+            }
+        } else {
+            for (int idx = tid; idx < B * n; idx += blockDim.x) {
+                const int i = idx / B, b = idx % B;
+                const int64_t m = m0 + b;
+                W[(n + b) * ldw + i] = m < m_end ? in[(int64_t)i * ld + m] : 0.0;
+            }
+        }
+        __syncthreads();
+        for (int k = 0; k < n; ++k) {
+            if (warp == 0) {                        // dlarfg on x = (W[k][k], W[n..n+B)[k])
+                double ss = 0.0;
+                for (int b = lane; b < B; b += 32) { const double x = W[(n + b) * ldw + k]; ss = fma(x, x, ss); }
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                if (lane == 0) {
+                    const double alpha = W[k * ldw + k];
+                    if (ss == 0.0) {
+                        hh[0] = 0.0; hh[1] = 0.0; hh[2] = alpha;
+                    } else {
+                        const double beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
+                        hh[0] = (beta - alpha) / beta;
+                        hh[1] = 1.0 / (alpha - beta);
+                        hh[2] = beta;
+                    }
+                }
+            }
+            __syncthreads();
+            const double tau = hh[0], inv = hh[1];
+            const int j = tid;
+            if (j == k) W[k * ldw + k] = hh[2];
+            if (j > k && j < n && tau != 0.0) {
+                double dot = 0.0;
+                for (int b = 0; b < B; ++b) dot = fma(W[(n + b) * ldw + k], W[(n + b) * ldw + j], dot);
+                const double w = tau * fma(inv, dot, W[k * ldw + j]);
+                W[k * ldw + j] -= w;
+                const double wi = w * inv;
+                for (int b = 0; b < B; ++b) W[(n + b) * ldw + j] = fma(-wi, W[(n + b) * ldw + k], W[(n + b) * ldw + j]);
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    double *out = r_out + (size_t)blockIdx.x * n * n;
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+        const int i = idx / n, j = idx % n;
+        out[idx] = j >= i ? W[i * ldw + j] : 0.0;
+    }
+}
+
+// column-major copies for cuSOLVER: Ax = R[:, 0:K]  ((K+1) x K), Ry = R[:, 1:K+1]
+__global__ void split_r_kernel(const double *__restrict__ R, int n, double *__restrict__ Ax, double *__restrict__ Ry)
+{
+    const int K = n - 1;
+    for (int idx = threadIdx.x + blockIdx.x * blockDim.x; idx < n * K; idx += blockDim.x * gridDim.x) {
+        const int i = idx % n, j = idx / n;
+        Ax[idx] = R[i * n + j];
+        Ry[idx] = R[i * n + j + 1];
+    }
+}
+
+// Atilde = U_r^T Ry V_r S_r^-1  (time_unit.py:85-89), column-major r x r.  Single block.
+__global__ void atilde_from_svd_kernel(const double *__restrict__ U, int ldu, const double *__restrict__ VT, int ldvt,
+                                       const double *__restrict__ Ry, int n, const double *__restrict__ inv_sigma, int r,
+                                       double *__restrict__ T /* n x r */, double *__restrict__ At)
+{
+    const int K = n - 1;
+    for (int idx = threadIdx.x; idx < n * r; idx += blockDim.x) {       // T[i][b] = sum_j Ry[i][j] V[j][b] / s_b
+        const int i = idx % n, b = idx / n;
+        double s = 0.0;
+        for (int j = 0; j < K; ++j) s = fma(Ry[i + j * n], VT[b + j * ldvt], s);
+        T[idx] = s * inv_sigma[b];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < r * r; idx += blockDim.x) {       // At[a][b] = sum_i U[i][a] T[i][b]
+        const int a = idx % r, b = idx / r;
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s = fma(U[i + a * ldu], T[i + b * n], s);
+        At[idx] = s;
+    }
+}
+
 static int cusolver_fail(cusolverStatus_t st, const char *what)
 {
     set_error("%s failed with cusolver status %d", what, (int)st);
@@ -192,11 +302,16 @@ extern "C" int ae_dmd_from_gram(const double *gram_dev, int32_t K, double dt, do
     {
         // singular values of X, descending; rank rule of time_unit.py:75-76
         double total = 0.0, run = 0.0;
-        for (int j = 0; j < K; ++j) { sig[j] = sqrt(fmax(lam[K - 1 - j], 0.0)); total += sig[j]; }
-        for (int j = 0; j < K; ++j) {
+        // The Gram matrix carries ~K*eps*sigma_1^2 of rounding, i.e. its small eigenvalues are noise
+        // below sigma ~ 1e-7 sigma_1: such values are excluded before the reference's rule is applied.
+        for (int j = 0; j < K; ++j) sig[j] = sqrt(fmax(lam[K - 1 - j], 0.0));
+        int kept = 0;
+        for (int j = 0; j < K; ++j) { if (sig[j] > 1e-7 * sig[0]) { kept = j + 1; total += sig[j]; } else break; }
+        for (int j = 0; j < kept; ++j) {
             run += sig[j];
-            if (1.0 - run / total > rank_tol && sig[j] > 0.0) r = j + 1; else break;
+            if ((1.0 - run / total > rank_tol || j + 1 < kept) && sig[j] > 0.0) r = j + 1; else break;
         }
+        if (r == 0 && kept > 0) r = 1;
         if (r < 1) { set_error("ae_dmd_from_gram: no singular value survives the rank rule"); status = AE_BAD_ARG; goto done; }
         for (int j = 0; j < r; ++j) inv[j] = 1.0 / sig[j];
         if (sigma_out) memcpy(sigma_out, sig, sizeof(double) * K);
@@ -235,5 +350,132 @@ done:
     cudaFree(dV); cudaFree(dW); cudaFree(dwork); cudaFree(dT); cudaFree(dAt); cudaFree(dInv); cudaFree(dEig);
     cudaFree(dbuf); cudaFree(dinfo);
     free(hbuf); free(lam); free(sig); free(inv); free(W);
+    return status;
+}
+
+static int tsqr_block_rows(int n)
+{
+    const int ldw = n | 1;
+    int B = (int)((200 * 1024) / (sizeof(double) * ldw)) - n;
+    if (B > 96) B = 96;
+    return B;
+}
+
+extern "C" int ae_tsqr(const double *snap, int64_t ld, int64_t len, int32_t n, double *r_out, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!snap || !r_out || n < 1 || n > kGN || len < 1) { set_error("ae_tsqr: bad argument (n=%d)", n); return AE_BAD_ARG; }
+    const int B = tsqr_block_rows(n);
+    if (B < 8) { set_error("ae_tsqr: n=%d too large for shared memory", n); return AE_BAD_ARG; }
+    const int ldw = n | 1;
+    const size_t smem = (size_t)(n + B) * ldw * sizeof(double);
+    AE_CUDA(cudaFuncSetAttribute((const void *)tsqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ncta = 148;
+    int64_t rows = (len + ncta - 1) / ncta;
+    rows = (rows + B - 1) / B * B;
+    ncta = (int)((len + rows - 1) / rows);
+    double *parts = nullptr;
+    AE_CUDA(cudaMallocAsync((void **)&parts, (size_t)ncta * n * n * sizeof(double), st));
+    tsqr_kernel<<<ncta, 128, smem, st>>>(snap, ld, len, n, 0, rows, B, parts);
+    // second level: QR of the stacked triangles (ncta*n x n, row-major) in one CTA
+    tsqr_kernel<<<1, 128, smem, st>>>(parts, n, (int64_t)ncta * n, n, 1, (int64_t)ncta * n, B, r_out);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(parts, st);
+    AE_CUDA(e);
+    return AE_OK;
+}
+
+extern "C" int ae_tsqr_merge(const double *r_stack, int32_t count, int32_t n, double *r_out, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!r_stack || !r_out || count < 1 || n < 1 || n > kGN) { set_error("ae_tsqr_merge: bad argument"); return AE_BAD_ARG; }
+    const int B = tsqr_block_rows(n);
+    const int ldw = n | 1;
+    const size_t smem = (size_t)(n + B) * ldw * sizeof(double);
+    AE_CUDA(cudaFuncSetAttribute((const void *)tsqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tsqr_kernel<<<1, 128, smem, st>>>(r_stack, n, (int64_t)count * n, n, 1, (int64_t)count * n, B, r_out);
+    AE_CUDA(cudaGetLastError());
+    return AE_OK;
+}
+
+extern "C" int ae_dmd_from_r(const double *r_dev, int32_t K, double dt, double rank_tol, double *alpha_re,
+                             double *alpha_im, double *sigma_out, int32_t *rank, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!r_dev || K < 1 || K + 1 > kGN || !alpha_re || !alpha_im || !rank) { set_error("ae_dmd_from_r: bad argument"); return AE_BAD_ARG; }
+    int status = AE_OK;
+    const int n = K + 1;
+    cusolverDnHandle_t h = nullptr;
+    cusolverDnParams_t params = nullptr;
+    double *dAx = nullptr, *dRy = nullptr, *dS = nullptr, *dU = nullptr, *dVT = nullptr, *dwork = nullptr, *dT = nullptr,
+           *dAt = nullptr, *dInv = nullptr, *dEig = nullptr;
+    void *dbuf = nullptr, *hbuf = nullptr;
+    int *dinfo = nullptr;
+    int lwork = 0, info = 0, r = 0;
+    size_t dbytes = 0, hbytes = 0;
+    double *sig = (double *)malloc(sizeof(double) * K), *inv = (double *)malloc(sizeof(double) * K),
+           *W = (double *)malloc(sizeof(double) * 2 * K);
+
+    AE_CUSOLVER(cusolverDnCreate(&h));
+    AE_CUSOLVER(cusolverDnSetStream(h, st));
+    AE_CUDA_G(cudaMalloc((void **)&dAx, sizeof(double) * n * K));
+    AE_CUDA_G(cudaMalloc((void **)&dRy, sizeof(double) * n * K));
+    AE_CUDA_G(cudaMalloc((void **)&dS, sizeof(double) * K));
+    AE_CUDA_G(cudaMalloc((void **)&dU, sizeof(double) * n * K));
+    AE_CUDA_G(cudaMalloc((void **)&dVT, sizeof(double) * K * K));
+    AE_CUDA_G(cudaMalloc((void **)&dinfo, sizeof(int)));
+    split_r_kernel<<<32, 256, 0, st>>>(r_dev, n, dAx, dRy);
+    AE_CUDA_G(cudaGetLastError());
+    // thin SVD of the (K+1) x K triangular factor: same singular values and V as X (time_unit.py:72)
+    AE_CUSOLVER(cusolverDnDgesvd_bufferSize(h, n, K, &lwork));
+    AE_CUDA_G(cudaMalloc((void **)&dwork, sizeof(double) * (size_t)lwork));
+    AE_CUSOLVER(cusolverDnDgesvd(h, 'S', 'S', n, K, dAx, n, dS, dU, n, dVT, K, dwork, lwork, nullptr, dinfo));
+    AE_CUDA_G(cudaMemcpyAsync(sig, dS, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
+    AE_CUDA_G(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AE_CUDA_G(cudaStreamSynchronize(st));
+    if (info != 0) { set_error("gesvd info=%d", info); status = AE_CUDA_ERROR; goto done; }
+    {
+        double total = 0.0, run = 0.0;                  // rank rule, time_unit.py:75-76
+        for (int j = 0; j < K; ++j) total += sig[j];
+        for (int j = 0; j < K; ++j) {
+            run += sig[j];
+            if (1.0 - run / total > rank_tol && sig[j] > 0.0) r = j + 1; else break;
+        }
+        if (r < 1) { set_error("ae_dmd_from_r: no singular value survives the rank rule"); status = AE_BAD_ARG; goto done; }
+        for (int j = 0; j < r; ++j) inv[j] = 1.0 / sig[j];
+        if (sigma_out) memcpy(sigma_out, sig, sizeof(double) * K);
+    }
+    AE_CUDA_G(cudaMalloc((void **)&dT, sizeof(double) * n * r));
+    AE_CUDA_G(cudaMalloc((void **)&dAt, sizeof(double) * r * r));
+    AE_CUDA_G(cudaMalloc((void **)&dInv, sizeof(double) * r));
+    AE_CUDA_G(cudaMalloc((void **)&dEig, sizeof(double) * 2 * r));
+    AE_CUDA_G(cudaMemcpyAsync(dInv, inv, sizeof(double) * r, cudaMemcpyHostToDevice, st));
+    atilde_from_svd_kernel<<<1, 1024, 0, st>>>(dU, n, dVT, K, dRy, n, dInv, r, dT, dAt);
+    AE_CUDA_G(cudaGetLastError());
+    AE_CUSOLVER(cusolverDnCreateParams(&params));
+    AE_CUSOLVER(cusolverDnXgeev_bufferSize(h, params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, r, CUDA_R_64F,
+                                           dAt, r, CUDA_C_64F, dEig, CUDA_R_64F, nullptr, 1, CUDA_R_64F, nullptr, 1,
+                                           CUDA_R_64F, &dbytes, &hbytes));
+    AE_CUDA_G(cudaMalloc(&dbuf, dbytes ? dbytes : 8));
+    hbuf = malloc(hbytes ? hbytes : 8);
+    AE_CUSOLVER(cusolverDnXgeev(h, params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, r, CUDA_R_64F, dAt, r,
+                                CUDA_C_64F, dEig, CUDA_R_64F, nullptr, 1, CUDA_R_64F, nullptr, 1, CUDA_R_64F, dbuf,
+                                dbytes, hbuf, hbytes, dinfo));
+    AE_CUDA_G(cudaMemcpyAsync(W, dEig, sizeof(double) * 2 * r, cudaMemcpyDeviceToHost, st));
+    AE_CUDA_G(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AE_CUDA_G(cudaStreamSynchronize(st));
+    if (info != 0) { set_error("geev info=%d", info); status = AE_CUDA_ERROR; goto done; }
+    for (int j = 0; j < r; ++j) {                       // alpha = (1 - 1/lambda)/dt  (time_unit.py:91)
+        const double re = W[2 * j], im = W[2 * j + 1], d = re * re + im * im;
+        alpha_re[j] = (1.0 - re / d) / dt;
+        alpha_im[j] = (im / d) / dt;
+    }
+    *rank = r;
+done:
+    if (params) cusolverDnDestroyParams(params);
+    if (h) cusolverDnDestroy(h);
+    cudaFree(dAx); cudaFree(dRy); cudaFree(dS); cudaFree(dU); cudaFree(dVT); cudaFree(dwork); cudaFree(dT);
+    cudaFree(dAt); cudaFree(dInv); cudaFree(dEig); cudaFree(dbuf); cudaFree(dinfo);
+    free(hbuf); free(sig); free(inv); free(W);
     return status;
 }

@@ -98,7 +98,8 @@ extern "C" int ae_source_iteration(const ae_slab *s, ae_work *w, const double *p
 // group.py:97-116
 extern "C" int ae_power_iteration(const ae_slab *s, ae_work *w, double tol, int32_t max_iterations, double si_tol,
                                   int32_t si_max_iterations, double *psi_out, double *k_new, double *k_old,
-                                  int32_t *iters, double *k_hist, int32_t *si_hist, void *stream)
+                                  int32_t *iters, double *k_hist, int32_t *si_hist, int32_t *last_q_index,
+                                  void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     AE_TRY(check_work(s, w, "ae_power_iteration"));
@@ -131,6 +132,7 @@ extern "C" int ae_power_iteration(const ae_slab *s, ae_work *w, double tol, int3
     if (k_new) *k_new = kn;
     if (k_old) *k_old = ko;
     if (iters) *iters = iteration;
+    if (last_q_index) *last_q_index = last_q;
     return status;
 }
 

@@ -61,26 +61,32 @@ struct FinArgs {
     int P, G, M;
     int init;                   // 1: phi := cold (no norm), 0: phi := sum of partials
     int gate;
-    int tab_in_smem;
     int iteration;
     double cold, tol;
 };
 
-// One thread per cell.  smem: tile[G][kCB] (this cell's new flux for every group) + optional tables.
-__global__ void __launch_bounds__(kCB) finalize_kernel(const FinArgs p)
+__device__ __forceinline__ void publish_change(const FinArgs &p, double num, double den, double *red)
 {
-    extern __shared__ double sm[];
+    const int iteration = p.iteration;
+    const double tol = p.tol;
+    ae_ctrl *ctrl = p.ctrl;
+    grid_sum2(num, den, p.scratch, ctrl, red, [=](double a, double b) {
+        const double change = sqrt(a) / sqrt(b);        // group.py:78
+        ctrl->change = change;
+        ctrl->inner_iters = iteration;
+        if (change < tol) ctrl->inner_done = 1;         // group.py:79
+    });
+}
+
+constexpr int kGSmall = 8;      // up to this many groups one thread owns a whole cell
+
+// G <= kGSmall: one thread per cell does everything (flux assembly, norm, scatter source).
+// This is the latency-critical path of the one-group Kornreich-Parsons problems.
+__global__ void __launch_bounds__(kCB) finalize_small_kernel(const FinArgs p)
+{
     __shared__ double red[64];
     if (p.gate && p.ctrl->inner_done) return;
     const int tid = threadIdx.x;
-    double *tile = sm;                                   // [G][kCB]
-    const double *tab = p.scat;
-    if (p.tab_in_smem) {
-        double *st = sm + (size_t)p.G * kCB;
-        const int n = p.M * p.G * p.G;
-        for (int i = tid; i < n; i += kCB) st[i] = p.scat[i];
-        tab = st;
-    }
     if (p.init && blockIdx.x == 0 && tid == 0) {
         p.ctrl->inner_done = 0;
         p.ctrl->inner_iters = 0;
@@ -91,46 +97,121 @@ __global__ void __launch_bounds__(kCB) finalize_kernel(const FinArgs p)
     const int64_t n = (int64_t)p.G * p.Zp;
     double num = 0.0, den = 0.0;
     if (s < p.Zp) {
-        for (int g = 0; g < p.G; ++g) {
-            const int64_t i = (int64_t)g * p.Zp + s;
-            double v;
-            if (p.init) {
-                v = p.cold;
-            } else {
-                v = p.partial[i];
-                for (int pp = 1; pp < p.P; ++pp) v += p.partial[(int64_t)pp * n + i];
+        double v[kGSmall];
+#pragma unroll
+        for (int g = 0; g < kGSmall; ++g) {
+            v[g] = 0.0;
+            if (g < p.G) {
+                const int64_t i = (int64_t)g * p.Zp + s;
+                double x;
+                if (p.init) {
+                    x = p.cold;
+                } else {
+                    x = p.partial[i];
+                    for (int pp = 1; pp < p.P; ++pp) x += p.partial[(int64_t)pp * n + i];
+                }
+                if (!valid) x = 0.0;
+                if (!p.init) {
+                    const double d = x - p.phi[i];      // group.py:78
+                    num = fma(d, d, num);
+                    den = fma(x, x, den);
+                }
+                p.phi[i] = x;                           // group.py:80 phi_old = phi.copy()
+                v[g] = x;
             }
-            if (!valid) v = 0.0;
-            if (!p.init) {
-                const double d = v - p.phi[i];          // group.py:78
-                num = fma(d, d, num);
-                den = fma(v, v, den);
+        }
+        const double *sc = p.scat + (size_t)p.mat[s] * p.G * p.G;
+#pragma unroll
+        for (int g = 0; g < kGSmall; ++g) {
+            if (g < p.G) {
+                double acc = 0.0;
+#pragma unroll
+                for (int gp = 0; gp < kGSmall; ++gp)
+                    if (gp < p.G) acc = fma(v[gp], __ldg(sc + gp * p.G + g), acc);
+                const int64_t i = (int64_t)g * p.Zp + s;
+                p.q_next[i] = p.base[i] + 0.5 * acc;    // group.py:73 / time_unit.py:53
             }
-            p.phi[i] = v;                               // group.py:80 phi_old = phi.copy()
-            tile[g * kCB + tid] = v;
         }
     }
-    __syncthreads();
-    if (s < p.Zp) {
-        const double *sc = tab + (size_t)p.mat[s] * p.G * p.G;
-        for (int g = 0; g < p.G; ++g) {
-            double acc = 0.0;
-            for (int gp = 0; gp < p.G; ++gp) acc = fma(tile[gp * kCB + tid], sc[gp * p.G + g], acc);
-            const int64_t i = (int64_t)g * p.Zp + s;
-            p.q_next[i] = p.base[i] + 0.5 * acc;        // group.py:73 / time_unit.py:53
+    if (!p.init) publish_change(p, num, den, red);
+}
+
+// G > kGSmall, step 1: phi := sum of partials (or cold), norm.  Elementwise over [G][Zp], 2 doubles/thread.
+__global__ void __launch_bounds__(256) flux_assemble_kernel(const FinArgs p)
+{
+    __shared__ double red[64];
+    if (p.gate && p.ctrl->inner_done) return;
+    if (p.init && blockIdx.x == 0 && threadIdx.x == 0) {
+        p.ctrl->inner_done = 0;
+        p.ctrl->inner_iters = 0;
+        p.ctrl->ticket = 0;
+    }
+    const int64_t n = (int64_t)p.G * p.Zp, n2 = n / 2;       // Zp is even
+    double num = 0.0, den = 0.0;
+    for (int64_t i2 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i2 < n2; i2 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = 2 * i2;
+        double2 x;
+        if (p.init) {
+            x = make_double2(p.cold, p.cold);
+        } else {
+            x = *reinterpret_cast<const double2 *>(p.partial + i);
+            for (int pp = 1; pp < p.P; ++pp) {
+                const double2 y = *reinterpret_cast<const double2 *>(p.partial + (int64_t)pp * n + i);
+                x.x += y.x; x.y += y.y;
+            }
+        }
+        const int64_t sidx = i % p.Zp;                       // both halves are cells lane*8+2k, +1 of one lane
+        const int64_t z = logical_cell(sidx);
+        if (z >= p.Z) x.x = 0.0;
+        if (z + 1 >= p.Z) x.y = 0.0;
+        if (!p.init) {
+            const double2 o = *reinterpret_cast<const double2 *>(p.phi + i);
+            const double dx = x.x - o.x, dy = x.y - o.y;     // group.py:78
+            num = fma(dx, dx, fma(dy, dy, num));
+            den = fma(x.x, x.x, fma(x.y, x.y, den));
+        }
+        *reinterpret_cast<double2 *>(p.phi + i) = x;         // group.py:80
+    }
+    if (!p.init) publish_change(p, num, den, red);
+}
+
+// G > kGSmall, step 2: q_next[g][s] = base[g][s] + 0.5 * sum_g' phi[g'][s] * sigma_s[m(s)][g'][g].
+// Thread (x = cell, y = block of kGB output groups).  The phi column of a cell is shared by the
+// threadIdx.y threads of the CTA through L1; the scatter rows are warp-uniform L1 hits whenever
+// the 32 cells of a warp share a material (always, except at the 4 region interfaces).
+constexpr int kGB = 8;
+__global__ void __launch_bounds__(256) scatter_source_kernel(const FinArgs p)
+{
+    if (p.gate && p.ctrl->inner_done) return;
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int g0 = (blockIdx.y * blockDim.y + threadIdx.y) * kGB;
+    if (s >= p.Zp || g0 >= p.G) return;
+    const double *sc = p.scat + (size_t)p.mat[s] * p.G * p.G + g0;
+    const int ng = min(kGB, p.G - g0);
+    double acc[kGB];
+#pragma unroll
+    for (int j = 0; j < kGB; ++j) acc[j] = 0.0;
+    if (ng == kGB) {
+#pragma unroll 2
+        for (int gp = 0; gp < p.G; ++gp) {
+            const double x = p.phi[(int64_t)gp * p.Zp + s];
+#pragma unroll
+            for (int j = 0; j < kGB; ++j) acc[j] = fma(x, __ldg(sc + gp * p.G + j), acc[j]);
+        }
+    } else {
+        for (int gp = 0; gp < p.G; ++gp) {
+            const double x = p.phi[(int64_t)gp * p.Zp + s];
+#pragma unroll
+            for (int j = 0; j < kGB; ++j)
+                if (j < ng) acc[j] = fma(x, __ldg(sc + gp * p.G + j), acc[j]);
         }
     }
-    if (!p.init) {
-        const int iteration = p.iteration;
-        const double tol = p.tol;
-        ae_ctrl *ctrl = p.ctrl;
-        grid_sum2(num, den, p.scratch, ctrl, red, [=](double a, double b) {
-            const double change = sqrt(a) / sqrt(b);    // group.py:78
-            ctrl->change = change;
-            ctrl->inner_iters = iteration;
-            if (change < tol) ctrl->inner_done = 1;     // group.py:79
-        });
-    }
+#pragma unroll
+    for (int j = 0; j < kGB; ++j)
+        if (j < ng) {
+            const int64_t i = (int64_t)(g0 + j) * p.Zp + s;
+            p.q_next[i] = p.base[i] + 0.5 * acc[j];          // group.py:73 / time_unit.py:53
+        }
 }
 
 // base[g][s] = s_ext[g][s] + 0.5*chi[m][g] * sum_g' nusf[m][g'] * phi[g'][s]
@@ -219,12 +300,6 @@ __global__ void ctrl_init_kernel(ae_ctrl *ctrl)
 
 static int per_cell_blocks(int64_t Zp) { return (int)((Zp + kCB - 1) / kCB); }
 
-static int smem_optin(const void *fn, size_t bytes)
-{
-    if (bytes > 48 * 1024) AE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return AE_OK;
-}
-
 int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, double *q_next, int init,
                     double cold, double tol, int iteration, int gate, cudaStream_t st)
 {
@@ -232,13 +307,22 @@ int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, 
     p.partial = partial; p.base = w->base; p.mat = s->mat; p.scat = s->scat; p.phi = w->phi; p.q_next = q_next;
     p.scratch = w->norm_scratch; p.ctrl = w->ctrl; p.Z = s->Z; p.Zp = s->Zp; p.P = P; p.G = s->G; p.M = s->M;
     p.init = init; p.gate = gate; p.iteration = iteration; p.cold = cold; p.tol = tol;
-    const size_t tile_bytes = (size_t)s->G * kCB * sizeof(double);
-    const size_t tab_bytes = (size_t)s->M * s->G * s->G * sizeof(double);
-    p.tab_in_smem = (tile_bytes + tab_bytes <= 200 * 1024) ? 1 : 0;
-    const size_t smem = tile_bytes + (p.tab_in_smem ? tab_bytes : 0);
-    if (smem > 227 * 1024) { set_error("finalize: G=%d needs %zu B of shared memory", s->G, smem); return AE_BAD_ARG; }
-    AE_TRY(smem_optin((const void *)finalize_kernel, smem));
-    finalize_kernel<<<per_cell_blocks(s->Zp), kCB, smem, st>>>(p);
+    if (s->G <= kGSmall) {
+        finalize_small_kernel<<<per_cell_blocks(s->Zp), kCB, 0, st>>>(p);
+        AE_CUDA(cudaGetLastError());
+        return AE_OK;
+    }
+    const int64_t n2 = (int64_t)s->G * s->Zp / 2;
+    int blocks = (int)((n2 + 255) / 256);
+    const int cap = per_cell_blocks(s->Zp) * 2;          // norm_scratch holds 4 doubles per per-cell block
+    if (blocks > cap) blocks = cap;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    flux_assemble_kernel<<<blocks, 256, 0, st>>>(p);
+    AE_CUDA(cudaGetLastError());
+    const int gblocks = (s->G + kGB - 1) / kGB;
+    const int by = gblocks < 8 ? gblocks : 8;            // 32 cells x by group-blocks per CTA
+    dim3 block(32, by), grid((unsigned)((s->Zp + 31) / 32), (gblocks + by - 1) / by);
+    scatter_source_kernel<<<grid, block, 0, st>>>(p);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }

@@ -243,9 +243,12 @@ class SlabDevice:
         k_new, k_old, it = C.c_double(0), C.c_double(0), C.c_int32(0)
         k_hist = (C.c_double * max_iterations)()
         si_hist = (C.c_int32 * max_iterations)()
+        lq = C.c_int32(0)
         st = self.lib.ae_power_iteration(C.byref(self.slab), C.byref(self.work), tol, max_iterations, si_tol,
                                          si_max_iterations, psi_out.data_ptr() if psi_out is not None else None,
-                                         C.byref(k_new), C.byref(k_old), C.byref(it), k_hist, si_hist, self.stream)
+                                         C.byref(k_new), C.byref(k_old), C.byref(it), k_hist, si_hist, C.byref(lq),
+                                         self.stream)
+        self.last_q_index = lq.value
         n = it.value
         return dict(status=st, k_new=k_new.value, k_old=k_old.value, iterations=n,
                     phi_new=self.cells_to_host(self.phi), phi_old=self.cells_to_host(self.phi_outer),
@@ -277,6 +280,27 @@ class SlabDevice:
         if self.comm is not None:
             self.comm.allreduce_(g)
         return g
+
+    def tsqr(self, snap, row_len, first, count):
+        """Triangular factor R [count][count] of the snapshot window (Householder TSQR, Q never formed).
+        Row-sharded ranks exchange their factors (allreduce of a zero-padded stack) and merge them."""
+        torch = self.torch
+        r = torch.empty(count * count, dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.ae_tsqr(snap.data_ptr() + 8 * first * row_len, row_len, row_len, count, r.data_ptr(),
+                                    self.stream))
+        if self.comm is not None:
+            stack = torch.zeros(self.comm.world * count * count, dtype=torch.float64, device=self.dev)
+            stack[self.comm.rank * count * count:(self.comm.rank + 1) * count * count] = r
+            self.comm.allreduce_(stack)
+            _lib.check(self.lib.ae_tsqr_merge(stack.data_ptr(), self.comm.world, count, r.data_ptr(), self.stream))
+        return r
+
+    def dmd_from_r(self, r, K, dt, rank_tol=1e-13):
+        are, aim, sig = (C.c_double * K)(), (C.c_double * K)(), (C.c_double * K)()
+        rk = C.c_int32(0)
+        _lib.check(self.lib.ae_dmd_from_r(r.data_ptr(), K, dt, rank_tol, are, aim, sig, C.byref(rk), self.stream))
+        n = rk.value
+        return np.array(are[:n]) + 1j * np.array(aim[:n]), np.array(sig[:]), n
 
     def dmd_from_gram(self, gram, K, dt, rank_tol=1e-13):
         are, aim, sig = (C.c_double * K)(), (C.c_double * K)(), (C.c_double * K)()

@@ -130,11 +130,13 @@ int ae_source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, doub
 
 /* ---- power iteration: OneGroup.perform_power_iteration (group.py:97-116) --------------- */
 /* w->phi_outer is phi.old (in/out); w->phi returns phi.new.  k_hist (host, may be NULL) receives
- * k.new per iteration so the caller can print the reference's banner (group.py:110-113). */
+ * k.new per iteration so the caller can print the reference's banner (group.py:110-113).
+ * psi_out (device, may be NULL) receives angle.psi_midpoint of the last sweep; *last_q_index
+ * says which of q0/q1 fed that sweep so it can also be replayed later with ae_sweep_set. */
 int ae_power_iteration(const ae_slab *s, ae_work *w, double tol, int32_t max_iterations,
                        double si_tol, int32_t si_max_iterations, double *psi_out,
                        double *k_new, double *k_old, int32_t *iters, double *k_hist, int32_t *si_hist,
-                       void *stream);
+                       int32_t *last_q_index, void *stream);
 
 /* ---- time stepping: TimeUnit.calculate_one_step_flux (time_unit.py:29-42) and
  *      calculate_time_dependent_flux (time_unit.py:17-27), with repairs R2-R5 ---- */
@@ -157,6 +159,19 @@ int ae_gram(const double *snap, int64_t ld, int64_t len, int32_t n, double *gram
  * *rank is the number of alpha values written. */
 int ae_dmd_from_gram(const double *gram, int32_t K, double dt, double rank_tol,
                      double *alpha_re, double *alpha_im, double *sigma, int32_t *rank, void *stream);
+
+/* R-only TSQR of the snapshot window: r[n][n] (device, row-major, upper triangular) with
+ * S^T = Q r for the tall matrix S^T (len x n); Q is never formed.  Householder, backward stable:
+ * resolves the singular values the reference's rank rule looks at (down to 1e-13 of the sum),
+ * which the Gram route cannot (it squares the condition number). */
+int ae_tsqr(const double *snap, int64_t ld, int64_t len, int32_t n, double *r, void *stream);
+/* QR of `count` stacked n x n triangles (device, row-major): the cross-rank step after an
+ * allgather of the per-rank factors of a row-sharded snapshot matrix. */
+int ae_tsqr_merge(const double *r_stack, int32_t count, int32_t n, double *r, void *stream);
+/* As ae_dmd_from_gram, from the triangular factor r [K+1][K+1] (device): thin SVD of r[:, 0:K]
+ * (cuSOLVER gesvd) gives sigma and V of X; Atilde = U_r^T r[:, 1:K+1] V S^-1. */
+int ae_dmd_from_r(const double *r, int32_t K, double dt, double rank_tol,
+                  double *alpha_re, double *alpha_im, double *sigma, int32_t *rank, void *stream);
 
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink ---------------------------------- */
 int ae_comm_unique_id(void *id128);                                     /* host, 128 bytes */
