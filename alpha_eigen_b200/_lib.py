@@ -33,7 +33,7 @@ class AeSlab(C.Structure):
 class AeWork(C.Structure):
     _fields_ = [("phi", C.c_void_p), ("phi_outer", C.c_void_p), ("base", C.c_void_p), ("q0", C.c_void_p),
                 ("q1", C.c_void_p), ("partial", C.c_void_p), ("norm_scratch", C.c_void_p), ("ctrl", C.c_void_p),
-                ("ctrl_host", C.c_void_p), ("comm", C.c_void_p), ("P", C.c_int32), ("batch", C.c_int32)]
+                ("ctrl_host", C.c_void_p), ("sweep_sync", C.c_void_p), ("comm", C.c_void_p), ("P", C.c_int32), ("batch", C.c_int32)]
 
 
 # every symbol include/alpha_eigen_b200.h declares: (restype, argtypes)
@@ -45,7 +45,8 @@ SYMBOLS = {
     "ae_cell_offset": (C.c_int64, [C.c_int64]),
     "ae_partial_count": (C.c_int32, [C.c_int32, C.c_int32]),
     "ae_norm_blocks": (C.c_int64, [C.c_int64]),
-    "ae_sweep_set": (C.c_int, [C.POINTER(AeSlab), _P, _P, _P, _P, _P]),
+    "ae_sweep_set": (C.c_int, [C.POINTER(AeSlab), _P, _P, _P, _P, _P, _P]),
+    "ae_sweep_sync_bytes": (C.c_int64, []),
     "ae_reduce_partials": (C.c_int, [C.POINTER(AeSlab), _P, C.c_int32, _P, _P]),
     "ae_flux_update": (C.c_int, [C.POINTER(AeSlab), C.POINTER(AeWork), _P, C.c_int32, _P, C.c_double, C.c_int32, _P]),
     "ae_pack_cells": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),

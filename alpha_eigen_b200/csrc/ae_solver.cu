@@ -9,7 +9,7 @@
 
 namespace ae {
 int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double *psi_out, double *partial,
-                 const ae_ctrl *ctrl, int gate, cudaStream_t st);
+                 void *sync, const ae_ctrl *ctrl, int gate, cudaStream_t st);
 int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, double *q_next, int init,
                     double cold, double tol, int iteration, int gate, cudaStream_t st);
 int launch_fission_base(const ae_slab *s, const double *phi, double *base, cudaStream_t st);
@@ -27,7 +27,7 @@ static int poll_ctrl(ae_work *w, cudaStream_t st)
 static int check_work(const ae_slab *s, const ae_work *w, const char *who)
 {
     if (!s || !w || !w->phi || !w->phi_outer || !w->base || !w->q0 || !w->q1 || !w->partial || !w->norm_scratch ||
-        !w->ctrl || !w->ctrl_host || w->P != ae_partial_count(s->A, s->n_neg)) {
+        !w->ctrl || !w->ctrl_host || !w->sweep_sync || w->P != ae_partial_count(s->A, s->n_neg)) {
         set_error("%s: incomplete ae_work / ae_slab", who);
         return AE_BAD_ARG;
     }
@@ -55,7 +55,7 @@ static int source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, 
         for (int b = 0; b < nb; ++b) {
             const int i = it + b;                       // 0-based; reference iteration number is i+1
             const int gate = b > 0;                     // first of a batch always runs
-            AE_TRY(launch_sweep(s, q[i & 1], psi_in, nullptr, w->partial, w->ctrl, gate, st));
+            AE_TRY(launch_sweep(s, q[i & 1], psi_in, nullptr, w->partial, w->sweep_sync, w->ctrl, gate, st));
             if (w->comm) {
                 // angle-sharded ranks: local partial sum -> NCCL sum over ranks -> same finalize on every rank
                 AE_TRY(ae_reduce_partials(s, w->partial, w->P, w->partial, st));
@@ -126,7 +126,7 @@ extern "C" int ae_power_iteration(const ae_slab *s, ae_work *w, double tol, int3
     if (status == AE_OK && psi_out) {
         // angle.psi_midpoint of the last sweep executed (group.py:59): replay it with the same source
         const double *q = last_q ? w->q1 : w->q0;
-        AE_TRY(launch_sweep(s, q, nullptr, psi_out, w->partial, w->ctrl, 0, st));
+        AE_TRY(launch_sweep(s, q, nullptr, psi_out, w->partial, w->sweep_sync, w->ctrl, 0, st));
         AE_CUDA(cudaStreamSynchronize(st));
     }
     if (k_new) *k_new = kn;
@@ -163,7 +163,7 @@ extern "C" int ae_time_step(const ae_slab *s, ae_work *w, const double *psi_prev
     if (status != AE_OK) return status;
     // commit: replay the last sweep with its own source, now writing psi (time_unit.py:26-27)
     const double *q = last_q ? w->q1 : w->q0;
-    AE_TRY(launch_sweep(s, q, psi_prev, psi_next, w->partial, w->ctrl, 0, st));
+    AE_TRY(launch_sweep(s, q, psi_prev, psi_next, w->partial, w->sweep_sync, w->ctrl, 0, st));
     return AE_OK;
 }
 

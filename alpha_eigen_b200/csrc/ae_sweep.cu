@@ -3,183 +3,348 @@
 // Replaces the per-cell Python loop of OneGroup.sweep1D (reference group.py:41-60) and the
 // angle loop + quadrature accumulate around it (group.py:74-77, time_unit.py:52-55).
 //
-// One cell update  psi_out = (q + (m - s/2) psi_in) / (m + s/2),  m = |mu|/hx,  s = sigT
-// is the affine map psi_out = a psi_in + b with a = (m - s/2)/(m + s/2) = 2m/(m + s/2) - 1 and
-// b = q/(m + s/2).  Maps compose associatively, (a2,b2)o(a1,b1) = (a2 a1, a2 b1 + b2), so a
-// row (one angle of one group) is solved by: each lane folds its 8 consecutive cells serially
-// (the reference's operation order inside a lane), a 5-step warp-shuffle scan composes the 32
-// lane maps, and a single running carry links consecutive 256-cell tiles.  One warp owns one
-// (group, angle) row for the whole slab, so there is no inter-CTA dependency; the warps of a
-// CTA are angles of the same group and direction and share hs/q/cdt loads through L1, and
-// their weighted midpoint fluxes are summed through shared memory once per tile into a
-// per-angle-block partial scalar flux (deterministic order).
+// Arithmetic.  One cell update  psi_out = (q + (m - s/2) psi_in) / (m + s/2),  m = |mu|/hx,
+// s = sigT, is the affine map psi_out = a psi_in + b with a = 2m/(m + s/2) - 1 and
+// b = q/(m + s/2).  Maps compose associatively, (a2,b2)o(a1,b1) = (a2 a1, a2 b1 + b2), so a row
+// (one angle of one group) is solved by: each lane folds its 8 consecutive cells serially (the
+// reference's order inside a lane), a 5-step warp-shuffle scan composes the 32 lane maps, and a
+// running carry links consecutive 256-cell tiles.
 //
-// Memory: cells are stored in the lane-blocked tile order of alpha_eigen_b200.h, so every
-// global access below is a fully coalesced 16-byte-per-lane vector access.
-// Algorithmic bytes per cell-angle-group update: 8 (psi read) + 8 (psi write) + 24/A
-// (hs, q, cdt amortised over the angles) + 8/AC (partial write).
+// Mapping.  A "row block" is up to 8 angles of one group and one direction; its 8 rows are the
+// 8 warps of a CTA, which therefore share the per-(cell, group) inputs hs, q, cdt and sum their
+// weighted midpoint fluxes through shared memory once per tile (deterministic order) into a
+// per-angle-block partial scalar flux.  The (row block, tile) pairs of the whole sweep set form
+// one sequence that is cut into equal contiguous ranges, one per persistent CTA (grid = resident
+// CTAs), so every SM gets the same number of tiles whatever A, G and the rank count are.  A range
+// that starts / ends inside a row block hands the running carries to its neighbour through a
+// small global mailbox; the piece that PRODUCES a hand-off is processed first and the piece that
+// CONSUMES one last, so the wait is satisfied long before it is reached whenever a CTA owns at
+// least one row block's worth of tiles.
+//
+// Memory.  Cells are stored in the lane-blocked tile order of alpha_eigen_b200.h, so a tile of
+// any row is one contiguous, 2 KB, 16-byte aligned run.  Tiles are staged by the TMA engine
+// (cp.async.bulk + mbarrier complete_tx) into a 3-stage shared-memory ring: one elected thread
+// issues (3 + 8) bulk copies per tile (hs, q, cdt once per CTA, psi per warp), three tiles
+// ahead of the math, so loads never sit on a warp's scoreboard.  psi is written back with
+// 16-byte streaming stores (in place is safe: a tile is read before it is written and
+// prefetches only run ahead).  Algorithmic bytes per cell-angle-group update:
+//   8 (psi read) + 8 (psi write) + 24/A (hs, q, cdt over the angles) + 8/8 (partial write).
 #include "ae_common.cuh"
 
 namespace ae {
 
+constexpr int kAC = 8;                  // warps (angles) per CTA
+constexpr int kStages = 3;              // TMA ring depth
+constexpr int kTileBytes = kTile * 8;   // 2 KB
+constexpr int kMaxCtas = 148 * 4;
+
+struct SweepSync {                      // global mailbox, zero-initialised once by the caller
+    unsigned ticket, done, epoch, pad;
+    unsigned flag[kMaxCtas][kAC];
+    double carry[kMaxCtas][kAC];
+};
+
 struct SweepArgs {
     const double *hs, *cdt, *q, *mu_ihx, *wgt, *psi_in;
     double *psi_out, *partial;
+    SweepSync *sync;
     int64_t Z, Zp;
-    int A, n_neg, G, nb_neg;
+    int64_t total_tiles;                // G * NBg * nt
+    int A, n_neg, G, nb_neg, nbg;       // nbg = angle blocks per group
 };
 
-// 1/d to ~1 ulp: MUFU.RCP64H seed (about 20 bits) + one cubic and one quadratic Newton step.
+// ---- PTX helpers: mbarrier + 1-D bulk async copy (TMA engine) -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void st_stream(double *p, double2 v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// 1/d to ~1 ulp: MUFU.RCP64H seed + two Newton steps (the sequence CUDA's own division starts with).
 __device__ __forceinline__ double rcp_nr(double d)
 {
     double x;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
     double e = fma(-d, x, 1.0);
-    e = fma(e, e, e);
     x = fma(x, e, x);
     e = fma(-d, x, 1.0);
     x = fma(x, e, x);
     return x;
 }
 
-// psi is touched exactly once per sweep: keep it out of L1.
-__device__ __forceinline__ double2 ld_stream(const double *p)
+// Walks the tiles a CTA processes.  Its range [t0, t1) of the flattened (row block, tile) sequence
+// is visited as: last (head) piece, whole row blocks, first (tail) piece -- see the file header.
+struct Cursor {
+    int nt, rb, ti;                      // tiles per row; current row block and tile (sweep order)
+    int b0, b1, first_ti;                // first / last row block of the range, tile where the range starts
+    int64_t j, len_last;                 // tiles done so far; length of the head piece
+    __device__ void init(int64_t t0, int64_t t1, int nt_)
+    {
+        nt = nt_;
+        b0 = (int)(t0 / nt); b1 = (int)((t1 - 1) / nt);
+        first_ti = (int)(t0 - (int64_t)b0 * nt);
+        j = 0;
+        if (b0 == b1) { len_last = t1 - t0; rb = b0; ti = first_ti; }
+        else { len_last = t1 - (int64_t)b1 * nt; rb = b1; ti = 0; }
+    }
+    __device__ void advance()
+    {
+        ++j; ++ti;
+        if (b0 == b1) return;
+        if (j == len_last) {                        // head piece done
+            if (b1 - b0 > 1) { rb = b0 + 1; ti = 0; } else { rb = b0; ti = first_ti; }
+        } else if (ti == nt && j > len_last) {      // a whole row block done
+            ++rb; ti = 0;
+            if (rb == b1) { rb = b0; ti = first_ti; }
+        }
+    }
+};
+
+struct RowCtx {                          // per (row block, warp) constants
+    double m, two_m, hw;
+    int64_t row;                         // element offset of this warp's psi row
+    int64_t poff;                        // element offset of the partial row
+    int g, nactive;
+    bool neg, active;
+};
+
+__device__ __forceinline__ void row_setup(const SweepArgs &p, int rb, int warp, RowCtx &c)
 {
-    double2 v;
-    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void st_stream(double *p, double2 v)
-{
-    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+    c.g = rb / p.nbg;
+    const int blk = rb % p.nbg;
+    c.neg = blk < p.nb_neg;
+    const int a0 = c.neg ? blk * kAC : p.n_neg + (blk - p.nb_neg) * kAC;
+    const int a_end = c.neg ? p.n_neg : p.A;
+    c.nactive = min(kAC, a_end - a0);
+    c.active = warp < c.nactive;
+    const int a = a0 + (c.active ? warp : 0);
+    c.m = fabs(p.mu_ihx[a]);
+    c.two_m = 2.0 * c.m;
+    c.hw = c.active ? 0.5 * p.wgt[a] : 0.0;
+    c.row = ((int64_t)c.g * p.A + a) * p.Zp;
+    c.poff = ((int64_t)blk * p.G + c.g) * p.Zp;
 }
 
-template <int AC, bool READ_PSI, bool WRITE_PSI, bool NEG>
-__device__ __forceinline__ void sweep_rows(const SweepArgs &p, int a0, int a_end, int blk, double *red)
+// One tile of one row from the staged inputs.  All 8 warps execute this (idle warps of a ragged
+// angle block chew on stale shared memory and are masked at the stores) so that the shuffles sit
+// in straight-line code.
+template <bool READ_PSI, bool WRITE_PSI, bool NEG>
+__device__ __forceinline__ void tile_body(const double *sh, const double *sq, const double *sc, const double *sp,
+                                          const RowCtx &c, double &carry, double *rw, double *pout, int64_t off,
+                                          int64_t Z, int lane)
 {
     const unsigned full = 0xffffffffu;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.y;
-    const int a = a0 + warp;
-    const bool active = a < a_end;
-    const int nactive = min(AC, a_end - a0);
-    const double m = active ? fabs(p.mu_ihx[a]) : 1.0;
-    const double two_m = 2.0 * m;
-    const double hw = active ? 0.5 * p.wgt[a] : 0.0;
-    const int64_t nt = p.Zp / kTile;
-    const int64_t goff = (int64_t)g * p.Zp + lane * 2;
-    const double *hs = p.hs + goff;
-    const double *q = p.q + goff;
-    const double *cdt = READ_PSI ? p.cdt + goff : nullptr;
-    const int64_t row = ((int64_t)g * p.A + (active ? a : a0)) * p.Zp + lane * 2;
-    const double *pin = READ_PSI ? p.psi_in + row : nullptr;
-    double *pout = WRITE_PSI ? p.psi_out + row : nullptr;
-    double *part = p.partial + ((int64_t)blk * p.G + g) * p.Zp;
-    double carry = 0.0;     // psi entering the tile (vacuum boundary: group.py:48,54)
-
-    for (int64_t it = 0; it < nt; ++it) {
-        const int64_t off = (NEG ? nt - 1 - it : it) * kTile;
-        double *redbuf = red + (it & 1) * (AC * kTile);
-        if (active) {
-            double2 vh[4], vq[4], vc[4], vp[4];
+    double ca[kL], cb[kL];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                vh[k] = __ldg(reinterpret_cast<const double2 *>(hs + off + k * 64));
-                vq[k] = __ldg(reinterpret_cast<const double2 *>(q + off + k * 64));
-                if (READ_PSI) {
-                    vc[k] = __ldg(reinterpret_cast<const double2 *>(cdt + off + k * 64));
-                    vp[k] = ld_stream(pin + off + k * 64);
-                }
-            }
-            double ca[kL], cb[kL];
-#pragma unroll
-            for (int j = 0; j < kL; ++j) {
-                const double h = (j & 1) ? vh[j >> 1].y : vh[j >> 1].x;
-                double src = (j & 1) ? vq[j >> 1].y : vq[j >> 1].x;
-                if (READ_PSI) {
-                    const double c = (j & 1) ? vc[j >> 1].y : vc[j >> 1].x;
-                    const double pp = (j & 1) ? vp[j >> 1].y : vp[j >> 1].x;
-                    src = fma(c, pp, src);              // time_unit.py:23: S + psi*inv_speed/dt
-                }
-                const double r = rcp_nr(m + h);         // 1/(0.5*sigT + mu/hx), group.py:50
-                ca[j] = fma(two_m, r, -1.0);            // (mu/hx - 0.5*sigT)/(0.5*sigT + mu/hx)
-                cb[j] = src * r;
-            }
-            // fold this lane's 8 cells in sweep order
-            double Ai, Bi;
-            if (!NEG) {
-                Ai = ca[0]; Bi = cb[0];
-#pragma unroll
-                for (int j = 1; j < kL; ++j) { Bi = fma(ca[j], Bi, cb[j]); Ai *= ca[j]; }
-            } else {
-                Ai = ca[kL - 1]; Bi = cb[kL - 1];
-#pragma unroll
-                for (int j = kL - 2; j >= 0; --j) { Bi = fma(ca[j], Bi, cb[j]); Ai *= ca[j]; }
-            }
-            // inclusive scan of the lane maps along the sweep direction
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const double Ao = NEG ? __shfl_down_sync(full, Ai, d) : __shfl_up_sync(full, Ai, d);
-                const double Bo = NEG ? __shfl_down_sync(full, Bi, d) : __shfl_up_sync(full, Bi, d);
-                const bool take = NEG ? (lane + d < 32) : (lane >= d);
-                if (take) { Bi = fma(Ai, Bo, Bi); Ai *= Ao; }
-            }
-            double Ae = NEG ? __shfl_down_sync(full, Ai, 1) : __shfl_up_sync(full, Ai, 1);
-            double Be = NEG ? __shfl_down_sync(full, Bi, 1) : __shfl_up_sync(full, Bi, 1);
-            if (NEG ? (lane == 31) : (lane == 0)) { Ae = 1.0; Be = 0.0; }
-            double in = fma(Ae, carry, Be);
-            const double At = __shfl_sync(full, Ai, NEG ? 0 : 31);
-            const double Bt = __shfl_sync(full, Bi, NEG ? 0 : 31);
-            carry = fma(At, carry, Bt);
-
-            double f[kL];
-#pragma unroll
-            for (int jj = 0; jj < kL; ++jj) {
-                const int j = NEG ? kL - 1 - jj : jj;
-                const double out = fma(ca[j], in, cb[j]);
-                const double s2 = in + out;             // psi_mid = 0.5*(in+out), group.py:51,57
-                f[j] = s2;
-                in = out;
-            }
-            double *rw = redbuf + warp * kTile + lane * 2;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                *reinterpret_cast<double2 *>(rw + k * 64) = make_double2(hw * f[2 * k], hw * f[2 * k + 1]);
-            if (WRITE_PSI) {
-                const bool ragged = off + kTile > p.Z;  // only the last tile holds padding cells
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    double2 v = make_double2(0.5 * f[2 * k], 0.5 * f[2 * k + 1]);
-                    if (ragged) {
-                        const int64_t z = off + lane * kL + 2 * k;
-                        if (z >= p.Z) v.x = 0.0;
-                        if (z + 1 >= p.Z) v.y = 0.0;
-                    }
-                    st_stream(pout + off + k * 64, v);
-                }
-            }
+    for (int k = 0; k < 4; ++k) {
+        const double2 h = *reinterpret_cast<const double2 *>(sh + k * 64);
+        double2 s = *reinterpret_cast<const double2 *>(sq + k * 64);
+        if (READ_PSI) {
+            const double2 cc = *reinterpret_cast<const double2 *>(sc + k * 64);
+            const double2 pp = *reinterpret_cast<const double2 *>(sp + k * 64);
+            s.x = fma(cc.x, pp.x, s.x);             // time_unit.py:23: S + psi*inv_speed/dt
+            s.y = fma(cc.y, pp.y, s.y);
         }
-        __syncthreads();
-        // partial scalar flux of this angle block: sum over its warps in angle order (group.py:77)
-        for (int c = threadIdx.x; c < kTile; c += AC * 32) {
-            double sum = redbuf[c];
-            for (int w = 1; w < nactive; ++w) sum += redbuf[w * kTile + c];
-            part[off + c] = sum;
+        const double r0 = rcp_nr(c.m + h.x);        // 1/(0.5*sigT + mu/hx), group.py:50
+        const double r1 = rcp_nr(c.m + h.y);
+        ca[2 * k] = fma(c.two_m, r0, -1.0);         // (mu/hx - 0.5*sigT)/(0.5*sigT + mu/hx)
+        ca[2 * k + 1] = fma(c.two_m, r1, -1.0);
+        cb[2 * k] = s.x * r0;
+        cb[2 * k + 1] = s.y * r1;
+    }
+    // fold this lane's 8 cells in sweep order
+    double Ai, Bi;
+    if (!NEG) {
+        Ai = ca[0]; Bi = cb[0];
+#pragma unroll
+        for (int j = 1; j < kL; ++j) { Bi = fma(ca[j], Bi, cb[j]); Ai *= ca[j]; }
+    } else {
+        Ai = ca[kL - 1]; Bi = cb[kL - 1];
+#pragma unroll
+        for (int j = kL - 2; j >= 0; --j) { Bi = fma(ca[j], Bi, cb[j]); Ai *= ca[j]; }
+    }
+    // inclusive scan of the lane maps along the sweep direction
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double Ao = NEG ? __shfl_down_sync(full, Ai, d) : __shfl_up_sync(full, Ai, d);
+        const double Bo = NEG ? __shfl_down_sync(full, Bi, d) : __shfl_up_sync(full, Bi, d);
+        const bool take = NEG ? (lane + d < 32) : (lane >= d);
+        if (take) { Bi = fma(Ai, Bo, Bi); Ai *= Ao; }
+    }
+    double Ae = NEG ? __shfl_down_sync(full, Ai, 1) : __shfl_up_sync(full, Ai, 1);
+    double Be = NEG ? __shfl_down_sync(full, Bi, 1) : __shfl_up_sync(full, Bi, 1);
+    if (NEG ? (lane == 31) : (lane == 0)) { Ae = 1.0; Be = 0.0; }
+    double in = fma(Ae, carry, Be);
+    const double At = __shfl_sync(full, Ai, NEG ? 0 : 31);
+    const double Bt = __shfl_sync(full, Bi, NEG ? 0 : 31);
+    carry = fma(At, carry, Bt);
+
+    double f[kL];                                   // in + out = 2 * psi_mid (group.py:51,57)
+#pragma unroll
+    for (int jj = 0; jj < kL; ++jj) {
+        const int j = NEG ? kL - 1 - jj : jj;
+        const double out = fma(ca[j], in, cb[j]);
+        f[j] = in + out;
+        in = out;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<double2 *>(rw + k * 64) = make_double2(f[2 * k], f[2 * k + 1]);
+    if (WRITE_PSI && c.active) {
+        const bool ragged = off + kTile > Z;        // only the last tile holds padding cells
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double2 v = make_double2(0.5 * f[2 * k], 0.5 * f[2 * k + 1]);
+            if (ragged) {
+                const int64_t z = off + lane * kL + 2 * k;
+                if (z >= Z) v.x = 0.0;
+                if (z + 1 >= Z) v.y = 0.0;
+            }
+            st_stream(pout + off + k * 64, v);
         }
-        // no second barrier: the next tile writes the other half of `red`
     }
 }
 
-template <int AC, bool READ_PSI, bool WRITE_PSI>
-__global__ void __launch_bounds__(AC * 32) sweep_kernel(const SweepArgs p, const ae_ctrl *ctrl, int gate)
+template <bool READ_PSI, bool WRITE_PSI>
+__global__ void __launch_bounds__(kAC * 32, 2) sweep_kernel(const SweepArgs p, const ae_ctrl *ctrl, int gate)
 {
-    extern __shared__ double red[];                     // [2][AC][kTile]
-    if (gate && ctrl->inner_done) return;               // batch launched past convergence
-    const int blk = blockIdx.x;
-    if (blk < p.nb_neg) {
-        sweep_rows<AC, READ_PSI, WRITE_PSI, true>(p, blk * AC, p.n_neg, blk, red);
-    } else {
-        sweep_rows<AC, READ_PSI, WRITE_PSI, false>(p, p.n_neg + (blk - p.nb_neg) * AC, p.A, blk, red);
+    constexpr int kSlots = (READ_PSI ? 3 + kAC : 2);            // 2 KB slots per stage
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *ring = reinterpret_cast<double *>(smem_raw);                    // [kStages][kSlots][kTile]
+    double *red = ring + kStages * kSlots * kTile;                          // [2][kAC][kTile]
+    double *hws = red + 2 * kAC * kTile;                                    // [2][kAC] weights of the tile in `red`
+    uint64_t *full = reinterpret_cast<uint64_t *>(hws + 2 * kAC);           // [kStages]
+    __shared__ int s_cta;
+    if (gate && ctrl->inner_done) return;                                   // batch launched past convergence
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    SweepSync *sy = p.sync;
+    if (tid == 0) {
+        s_cta = (int)atomicInc(&sy->ticket, gridDim.x - 1);                // logical id in START order; self-resetting
+        for (int s = 0; s < kStages; ++s) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int cta = s_cta;
+    const unsigned stamp = sy->epoch + 1;                                   // epoch only advances after every CTA has left
+    const int64_t nt = p.Zp / kTile;
+    const int64_t T = p.total_tiles, NC = gridDim.x;
+    const int64_t t0 = cta * T / NC, t1 = (cta + 1) * T / NC, W = t1 - t0;
+    const bool publishes = (t1 % nt) != 0;                                  // range ends inside a row block
+    Cursor cur, pcur;                                                       // consumer / producer (thread 0) cursors
+    cur.init(t0, t1, (int)nt);
+    pcur = cur;
+
+    // producer side (thread 0): issue the bulk copies of the tile under pcur into stage pcur.j % kStages
+    RowCtx pc;
+    int pc_rb = -1;
+    auto issue = [&]() {
+        if (pcur.rb != pc_rb) { row_setup(p, pcur.rb, 0, pc); pc_rb = pcur.rb; }
+        const RowCtx &c = pc;
+        const int64_t off = (int64_t)(c.neg ? nt - 1 - pcur.ti : pcur.ti) * kTile;
+        const int st = (int)(pcur.j % kStages);
+        double *dst = ring + (size_t)st * kSlots * kTile;
+        uint64_t *bar = full + st;
+        const int64_t goff = (int64_t)c.g * p.Zp + off;
+        const int nact = c.nactive;
+        mbar_expect_tx(bar, (uint32_t)((READ_PSI ? 3 + nact : 2) * kTileBytes));
+        bulk_g2s(dst, p.hs + goff, kTileBytes, bar);
+        bulk_g2s(dst + kTile, p.q + goff, kTileBytes, bar);
+        if (READ_PSI) {
+            bulk_g2s(dst + 2 * kTile, p.cdt + goff, kTileBytes, bar);
+            for (int w = 0; w < nact; ++w)
+                bulk_g2s(dst + (3 + w) * kTile, p.psi_in + c.row + (int64_t)w * p.Zp + off, kTileBytes, bar);
+        }
+        pcur.advance();
+    };
+    if (tid == 0)
+        for (int64_t j = 0; j < kStages && j < W; ++j) issue();
+
+    RowCtx c;
+    int cur_rb = -1;
+    double carry = 0.0;
+    for (int64_t j = 0; j < W; ++j, cur.advance()) {
+        const int rb = cur.rb, ti = cur.ti;
+        if (rb != cur_rb || ti == 0) {
+            if (rb != cur_rb) { row_setup(p, rb, warp, c); cur_rb = rb; }
+            carry = 0.0;                                                    // vacuum boundary: group.py:48,54
+            if (ti != 0) {                                                  // continue a row another CTA started
+                if (lane == 0 && c.active) {
+                    while (ld_acquire(&sy->flag[cta - 1][warp]) != stamp) {}
+                    carry = sy->carry[cta - 1][warp];
+                }
+                carry = __shfl_sync(0xffffffffu, carry, 0);
+            }
+        }
+        const int st = (int)(j % kStages);
+        const int64_t off = (int64_t)(c.neg ? nt - 1 - ti : ti) * kTile;
+        const double *stage = ring + (size_t)st * kSlots * kTile + lane * 2;
+        double *redbuf = red + (j & 1) * (kAC * kTile);
+        if (lane == 0) hws[(j & 1) * kAC + warp] = c.hw;
+        mbar_wait(full + st, (uint32_t)((j / kStages) & 1));
+        double *pout = WRITE_PSI ? p.psi_out + c.row + lane * 2 : nullptr;
+        if (c.neg)
+            tile_body<READ_PSI, WRITE_PSI, true>(stage, stage + kTile, stage + 2 * kTile, stage + (3 + warp) * kTile, c,
+                                                 carry, redbuf + warp * kTile + lane * 2, pout, off, p.Z, lane);
+        else
+            tile_body<READ_PSI, WRITE_PSI, false>(stage, stage + kTile, stage + 2 * kTile, stage + (3 + warp) * kTile, c,
+                                                  carry, redbuf + warp * kTile + lane * 2, pout, off, p.Z, lane);
+        // hand the carries to the CTA that continues this row (its range starts where ours ends)
+        if (publishes && j == cur.len_last - 1 && lane == 0 && c.active) {
+            sy->carry[cta][warp] = carry;
+            st_release(&sy->flag[cta][warp], stamp);
+        }
+        __syncthreads();                        // stage st and red[j&1] are complete / consumed
+        if (tid == 0 && j + kStages < W) issue();
+        // partial scalar flux of this angle block: sum_w 0.5*w_a*(in+out), angle order (group.py:77)
+        {
+            const double *hwv = hws + (j & 1) * kAC;
+            double sum = hwv[0] * redbuf[tid];
+            for (int w = 1; w < c.nactive; ++w) sum = fma(hwv[w], redbuf[w * kTile + tid], sum);
+            p.partial[c.poff + off + tid] = sum;
+        }
+    }
+    // last CTA out advances the epoch (stamps of this launch can never match the next one's)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicInc(&sy->done, gridDim.x - 1) == gridDim.x - 1) atomicAdd(&sy->epoch, 1u);
     }
 }
 
@@ -195,64 +360,68 @@ __global__ void reduce_partials_kernel(const double *partial, int P, int64_t Z, 
     }
 }
 
-int angles_per_cta(int A, int n_neg)
+template <bool RD, bool WR>
+static int launch_variant(const SweepArgs &p, const ae_ctrl *ctrl, int gate, cudaStream_t st)
 {
-    const int side = max(n_neg, A - n_neg);
-    int ac = 1;
-    while (ac < 8 && ac < side) ac <<= 1;
-    return ac;
-}
-
-template <int AC>
-static int launch_ac(const SweepArgs &p, const ae_ctrl *ctrl, int gate, cudaStream_t st)
-{
-    const int nb_pos = (p.A - p.n_neg + AC - 1) / AC;
-    dim3 grid(p.nb_neg + nb_pos, p.G);
-    const size_t smem = 2 * AC * kTile * sizeof(double);
-    const bool rd = p.psi_in != nullptr, wr = p.psi_out != nullptr;
-    if (rd && wr) sweep_kernel<AC, true, true><<<grid, AC * 32, smem, st>>>(p, ctrl, gate);
-    else if (rd) sweep_kernel<AC, true, false><<<grid, AC * 32, smem, st>>>(p, ctrl, gate);
-    else if (wr) sweep_kernel<AC, false, true><<<grid, AC * 32, smem, st>>>(p, ctrl, gate);
-    else sweep_kernel<AC, false, false><<<grid, AC * 32, smem, st>>>(p, ctrl, gate);
+    constexpr int slots = RD ? 3 + kAC : 2;
+    const size_t smem = (size_t)(kStages * slots + 2 * kAC) * kTileBytes + 2 * kAC * sizeof(double) + kStages * sizeof(uint64_t);
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
+        AE_CUDA(cudaFuncSetAttribute((const void *)sweep_kernel<RD, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int n = 0;
+        AE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sweep_kernel<RD, WR>, kAC * 32, smem));
+        if (n < 1) { set_error("sweep kernel does not fit on an SM"); return AE_CUDA_ERROR; }
+        ctas_per_sm = n;
+    }
+    int dev = 0, sms = 0;
+    AE_CUDA(cudaGetDevice(&dev));
+    AE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int64_t grid = (int64_t)sms * ctas_per_sm;
+    if (grid > kMaxCtas) grid = kMaxCtas;
+    const int64_t min_tiles = 4;                        // do not slice tiny problems thinner than this
+    if (grid > (p.total_tiles + min_tiles - 1) / min_tiles) grid = (p.total_tiles + min_tiles - 1) / min_tiles;
+    if (grid < 1) grid = 1;
+    sweep_kernel<RD, WR><<<(unsigned)grid, kAC * 32, smem, st>>>(p, ctrl, gate);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }
 
 // internal launcher shared with the solver loops (gate: skip when ctrl->inner_done is set)
 int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double *psi_out, double *partial,
-                 const ae_ctrl *ctrl, int gate, cudaStream_t st)
+                 void *sync, const ae_ctrl *ctrl, int gate, cudaStream_t st)
 {
-    if (!s || !q || !partial || s->Zp % kTile || s->A <= 0 || s->G <= 0) {
+    if (!s || !q || !partial || !sync || s->Zp % kTile || s->A <= 0 || s->G <= 0) {
         set_error("ae_sweep_set: bad argument");
         return AE_BAD_ARG;
     }
     if (psi_in && !s->cdt) { set_error("ae_sweep_set: psi_in given but slab has no cdt"); return AE_BAD_ARG; }
     SweepArgs p;
     p.hs = s->hs; p.cdt = s->cdt; p.q = q; p.mu_ihx = s->mu_ihx; p.wgt = s->wgt;
-    p.psi_in = psi_in; p.psi_out = psi_out; p.partial = partial;
+    p.psi_in = psi_in; p.psi_out = psi_out; p.partial = partial; p.sync = (SweepSync *)sync;
     p.Z = s->Z; p.Zp = s->Zp; p.A = s->A; p.n_neg = s->n_neg; p.G = s->G;
-    const int ac = angles_per_cta(s->A, s->n_neg);
-    p.nb_neg = (s->n_neg + ac - 1) / ac;
-    switch (ac) {
-        case 1: return launch_ac<1>(p, ctrl, gate, st);
-        case 2: return launch_ac<2>(p, ctrl, gate, st);
-        case 4: return launch_ac<4>(p, ctrl, gate, st);
-        default: return launch_ac<8>(p, ctrl, gate, st);
-    }
+    p.nb_neg = (s->n_neg + kAC - 1) / kAC;
+    p.nbg = p.nb_neg + (s->A - s->n_neg + kAC - 1) / kAC;
+    p.total_tiles = (int64_t)s->G * p.nbg * (s->Zp / kTile);
+    const bool rd = psi_in != nullptr, wr = psi_out != nullptr;
+    if (rd && wr) return launch_variant<true, true>(p, ctrl, gate, st);
+    if (rd) return launch_variant<true, false>(p, ctrl, gate, st);
+    if (wr) return launch_variant<false, true>(p, ctrl, gate, st);
+    return launch_variant<false, false>(p, ctrl, gate, st);
 }
 
 }  // namespace ae
 
 extern "C" int32_t ae_partial_count(int32_t A, int32_t n_neg)
 {
-    const int ac = ae::angles_per_cta(A, n_neg);
-    return (n_neg + ac - 1) / ac + (A - n_neg + ac - 1) / ac;
+    return (n_neg + ae::kAC - 1) / ae::kAC + (A - n_neg + ae::kAC - 1) / ae::kAC;
 }
 
+extern "C" int64_t ae_sweep_sync_bytes(void) { return (int64_t)sizeof(ae::SweepSync); }
+
 extern "C" int ae_sweep_set(const ae_slab *s, const double *q, const double *psi_in, double *psi_out,
-                            double *partial, void *stream)
+                            double *partial, void *sync, void *stream)
 {
-    return ae::launch_sweep(s, q, psi_in, psi_out, partial, nullptr, 0, (cudaStream_t)stream);
+    return ae::launch_sweep(s, q, psi_in, psi_out, partial, sync, nullptr, 0, (cudaStream_t)stream);
 }
 
 extern "C" int ae_reduce_partials(const ae_slab *s, const double *partial, int32_t P, double *phi, void *stream)

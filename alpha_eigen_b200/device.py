@@ -123,6 +123,7 @@ class SlabDevice:
         self.q1 = torch.zeros(n, **f64)
         self.partial = torch.zeros(self.P * n, **f64)
         self.scratch = torch.zeros(4 * int(self.lib.ae_norm_blocks(self.Zp)), **f64)
+        self.sync = torch.zeros(int(self.lib.ae_sweep_sync_bytes()), dtype=torch.uint8, device=self.dev)
         self.ctrl = torch.zeros(C.sizeof(_lib.AeCtrl), dtype=torch.uint8, device=self.dev)
         self.ctrl_host = torch.zeros(C.sizeof(_lib.AeCtrl), dtype=torch.uint8).pin_memory()
         if batch is None:       # small problems are launch-latency bound: poll the flag less often
@@ -135,7 +136,7 @@ class SlabDevice:
         self.work = _lib.AeWork(self.phi.data_ptr(), self.phi_outer.data_ptr(), self.base.data_ptr(),
                                 self.q0.data_ptr(), self.q1.data_ptr(), self.partial.data_ptr(),
                                 self.scratch.data_ptr(), self.ctrl.data_ptr(), self.ctrl_host.data_ptr(),
-                                comm.handle.value if comm is not None else None, self.P, int(batch))
+                                self.sync.data_ptr(), comm.handle.value if comm is not None else None, self.P, int(batch))
         self.last_q_index = 0
 
     @classmethod
@@ -207,7 +208,7 @@ class SlabDevice:
         (summed over ranks when a communicator is attached)."""
         ptr = lambda t: t.data_ptr() if t is not None else None
         _lib.check(self.lib.ae_sweep_set(C.byref(self.slab), q.data_ptr(), ptr(psi_in), ptr(psi_out),
-                                         self.partial.data_ptr(), self.stream))
+                                         self.partial.data_ptr(), self.sync.data_ptr(), self.stream))
         phi = self.torch.empty(self.G * self.Zp, dtype=self.torch.float64, device=self.dev)
         _lib.check(self.lib.ae_reduce_partials(C.byref(self.slab), self.partial.data_ptr(), self.P, phi.data_ptr(),
                                                self.stream))

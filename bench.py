@@ -178,7 +178,7 @@ def main():
         if ev is not None:
             ev[0].record()
         dev.lib.ae_sweep_set(dev.slab, q[i & 1].data_ptr(), psi.data_ptr(), psi.data_ptr(), dev.partial.data_ptr(),
-                             dev.stream)
+                             dev.sync.data_ptr(), dev.stream)
         if ev is not None:
             ev[1].record()
         launches += 1
@@ -261,7 +261,7 @@ def main():
                        "step": "psi-streaming sweep set (in place) + phi allreduce (N>1) + flux-update kernel",
                        "l2": "inputs (psi %.1f GB per GPU) are larger than L2" % (psi.numel() * 8 / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "kernel": "ae::sweep_kernel<8,true,true>",
+                         "frac": achieved / hbm_peak, "traffic": None, "kernel": "ae::sweep_kernel<true,true>",
                          "kernel_ms": sweep_ms, "bytes_per_update": bytes_per_update, "peak_source": peak_src,
                          "sweep_share_of_step": sweep_ms / ms_per_step},
             "e2e": {"value": updates_per_step / (e_ms * 1e-3), "unit": "updates/s", "ms_per_step": e_ms,

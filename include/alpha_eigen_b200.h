@@ -77,6 +77,7 @@ typedef struct ae_work {
     double *norm_scratch;    /* [4 * ae_norm_blocks(Zp)] */
     ae_ctrl *ctrl;           /* device */
     ae_ctrl *ctrl_host;      /* pinned host */
+    void *sweep_sync;        /* device, ae_sweep_sync_bytes() bytes, zero-filled once */
     void *comm;              /* ae_comm handle for the phi allreduce, or NULL (single GPU) */
     int32_t P;               /* ae_partial_count(A, n_neg) */
     int32_t batch;           /* source iterations launched between host polls (>=1) */
@@ -97,7 +98,11 @@ int64_t ae_norm_blocks(int64_t Zp);
  *   partial         : [P][G][Zp] receives sum_a w_a psi_a per angle block (group.py:77)
  */
 int ae_sweep_set(const ae_slab *s, const double *q, const double *psi_in, double *psi_out,
-                 double *partial, void *stream);
+                 double *partial, void *sync, void *stream);
+/* `sync` is a device buffer of ae_sweep_sync_bytes() bytes, zero-filled ONCE by the caller: the
+ * mailbox through which persistent CTAs hand running boundary fluxes to each other.  One buffer
+ * per stream of sweeps (ae_work carries its own). */
+int64_t ae_sweep_sync_bytes(void);
 /* phi[G][Zp] = sum_p partial[p] in block order; padding cells are zeroed. */
 int ae_reduce_partials(const ae_slab *s, const double *partial, int32_t P, double *phi, void *stream);
 

@@ -26,7 +26,7 @@ def test_struct_sizes_match_header():
     import ctypes as C
     assert C.sizeof(_lib.AeCtrl) == 64
     assert C.sizeof(_lib.AeSlab) == 16 + 16 + 9 * 8
-    assert C.sizeof(_lib.AeWork) == 10 * 8 + 8
+    assert C.sizeof(_lib.AeWork) == 11 * 8 + 8
 
 
 @pytest.mark.parametrize("Z", [1, 7, 255, 256, 257, 450, 1800, 5000])
@@ -44,6 +44,7 @@ def test_partial_count():
     lib = _lib.load()
     assert lib.ae_partial_count(4, 2) == 2
     assert lib.ae_partial_count(16, 8) == 2
+    assert lib.ae_sweep_sync_bytes() > 0
     assert lib.ae_partial_count(196, 98) == 26
     assert lib.ae_partial_count(64, 32) == 8
     assert lib.ae_partial_count(3, 0) == 1
