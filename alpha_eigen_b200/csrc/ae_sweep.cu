@@ -29,19 +29,20 @@
 // 16-byte streaming stores (in place is safe: a tile is read before it is written and
 // prefetches only run ahead).  Algorithmic bytes per cell-angle-group update:
 //   8 (psi read) + 8 (psi write) + 24/A (hs, q, cdt over the angles) + 8/8 (partial write).
+#include <stdlib.h>
 #include "ae_common.cuh"
 
 namespace ae {
 
 constexpr int kAC = 8;                  // warps (angles) per CTA
-constexpr int kStages = 3;              // TMA ring depth
 constexpr int kTileBytes = kTile * 8;   // 2 KB
 constexpr int kMaxCtas = 148 * 4;
 
+constexpr int kMaxBlk = 2 * kAC;        // angles per row block, upper bound
 struct SweepSync {                      // global mailbox, zero-initialised once by the caller
     unsigned ticket, done, epoch, pad;
-    unsigned flag[kMaxCtas][kAC];
-    double carry[kMaxCtas][kAC];
+    unsigned flag[kMaxCtas][kMaxBlk];
+    double carry[kMaxCtas][kMaxBlk];
 };
 
 struct SweepArgs {
@@ -62,6 +63,10 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
@@ -137,38 +142,43 @@ struct Cursor {
     }
 };
 
-struct RowCtx {                          // per (row block, warp) constants
-    double m, two_m, hw;
-    int64_t row;                         // element offset of this warp's psi row
+template <int NA>
+struct RowCtx {                          // per (row block, warp) constants; a warp owns NA angles of the block
+    double m[NA], two_m[NA], hw[NA];
+    int64_t row;                         // element offset of the block's first psi row
     int64_t poff;                        // element offset of the partial row
-    int g, nactive;
-    bool neg, active;
+    int g, nblk;                         // group, angles present in this block (<= kAC*NA)
+    bool neg;
 };
 
-__device__ __forceinline__ void row_setup(const SweepArgs &p, int rb, int warp, RowCtx &c)
+// Angle i of warp w sits at index i*kAC + w of its block (so a ragged block keeps every warp busy first).
+template <int NA>
+__device__ __forceinline__ void row_setup(const SweepArgs &p, int rb, int warp, RowCtx<NA> &c)
 {
     c.g = rb / p.nbg;
     const int blk = rb % p.nbg;
     c.neg = blk < p.nb_neg;
-    const int a0 = c.neg ? blk * kAC : p.n_neg + (blk - p.nb_neg) * kAC;
+    const int a0 = c.neg ? blk * (kAC * NA) : p.n_neg + (blk - p.nb_neg) * (kAC * NA);
     const int a_end = c.neg ? p.n_neg : p.A;
-    c.nactive = min(kAC, a_end - a0);
-    c.active = warp < c.nactive;
-    const int a = a0 + (c.active ? warp : 0);
-    c.m = fabs(p.mu_ihx[a]);
-    c.two_m = 2.0 * c.m;
-    c.hw = c.active ? 0.5 * p.wgt[a] : 0.0;
-    c.row = ((int64_t)c.g * p.A + a) * p.Zp;
+    c.nblk = min(kAC * NA, a_end - a0);
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        const int idx = i * kAC + warp;
+        const int a = a0 + (idx < c.nblk ? idx : 0);
+        c.m[i] = fabs(p.mu_ihx[a]);
+        c.two_m[i] = 2.0 * c.m[i];
+        c.hw[i] = idx < c.nblk ? 0.5 * p.wgt[a] : 0.0;
+    }
+    c.row = ((int64_t)c.g * p.A + a0) * p.Zp;
     c.poff = ((int64_t)blk * p.G + c.g) * p.Zp;
 }
 
-// One tile of one row from the staged inputs.  All 8 warps execute this (idle warps of a ragged
-// angle block chew on stale shared memory and are masked at the stores) so that the shuffles sit
-// in straight-line code.
-template <bool READ_PSI, bool WRITE_PSI, bool NEG>
-__device__ __forceinline__ void tile_body(const double *sh, const double *sq, const double *sc, const double *sp,
-                                          const RowCtx &c, double &carry, double *rw, double *pout, int64_t off,
-                                          int64_t Z, int lane)
+// One tile of one row (angle) from the staged inputs: f[j] = in + out = 2*psi_mid of the lane's cells.
+// All 8 warps execute this even for an angle slot a ragged block does not have (they chew on stale
+// shared memory and are masked at the stores), so that the shuffles sit in straight-line code.
+template <bool READ_PSI, bool NEG>
+__device__ __forceinline__ void tile_row(const double *sh, const double *sq, const double *sc, const double *sp,
+                                         double m, double two_m, double &carry, double (&f)[kL], int lane)
 {
     const unsigned full = 0xffffffffu;
     double ca[kL], cb[kL];
@@ -182,10 +192,10 @@ __device__ __forceinline__ void tile_body(const double *sh, const double *sq, co
             s.x = fma(cc.x, pp.x, s.x);             // time_unit.py:23: S + psi*inv_speed/dt
             s.y = fma(cc.y, pp.y, s.y);
         }
-        const double r0 = rcp_nr(c.m + h.x);        // 1/(0.5*sigT + mu/hx), group.py:50
-        const double r1 = rcp_nr(c.m + h.y);
-        ca[2 * k] = fma(c.two_m, r0, -1.0);         // (mu/hx - 0.5*sigT)/(0.5*sigT + mu/hx)
-        ca[2 * k + 1] = fma(c.two_m, r1, -1.0);
+        const double r0 = rcp_nr(m + h.x);          // 1/(0.5*sigT + mu/hx), group.py:50
+        const double r1 = rcp_nr(m + h.y);
+        ca[2 * k] = fma(two_m, r0, -1.0);           // (mu/hx - 0.5*sigT)/(0.5*sigT + mu/hx)
+        ca[2 * k + 1] = fma(two_m, r1, -1.0);
         cb[2 * k] = s.x * r0;
         cb[2 * k + 1] = s.y * r1;
     }
@@ -215,41 +225,68 @@ __device__ __forceinline__ void tile_body(const double *sh, const double *sq, co
     const double At = __shfl_sync(full, Ai, NEG ? 0 : 31);
     const double Bt = __shfl_sync(full, Bi, NEG ? 0 : 31);
     carry = fma(At, carry, Bt);
-
-    double f[kL];                                   // in + out = 2 * psi_mid (group.py:51,57)
 #pragma unroll
     for (int jj = 0; jj < kL; ++jj) {
         const int j = NEG ? kL - 1 - jj : jj;
         const double out = fma(ca[j], in, cb[j]);
-        f[j] = in + out;
+        f[j] = in + out;                            // 2 * psi_mid (group.py:51,57)
         in = out;
     }
+}
+
+// The NA angles of this warp for one tile: sweep, psi write-back, weighted accumulate into `acc`.
+template <int NA, bool READ_PSI, bool WRITE_PSI, bool NEG>
+__device__ __forceinline__ void tile_body(const double *stage, const RowCtx<NA> &c, double (&carry)[NA], double (&acc)[kL],
+                                          double *psi_out, int64_t off, int64_t Z, int64_t Zp, int warp, int lane)
+{
 #pragma unroll
-    for (int k = 0; k < 4; ++k) *reinterpret_cast<double2 *>(rw + k * 64) = make_double2(f[2 * k], f[2 * k + 1]);
-    if (WRITE_PSI && c.active) {
-        const bool ragged = off + kTile > Z;        // only the last tile holds padding cells
+    for (int i = 0; i < NA; ++i) {
+        const int idx = i * kAC + warp;
+        double f[kL];
+        tile_row<READ_PSI, NEG>(stage, stage + kTile, stage + 2 * kTile, stage + (3 + idx) * kTile, c.m[i], c.two_m[i],
+                                carry[i], f, lane);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            double2 v = make_double2(0.5 * f[2 * k], 0.5 * f[2 * k + 1]);
-            if (ragged) {
-                const int64_t z = off + lane * kL + 2 * k;
-                if (z >= Z) v.x = 0.0;
-                if (z + 1 >= Z) v.y = 0.0;
+        for (int j = 0; j < kL; ++j) acc[j] = i == 0 ? c.hw[0] * f[j] : fma(c.hw[i], f[j], acc[j]);   // group.py:77
+        if (WRITE_PSI && idx < c.nblk) {
+            double *pout = psi_out + c.row + (int64_t)idx * Zp + off + lane * 2;
+            const bool ragged = off + kTile > Z;    // only the last tile holds padding cells
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                double2 v = make_double2(0.5 * f[2 * k], 0.5 * f[2 * k + 1]);
+                if (ragged) {
+                    const int64_t z = off + lane * kL + 2 * k;
+                    if (z >= Z) v.x = 0.0;
+                    if (z + 1 >= Z) v.y = 0.0;
+                }
+                st_stream(pout + k * 64, v);
             }
-            st_stream(pout + off + k * 64, v);
         }
     }
 }
 
-template <bool READ_PSI, bool WRITE_PSI>
-__global__ void __launch_bounds__(kAC * 32, 2) sweep_kernel(const SweepArgs p, const ae_ctrl *ctrl, int gate)
+template <int NA> struct StageCfg { static constexpr int stages = NA == 1 ? 3 : 2; };
+
+constexpr int kThreads = (kAC + 1) * 32;    // 8 compute warps + 1 auxiliary warp (TMA producer and flux reducer)
+
+// Warp-specialised persistent kernel.  Compute warp w owns NA angles of the current row block and never
+// meets a CTA-wide barrier inside the tile loop; the auxiliary warp feeds the TMA ring and folds the
+// per-warp weighted fluxes into the partial scalar flux.  Hand-shakes are mbarriers:
+//   full[s]      aux -> compute   tile staged (expect_tx bytes landed)
+//   empty[s]     compute -> aux   all 8 warps are done reading stage s
+//   red_full[b]  compute -> aux   all 8 warps have written their flux contribution of a tile into red[b]
+//   red_empty[b] aux -> compute   red[b] has been reduced and may be overwritten
+template <int NA, bool READ_PSI, bool WRITE_PSI>
+__global__ void __launch_bounds__(kThreads, 2) sweep_kernel(const SweepArgs p, const ae_ctrl *ctrl, int gate)
 {
-    constexpr int kSlots = (READ_PSI ? 3 + kAC : 2);            // 2 KB slots per stage
+    constexpr int kStages = StageCfg<NA>::stages;
+    constexpr int kSlots = (READ_PSI ? 3 + kAC * NA : 2);       // 2 KB slots per stage
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *ring = reinterpret_cast<double *>(smem_raw);                    // [kStages][kSlots][kTile]
     double *red = ring + kStages * kSlots * kTile;                          // [2][kAC][kTile]
-    double *hws = red + 2 * kAC * kTile;                                    // [2][kAC] weights of the tile in `red`
-    uint64_t *full = reinterpret_cast<uint64_t *>(hws + 2 * kAC);           // [kStages]
+    uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * kAC * kTile);   // [kStages]
+    uint64_t *empty = full + kStages;                                       // [kStages]
+    uint64_t *red_full = empty + kStages;                                   // [2]
+    uint64_t *red_empty = red_full + 2;                                     // [2]
     __shared__ int s_cta;
     if (gate && ctrl->inner_done) return;                                   // batch launched past convergence
 
@@ -257,7 +294,8 @@ __global__ void __launch_bounds__(kAC * 32, 2) sweep_kernel(const SweepArgs p, c
     SweepSync *sy = p.sync;
     if (tid == 0) {
         s_cta = (int)atomicInc(&sy->ticket, gridDim.x - 1);                // logical id in START order; self-resetting
-        for (int s = 0; s < kStages; ++s) mbar_init(full + s, 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kAC); }
+        for (int b = 0; b < 2; ++b) { mbar_init(red_full + b, kAC); mbar_init(red_empty + b, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -267,77 +305,108 @@ __global__ void __launch_bounds__(kAC * 32, 2) sweep_kernel(const SweepArgs p, c
     const int64_t T = p.total_tiles, NC = gridDim.x;
     const int64_t t0 = cta * T / NC, t1 = (cta + 1) * T / NC, W = t1 - t0;
     const bool publishes = (t1 % nt) != 0;                                  // range ends inside a row block
-    Cursor cur, pcur;                                                       // consumer / producer (thread 0) cursors
+    Cursor cur;
     cur.init(t0, t1, (int)nt);
-    pcur = cur;
 
-    // producer side (thread 0): issue the bulk copies of the tile under pcur into stage pcur.j % kStages
-    RowCtx pc;
-    int pc_rb = -1;
-    auto issue = [&]() {
-        if (pcur.rb != pc_rb) { row_setup(p, pcur.rb, 0, pc); pc_rb = pcur.rb; }
-        const RowCtx &c = pc;
-        const int64_t off = (int64_t)(c.neg ? nt - 1 - pcur.ti : pcur.ti) * kTile;
-        const int st = (int)(pcur.j % kStages);
-        double *dst = ring + (size_t)st * kSlots * kTile;
-        uint64_t *bar = full + st;
-        const int64_t goff = (int64_t)c.g * p.Zp + off;
-        const int nact = c.nactive;
-        mbar_expect_tx(bar, (uint32_t)((READ_PSI ? 3 + nact : 2) * kTileBytes));
-        bulk_g2s(dst, p.hs + goff, kTileBytes, bar);
-        bulk_g2s(dst + kTile, p.q + goff, kTileBytes, bar);
-        if (READ_PSI) {
-            bulk_g2s(dst + 2 * kTile, p.cdt + goff, kTileBytes, bar);
-            for (int w = 0; w < nact; ++w)
-                bulk_g2s(dst + (3 + w) * kTile, p.psi_in + c.row + (int64_t)w * p.Zp + off, kTileBytes, bar);
-        }
-        pcur.advance();
-    };
-    if (tid == 0)
-        for (int64_t j = 0; j < kStages && j < W; ++j) issue();
-
-    RowCtx c;
-    int cur_rb = -1;
-    double carry = 0.0;
-    for (int64_t j = 0; j < W; ++j, cur.advance()) {
-        const int rb = cur.rb, ti = cur.ti;
-        if (rb != cur_rb || ti == 0) {
-            if (rb != cur_rb) { row_setup(p, rb, warp, c); cur_rb = rb; }
-            carry = 0.0;                                                    // vacuum boundary: group.py:48,54
-            if (ti != 0) {                                                  // continue a row another CTA started
-                if (lane == 0 && c.active) {
-                    while (ld_acquire(&sy->flag[cta - 1][warp]) != stamp) {}
-                    carry = sy->carry[cta - 1][warp];
-                }
-                carry = __shfl_sync(0xffffffffu, carry, 0);
+    if (warp == kAC) {
+        // ================= auxiliary warp: TMA producer + flux reducer =================================
+        Cursor pcur = cur;                                                  // runs kStages tiles ahead of `cur`
+        RowCtx<NA> pc, rc;
+        int pc_rb = -1, rc_rb = -1;
+        auto issue = [&]() {                                                // stage the tile under pcur
+            if (pcur.rb != pc_rb) { row_setup<NA>(p, pcur.rb, 0, pc); pc_rb = pcur.rb; }
+            const int64_t off = (int64_t)(pc.neg ? nt - 1 - pcur.ti : pcur.ti) * kTile;
+            const int st = (int)(pcur.j % kStages);
+            double *dst = ring + (size_t)st * kSlots * kTile;
+            const int64_t goff = (int64_t)pc.g * p.Zp + off;
+            const int nslots = READ_PSI ? 3 + pc.nblk : 2;
+            mbar_wait(empty + st, (uint32_t)(((pcur.j / kStages) & 1) ^ 1));        // consumers released the stage
+            if (lane == 0) mbar_expect_tx(full + st, (uint32_t)(nslots * kTileBytes));
+            __syncwarp();
+            for (int l = lane; l < nslots; l += 32) {
+                const double *src = l == 0 ? p.hs + goff : l == 1 ? p.q + goff : l == 2 ? p.cdt + goff
+                                                                               : p.psi_in + pc.row + (int64_t)(l - 3) * p.Zp + off;
+                bulk_g2s(dst + l * kTile, src, kTileBytes, full + st);
             }
+            pcur.advance();
+        };
+        for (int64_t j = 0; j < kStages && j < W; ++j) issue();
+        for (int64_t j = 0; j < W; ++j, cur.advance()) {
+            if (cur.rb != rc_rb) { row_setup<NA>(p, cur.rb, 0, rc); rc_rb = cur.rb; }
+            const int64_t off = (int64_t)(rc.neg ? nt - 1 - cur.ti : cur.ti) * kTile;
+            const int b = (int)(j & 1);
+            const double *rb_ = red + b * (kAC * kTile) + lane * 2;
+            mbar_wait(red_full + b, (uint32_t)((j >> 1) & 1));
+            double2 acc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] = *reinterpret_cast<const double2 *>(rb_ + k * 64);
+#pragma unroll
+            for (int w = 1; w < kAC; ++w)                                   // warps = angles in order (group.py:77)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double2 v = *reinterpret_cast<const double2 *>(rb_ + w * kTile + k * 64);
+                    acc[k].x += v.x; acc[k].y += v.y;
+                }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(red_empty + b);
+            double *dst = p.partial + rc.poff + off + lane * 2;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<double2 *>(dst + k * 64) = acc[k];
+            if (j + kStages < W) issue();
         }
-        const int st = (int)(j % kStages);
-        const int64_t off = (int64_t)(c.neg ? nt - 1 - ti : ti) * kTile;
-        const double *stage = ring + (size_t)st * kSlots * kTile + lane * 2;
-        double *redbuf = red + (j & 1) * (kAC * kTile);
-        if (lane == 0) hws[(j & 1) * kAC + warp] = c.hw;
-        mbar_wait(full + st, (uint32_t)((j / kStages) & 1));
-        double *pout = WRITE_PSI ? p.psi_out + c.row + lane * 2 : nullptr;
-        if (c.neg)
-            tile_body<READ_PSI, WRITE_PSI, true>(stage, stage + kTile, stage + 2 * kTile, stage + (3 + warp) * kTile, c,
-                                                 carry, redbuf + warp * kTile + lane * 2, pout, off, p.Z, lane);
-        else
-            tile_body<READ_PSI, WRITE_PSI, false>(stage, stage + kTile, stage + 2 * kTile, stage + (3 + warp) * kTile, c,
-                                                  carry, redbuf + warp * kTile + lane * 2, pout, off, p.Z, lane);
-        // hand the carries to the CTA that continues this row (its range starts where ours ends)
-        if (publishes && j == cur.len_last - 1 && lane == 0 && c.active) {
-            sy->carry[cta][warp] = carry;
-            st_release(&sy->flag[cta][warp], stamp);
-        }
-        __syncthreads();                        // stage st and red[j&1] are complete / consumed
-        if (tid == 0 && j + kStages < W) issue();
-        // partial scalar flux of this angle block: sum_w 0.5*w_a*(in+out), angle order (group.py:77)
-        {
-            const double *hwv = hws + (j & 1) * kAC;
-            double sum = hwv[0] * redbuf[tid];
-            for (int w = 1; w < c.nactive; ++w) sum = fma(hwv[w], redbuf[w * kTile + tid], sum);
-            p.partial[c.poff + off + tid] = sum;
+    } else {
+        // ================= compute warps ==============================================================
+        RowCtx<NA> c;
+        int cur_rb = -1;
+        double carry[NA];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) carry[i] = 0.0;
+        for (int64_t j = 0; j < W; ++j, cur.advance()) {
+            const int rb = cur.rb, ti = cur.ti;
+            if (rb != cur_rb || ti == 0) {
+                if (rb != cur_rb) { row_setup<NA>(p, rb, warp, c); cur_rb = rb; }
+#pragma unroll
+                for (int i = 0; i < NA; ++i) carry[i] = 0.0;                // vacuum boundary: group.py:48,54
+                if (ti != 0) {                                              // continue a row another CTA started
+#pragma unroll
+                    for (int i = 0; i < NA; ++i) {
+                        const int idx = i * kAC + warp;
+                        if (lane == 0 && idx < c.nblk) {
+                            while (ld_acquire(&sy->flag[cta - 1][idx]) != stamp) {}
+                            carry[i] = sy->carry[cta - 1][idx];
+                        }
+                        carry[i] = __shfl_sync(0xffffffffu, carry[i], 0);
+                    }
+                }
+            }
+            const int st = (int)(j % kStages), b = (int)(j & 1);
+            const int64_t off = (int64_t)(c.neg ? nt - 1 - ti : ti) * kTile;
+            const double *stage = ring + (size_t)st * kSlots * kTile + lane * 2;
+            double *rw = red + b * (kAC * kTile) + warp * kTile + lane * 2;
+            mbar_wait(full + st, (uint32_t)((j / kStages) & 1));
+            double acc[kL];
+            if (c.neg)
+                tile_body<NA, READ_PSI, WRITE_PSI, true>(stage, c, carry, acc, p.psi_out, off, p.Z, p.Zp, warp, lane);
+            else
+                tile_body<NA, READ_PSI, WRITE_PSI, false>(stage, c, carry, acc, p.psi_out, off, p.Z, p.Zp, warp, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + st);                         // this warp is done with the stage
+            mbar_wait(red_empty + b, (uint32_t)(((j >> 1) & 1) ^ 1));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<double2 *>(rw + k * 64) = make_double2(acc[2 * k], acc[2 * k + 1]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(red_full + b);
+            // hand the carries to the CTA that continues this row (its range starts where ours ends)
+            if (publishes && j == cur.len_last - 1 && lane == 0) {
+#pragma unroll
+                for (int i = 0; i < NA; ++i) {
+                    const int idx = i * kAC + warp;
+                    if (idx < c.nblk) {
+                        sy->carry[cta][idx] = carry[i];
+                        st_release(&sy->flag[cta][idx], stamp);
+                    }
+                }
+            }
         }
     }
     // last CTA out advances the epoch (stamps of this launch can never match the next one's)
@@ -360,16 +429,25 @@ __global__ void reduce_partials_kernel(const double *partial, int P, int64_t Z, 
     }
 }
 
-template <bool RD, bool WR>
+// angles per warp: 2 when a direction has enough angles to fill 16-angle blocks
+int angles_per_warp(int A, int n_neg)
+{
+    static const char *force = getenv("AE_ANGLES_PER_WARP");             // tuning knob (1 or 2)
+    if (force && (force[0] == '1' || force[0] == '2')) return force[0] - '0';
+    (void)A; (void)n_neg;
+    return 1;
+}
+
+template <int NA, bool RD, bool WR>
 static int launch_variant(const SweepArgs &p, const ae_ctrl *ctrl, int gate, cudaStream_t st)
 {
-    constexpr int slots = RD ? 3 + kAC : 2;
-    const size_t smem = (size_t)(kStages * slots + 2 * kAC) * kTileBytes + 2 * kAC * sizeof(double) + kStages * sizeof(uint64_t);
+    constexpr int slots = RD ? 3 + kAC * NA : 2;
+    const size_t smem = (size_t)(StageCfg<NA>::stages * slots + 2 * kAC) * kTileBytes + (2 * StageCfg<NA>::stages + 4) * sizeof(uint64_t);
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
-        AE_CUDA(cudaFuncSetAttribute((const void *)sweep_kernel<RD, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AE_CUDA(cudaFuncSetAttribute((const void *)sweep_kernel<NA, RD, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int n = 0;
-        AE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sweep_kernel<RD, WR>, kAC * 32, smem));
+        AE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sweep_kernel<NA, RD, WR>, kThreads, smem));
         if (n < 1) { set_error("sweep kernel does not fit on an SM"); return AE_CUDA_ERROR; }
         ctas_per_sm = n;
     }
@@ -381,9 +459,19 @@ static int launch_variant(const SweepArgs &p, const ae_ctrl *ctrl, int gate, cud
     const int64_t min_tiles = 4;                        // do not slice tiny problems thinner than this
     if (grid > (p.total_tiles + min_tiles - 1) / min_tiles) grid = (p.total_tiles + min_tiles - 1) / min_tiles;
     if (grid < 1) grid = 1;
-    sweep_kernel<RD, WR><<<(unsigned)grid, kAC * 32, smem, st>>>(p, ctrl, gate);
+    sweep_kernel<NA, RD, WR><<<(unsigned)grid, kThreads, smem, st>>>(p, ctrl, gate);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
+}
+
+template <int NA>
+static int launch_na(const SweepArgs &p, const ae_ctrl *ctrl, int gate, cudaStream_t st)
+{
+    const bool rd = p.psi_in != nullptr, wr = p.psi_out != nullptr;
+    if (rd && wr) return launch_variant<NA, true, true>(p, ctrl, gate, st);
+    if (rd) return launch_variant<NA, true, false>(p, ctrl, gate, st);
+    if (wr) return launch_variant<NA, false, true>(p, ctrl, gate, st);
+    return launch_variant<NA, false, false>(p, ctrl, gate, st);
 }
 
 // internal launcher shared with the solver loops (gate: skip when ctrl->inner_done is set)
@@ -395,25 +483,24 @@ int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double
         return AE_BAD_ARG;
     }
     if (psi_in && !s->cdt) { set_error("ae_sweep_set: psi_in given but slab has no cdt"); return AE_BAD_ARG; }
+    const int na = angles_per_warp(s->A, s->n_neg);
+    const int blk = kAC * na;
     SweepArgs p;
     p.hs = s->hs; p.cdt = s->cdt; p.q = q; p.mu_ihx = s->mu_ihx; p.wgt = s->wgt;
     p.psi_in = psi_in; p.psi_out = psi_out; p.partial = partial; p.sync = (SweepSync *)sync;
     p.Z = s->Z; p.Zp = s->Zp; p.A = s->A; p.n_neg = s->n_neg; p.G = s->G;
-    p.nb_neg = (s->n_neg + kAC - 1) / kAC;
-    p.nbg = p.nb_neg + (s->A - s->n_neg + kAC - 1) / kAC;
+    p.nb_neg = (s->n_neg + blk - 1) / blk;
+    p.nbg = p.nb_neg + (s->A - s->n_neg + blk - 1) / blk;
     p.total_tiles = (int64_t)s->G * p.nbg * (s->Zp / kTile);
-    const bool rd = psi_in != nullptr, wr = psi_out != nullptr;
-    if (rd && wr) return launch_variant<true, true>(p, ctrl, gate, st);
-    if (rd) return launch_variant<true, false>(p, ctrl, gate, st);
-    if (wr) return launch_variant<false, true>(p, ctrl, gate, st);
-    return launch_variant<false, false>(p, ctrl, gate, st);
+    return na == 2 ? launch_na<2>(p, ctrl, gate, st) : launch_na<1>(p, ctrl, gate, st);
 }
 
 }  // namespace ae
 
 extern "C" int32_t ae_partial_count(int32_t A, int32_t n_neg)
 {
-    return (n_neg + ae::kAC - 1) / ae::kAC + (A - n_neg + ae::kAC - 1) / ae::kAC;
+    const int blk = ae::kAC * ae::angles_per_warp(A, n_neg);
+    return (n_neg + blk - 1) / blk + (A - n_neg + blk - 1) / blk;
 }
 
 extern "C" int64_t ae_sweep_sync_bytes(void) { return (int64_t)sizeof(ae::SweepSync); }

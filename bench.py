@@ -248,8 +248,7 @@ def main():
 
     if rank == 0:
         hbm_peak, peak_src = peaks()
-        Ac = 8
-        bytes_per_update = 16.0 + 24.0 / dev.A + 8.0 / Ac              # psi r+w, hs/q/cdt over angles, partial
+        bytes_per_update = 16.0 + 24.0 / dev.A + 8.0 * dev.P / dev.A    # psi r+w, hs/q/cdt over angles, partial
         alg_bytes = bytes_per_update * local_updates
         achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
         line = {
@@ -261,7 +260,7 @@ def main():
                        "step": "psi-streaming sweep set (in place) + phi allreduce (N>1) + flux-update kernel",
                        "l2": "inputs (psi %.1f GB per GPU) are larger than L2" % (psi.numel() * 8 / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "kernel": "ae::sweep_kernel<true,true>",
+                         "frac": achieved / hbm_peak, "traffic": None, "kernel": "ae::sweep_kernel<NA,true,true>",
                          "kernel_ms": sweep_ms, "bytes_per_update": bytes_per_update, "peak_source": peak_src,
                          "sweep_share_of_step": sweep_ms / ms_per_step},
             "e2e": {"value": updates_per_step / (e_ms * 1e-3), "unit": "updates/s", "ms_per_step": e_ms,
