@@ -34,11 +34,11 @@
 
 namespace ae {
 
-constexpr int kAC = 8;                  // warps (angles) per CTA
+constexpr int kACsmall = 8, kACbig = 16; // compute warps (angles) per CTA: small / many-angle problems
 constexpr int kTileBytes = kTile * 8;   // 2 KB
 constexpr int kMaxCtas = 148 * 4;
 
-constexpr int kMaxBlk = 2 * kAC;        // angles per row block, upper bound
+constexpr int kMaxBlk = 16;             // angles per row block, upper bound
 struct SweepSync {                      // global mailbox, zero-initialised once by the caller
     unsigned ticket, done, epoch, pad;
     unsigned flag[kMaxCtas][kMaxBlk];
@@ -142,46 +142,38 @@ struct Cursor {
     }
 };
 
-template <int NA>
-struct RowCtx {                          // per (row block, warp) constants; a warp owns NA angles of the block
-    double m[NA], two_m[NA], hw[NA];
+struct RowCtx {                          // per (row block, warp) constants
+    double m, two_m, hw;
     int64_t row;                         // element offset of the block's first psi row
     int64_t poff;                        // element offset of the partial row
-    int g, nblk;                         // group, angles present in this block (<= kAC*NA)
+    int g, nblk;                         // group, angles present in this block (<= AC)
     bool neg;
 };
 
-// Angle i of warp w sits at index i*kAC + w of its block (so a ragged block keeps every warp busy first).
-template <int NA>
-__device__ __forceinline__ void row_setup(const SweepArgs &p, int rb, int warp, RowCtx<NA> &c)
+template <int AC>
+__device__ __forceinline__ void row_setup(const SweepArgs &p, int rb, int warp, RowCtx &c)
 {
     c.g = rb / p.nbg;
     const int blk = rb % p.nbg;
     c.neg = blk < p.nb_neg;
-    const int a0 = c.neg ? blk * (kAC * NA) : p.n_neg + (blk - p.nb_neg) * (kAC * NA);
+    const int a0 = c.neg ? blk * AC : p.n_neg + (blk - p.nb_neg) * AC;
     const int a_end = c.neg ? p.n_neg : p.A;
-    c.nblk = min(kAC * NA, a_end - a0);
-#pragma unroll
-    for (int i = 0; i < NA; ++i) {
-        const int idx = i * kAC + warp;
-        const int a = a0 + (idx < c.nblk ? idx : 0);
-        c.m[i] = fabs(p.mu_ihx[a]);
-        c.two_m[i] = 2.0 * c.m[i];
-        c.hw[i] = idx < c.nblk ? 0.5 * p.wgt[a] : 0.0;
-    }
+    c.nblk = min(AC, a_end - a0);
+    const int a = a0 + (warp < c.nblk ? warp : 0);
+    c.m = fabs(p.mu_ihx[a]);
+    c.two_m = 2.0 * c.m;
+    c.hw = warp < c.nblk ? 0.5 * p.wgt[a] : 0.0;
     c.row = ((int64_t)c.g * p.A + a0) * p.Zp;
     c.poff = ((int64_t)blk * p.G + c.g) * p.Zp;
 }
 
-// One tile of one row (angle) from the staged inputs: f[j] = in + out = 2*psi_mid of the lane's cells.
-// All 8 warps execute this even for an angle slot a ragged block does not have (they chew on stale
-// shared memory and are masked at the stores), so that the shuffles sit in straight-line code.
-template <bool READ_PSI, bool NEG>
-__device__ __forceinline__ void tile_row(const double *sh, const double *sq, const double *sc, const double *sp,
-                                         double m, double two_m, double &carry, double (&f)[kL], int lane)
+// Phase A of a tile: staged inputs -> per-cell affine maps (ca, cb).  After this the warp no longer
+// needs the ring stage.  All warps run it even for an angle slot a ragged block does not have (they
+// chew on stale shared memory and are masked at the stores), so the code stays straight-line.
+template <bool READ_PSI>
+__device__ __forceinline__ void tile_maps(const double *sh, const double *sq, const double *sc, const double *sp, double m,
+                                          double two_m, double (&ca)[kL], double (&cb)[kL])
 {
-    const unsigned full = 0xffffffffu;
-    double ca[kL], cb[kL];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const double2 h = *reinterpret_cast<const double2 *>(sh + k * 64);
@@ -199,17 +191,23 @@ __device__ __forceinline__ void tile_row(const double *sh, const double *sq, con
         cb[2 * k] = s.x * r0;
         cb[2 * k + 1] = s.y * r1;
     }
-    // fold this lane's 8 cells in sweep order
-    double Ai, Bi;
+}
+
+// Phase B: fold, warp scan, carry, cell-centre fluxes.  f[j] = in + out = 2*psi_mid of the lane's cells.
+template <bool NEG>
+__device__ __forceinline__ void tile_solve(double (&ca)[kL], double (&cb)[kL], double &carry, double (&f)[kL], int lane)
+{
+    const unsigned full = 0xffffffffu;
+    // Fold this lane's 8 cells in sweep order, keeping every running prefix map in place:
+    // afterwards (ca[j], cb[j]) maps the flux entering the LANE to the flux leaving cell j.
     if (!NEG) {
-        Ai = ca[0]; Bi = cb[0];
 #pragma unroll
-        for (int j = 1; j < kL; ++j) { Bi = fma(ca[j], Bi, cb[j]); Ai *= ca[j]; }
+        for (int j = 1; j < kL; ++j) { cb[j] = fma(ca[j], cb[j - 1], cb[j]); ca[j] *= ca[j - 1]; }
     } else {
-        Ai = ca[kL - 1]; Bi = cb[kL - 1];
 #pragma unroll
-        for (int j = kL - 2; j >= 0; --j) { Bi = fma(ca[j], Bi, cb[j]); Ai *= ca[j]; }
+        for (int j = kL - 2; j >= 0; --j) { cb[j] = fma(ca[j], cb[j + 1], cb[j]); ca[j] *= ca[j + 1]; }
     }
+    double Ai = NEG ? ca[0] : ca[kL - 1], Bi = NEG ? cb[0] : cb[kL - 1];
     // inclusive scan of the lane maps along the sweep direction
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -221,69 +219,40 @@ __device__ __forceinline__ void tile_row(const double *sh, const double *sq, con
     double Ae = NEG ? __shfl_down_sync(full, Ai, 1) : __shfl_up_sync(full, Ai, 1);
     double Be = NEG ? __shfl_down_sync(full, Bi, 1) : __shfl_up_sync(full, Bi, 1);
     if (NEG ? (lane == 31) : (lane == 0)) { Ae = 1.0; Be = 0.0; }
-    double in = fma(Ae, carry, Be);
+    const double in = fma(Ae, carry, Be);           // flux entering this lane's first cell
     const double At = __shfl_sync(full, Ai, NEG ? 0 : 31);
     const double Bt = __shfl_sync(full, Bi, NEG ? 0 : 31);
     carry = fma(At, carry, Bt);
+    // cell-edge fluxes are now independent given `in`; f = in + out = 2 * psi_mid (group.py:51,57)
+    double prev = in;
 #pragma unroll
     for (int jj = 0; jj < kL; ++jj) {
         const int j = NEG ? kL - 1 - jj : jj;
         const double out = fma(ca[j], in, cb[j]);
-        f[j] = in + out;                            // 2 * psi_mid (group.py:51,57)
-        in = out;
+        f[j] = prev + out;
+        prev = out;
     }
 }
 
-// The NA angles of this warp for one tile: sweep, psi write-back, weighted accumulate into `acc`.
-template <int NA, bool READ_PSI, bool WRITE_PSI, bool NEG>
-__device__ __forceinline__ void tile_body(const double *stage, const RowCtx<NA> &c, double (&carry)[NA], double (&acc)[kL],
-                                          double *psi_out, int64_t off, int64_t Z, int64_t Zp, int warp, int lane)
+template <int AC> struct StageCfg { static constexpr int stages = AC == kACbig ? 4 : 3; };
+
+// Warp-specialised persistent kernel: AC compute warps + reducer warp + producer warp.
+// Compute warp w owns one angle of the current row block and meets no CTA-wide barrier inside the tile
+// loop; the producer warp feeds the TMA ring; the reducer warp folds the per-warp weighted fluxes into
+// the partial scalar flux.  Hand-shakes are mbarriers:
+//   full[s]      producer -> compute   tile staged (expect_tx bytes landed)
+//   empty[s]     compute -> producer   all AC warps hold stage s in registers (released after phase A)
+//   red_full[b]  compute -> reducer    all AC warps have written their flux contribution into red[b]
+//   red_empty[b] reducer -> compute    red[b] has been summed and may be overwritten
+template <int AC, bool READ_PSI, bool WRITE_PSI>
+__global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_kernel(const SweepArgs p, const ae_ctrl *ctrl, int gate)
 {
-#pragma unroll
-    for (int i = 0; i < NA; ++i) {
-        const int idx = i * kAC + warp;
-        double f[kL];
-        tile_row<READ_PSI, NEG>(stage, stage + kTile, stage + 2 * kTile, stage + (3 + idx) * kTile, c.m[i], c.two_m[i],
-                                carry[i], f, lane);
-#pragma unroll
-        for (int j = 0; j < kL; ++j) acc[j] = i == 0 ? c.hw[0] * f[j] : fma(c.hw[i], f[j], acc[j]);   // group.py:77
-        if (WRITE_PSI && idx < c.nblk) {
-            double *pout = psi_out + c.row + (int64_t)idx * Zp + off + lane * 2;
-            const bool ragged = off + kTile > Z;    // only the last tile holds padding cells
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                double2 v = make_double2(0.5 * f[2 * k], 0.5 * f[2 * k + 1]);
-                if (ragged) {
-                    const int64_t z = off + lane * kL + 2 * k;
-                    if (z >= Z) v.x = 0.0;
-                    if (z + 1 >= Z) v.y = 0.0;
-                }
-                st_stream(pout + k * 64, v);
-            }
-        }
-    }
-}
-
-template <int NA> struct StageCfg { static constexpr int stages = NA == 1 ? 3 : 2; };
-
-constexpr int kThreads = (kAC + 1) * 32;    // 8 compute warps + 1 auxiliary warp (TMA producer and flux reducer)
-
-// Warp-specialised persistent kernel.  Compute warp w owns NA angles of the current row block and never
-// meets a CTA-wide barrier inside the tile loop; the auxiliary warp feeds the TMA ring and folds the
-// per-warp weighted fluxes into the partial scalar flux.  Hand-shakes are mbarriers:
-//   full[s]      aux -> compute   tile staged (expect_tx bytes landed)
-//   empty[s]     compute -> aux   all 8 warps are done reading stage s
-//   red_full[b]  compute -> aux   all 8 warps have written their flux contribution of a tile into red[b]
-//   red_empty[b] aux -> compute   red[b] has been reduced and may be overwritten
-template <int NA, bool READ_PSI, bool WRITE_PSI>
-__global__ void __launch_bounds__(kThreads, 2) sweep_kernel(const SweepArgs p, const ae_ctrl *ctrl, int gate)
-{
-    constexpr int kStages = StageCfg<NA>::stages;
-    constexpr int kSlots = (READ_PSI ? 3 + kAC * NA : 2);       // 2 KB slots per stage
+    constexpr int kStages = StageCfg<AC>::stages;
+    constexpr int kSlots = (READ_PSI ? 3 + AC : 2);             // 2 KB slots per stage
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *ring = reinterpret_cast<double *>(smem_raw);                    // [kStages][kSlots][kTile]
-    double *red = ring + kStages * kSlots * kTile;                          // [2][kAC][kTile]
-    uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * kAC * kTile);   // [kStages]
+    double *red = ring + kStages * kSlots * kTile;                          // [2][AC][kTile]
+    uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * AC * kTile);    // [kStages]
     uint64_t *empty = full + kStages;                                       // [kStages]
     uint64_t *red_full = empty + kStages;                                   // [2]
     uint64_t *red_empty = red_full + 2;                                     // [2]
@@ -294,8 +263,8 @@ __global__ void __launch_bounds__(kThreads, 2) sweep_kernel(const SweepArgs p, c
     SweepSync *sy = p.sync;
     if (tid == 0) {
         s_cta = (int)atomicInc(&sy->ticket, gridDim.x - 1);                // logical id in START order; self-resetting
-        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kAC); }
-        for (int b = 0; b < 2; ++b) { mbar_init(red_full + b, kAC); mbar_init(red_empty + b, 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, AC); }
+        for (int b = 0; b < 2; ++b) { mbar_init(red_full + b, AC); mbar_init(red_empty + b, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -307,41 +276,40 @@ __global__ void __launch_bounds__(kThreads, 2) sweep_kernel(const SweepArgs p, c
     const bool publishes = (t1 % nt) != 0;                                  // range ends inside a row block
     Cursor cur;
     cur.init(t0, t1, (int)nt);
+    RowCtx c;
+    int c_rb = -1;
 
-    if (warp == kAC) {
-        // ================= auxiliary warp: TMA producer + flux reducer =================================
-        Cursor pcur = cur;                                                  // runs kStages tiles ahead of `cur`
-        RowCtx<NA> pc, rc;
-        int pc_rb = -1, rc_rb = -1;
-        auto issue = [&]() {                                                // stage the tile under pcur
-            if (pcur.rb != pc_rb) { row_setup<NA>(p, pcur.rb, 0, pc); pc_rb = pcur.rb; }
-            const int64_t off = (int64_t)(pc.neg ? nt - 1 - pcur.ti : pcur.ti) * kTile;
-            const int st = (int)(pcur.j % kStages);
+    if (warp == AC + 1) {
+        // ================= producer warp: TMA ring =====================================================
+        for (int64_t j = 0; j < W; ++j, cur.advance()) {
+            if (cur.rb != c_rb) { row_setup<AC>(p, cur.rb, 0, c); c_rb = cur.rb; }
+            const int64_t off = (int64_t)(c.neg ? nt - 1 - cur.ti : cur.ti) * kTile;
+            const int st = (int)(j % kStages);
             double *dst = ring + (size_t)st * kSlots * kTile;
-            const int64_t goff = (int64_t)pc.g * p.Zp + off;
-            const int nslots = READ_PSI ? 3 + pc.nblk : 2;
-            mbar_wait(empty + st, (uint32_t)(((pcur.j / kStages) & 1) ^ 1));        // consumers released the stage
+            const int64_t goff = (int64_t)c.g * p.Zp + off;
+            const int nslots = READ_PSI ? 3 + c.nblk : 2;
+            mbar_wait(empty + st, (uint32_t)(((j / kStages) & 1) ^ 1));     // consumers released the stage
             if (lane == 0) mbar_expect_tx(full + st, (uint32_t)(nslots * kTileBytes));
             __syncwarp();
-            for (int l = lane; l < nslots; l += 32) {
-                const double *src = l == 0 ? p.hs + goff : l == 1 ? p.q + goff : l == 2 ? p.cdt + goff
-                                                                               : p.psi_in + pc.row + (int64_t)(l - 3) * p.Zp + off;
-                bulk_g2s(dst + l * kTile, src, kTileBytes, full + st);
+            if (lane < nslots) {
+                const double *src = lane == 0 ? p.hs + goff : lane == 1 ? p.q + goff : lane == 2 ? p.cdt + goff
+                                                                                   : p.psi_in + c.row + (int64_t)(lane - 3) * p.Zp + off;
+                bulk_g2s(dst + lane * kTile, src, kTileBytes, full + st);
             }
-            pcur.advance();
-        };
-        for (int64_t j = 0; j < kStages && j < W; ++j) issue();
+        }
+    } else if (warp == AC) {
+        // ================= reducer warp: partial scalar flux of the block ==============================
         for (int64_t j = 0; j < W; ++j, cur.advance()) {
-            if (cur.rb != rc_rb) { row_setup<NA>(p, cur.rb, 0, rc); rc_rb = cur.rb; }
-            const int64_t off = (int64_t)(rc.neg ? nt - 1 - cur.ti : cur.ti) * kTile;
+            if (cur.rb != c_rb) { row_setup<AC>(p, cur.rb, 0, c); c_rb = cur.rb; }
+            const int64_t off = (int64_t)(c.neg ? nt - 1 - cur.ti : cur.ti) * kTile;
             const int b = (int)(j & 1);
-            const double *rb_ = red + b * (kAC * kTile) + lane * 2;
+            const double *rb_ = red + b * (AC * kTile) + lane * 2;
             mbar_wait(red_full + b, (uint32_t)((j >> 1) & 1));
             double2 acc[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc[k] = *reinterpret_cast<const double2 *>(rb_ + k * 64);
 #pragma unroll
-            for (int w = 1; w < kAC; ++w)                                   // warps = angles in order (group.py:77)
+            for (int w = 1; w < AC; ++w)                                    // warps = angles in order (group.py:77)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const double2 v = *reinterpret_cast<const double2 *>(rb_ + w * kTile + k * 64);
@@ -349,63 +317,65 @@ __global__ void __launch_bounds__(kThreads, 2) sweep_kernel(const SweepArgs p, c
                 }
             __syncwarp();
             if (lane == 0) mbar_arrive(red_empty + b);
-            double *dst = p.partial + rc.poff + off + lane * 2;
+            double *dst = p.partial + c.poff + off + lane * 2;
 #pragma unroll
             for (int k = 0; k < 4; ++k) *reinterpret_cast<double2 *>(dst + k * 64) = acc[k];
-            if (j + kStages < W) issue();
         }
     } else {
         // ================= compute warps ==============================================================
-        RowCtx<NA> c;
-        int cur_rb = -1;
-        double carry[NA];
-#pragma unroll
-        for (int i = 0; i < NA; ++i) carry[i] = 0.0;
-        for (int64_t j = 0; j < W; ++j, cur.advance()) {
-            const int rb = cur.rb, ti = cur.ti;
-            if (rb != cur_rb || ti == 0) {
-                if (rb != cur_rb) { row_setup<NA>(p, rb, warp, c); cur_rb = rb; }
-#pragma unroll
-                for (int i = 0; i < NA; ++i) carry[i] = 0.0;                // vacuum boundary: group.py:48,54
-                if (ti != 0) {                                              // continue a row another CTA started
-#pragma unroll
-                    for (int i = 0; i < NA; ++i) {
-                        const int idx = i * kAC + warp;
-                        if (lane == 0 && idx < c.nblk) {
-                            while (ld_acquire(&sy->flag[cta - 1][idx]) != stamp) {}
-                            carry[i] = sy->carry[cta - 1][idx];
+        double carry = 0.0;
+        int64_t j = 0;
+        for (int piece = 0; piece < 2; ++piece) {
+            const int64_t jend = piece == 0 ? (cur.len_last < W ? cur.len_last : W) : W;
+            for (; j < jend; ++j, cur.advance()) {
+                const int rb = cur.rb, ti = cur.ti;
+                if (rb != c_rb || ti == 0) {
+                    if (rb != c_rb) { row_setup<AC>(p, rb, warp, c); c_rb = rb; }
+                    carry = 0.0;                                            // vacuum boundary: group.py:48,54
+                    if (ti != 0) {                                          // continue a row another CTA started
+                        if (lane == 0 && warp < c.nblk) {
+                            while (ld_acquire(&sy->flag[cta - 1][warp]) != stamp) {}
+                            carry = sy->carry[cta - 1][warp];
                         }
-                        carry[i] = __shfl_sync(0xffffffffu, carry[i], 0);
+                        carry = __shfl_sync(0xffffffffu, carry, 0);
                     }
                 }
+                const int st = (int)(j % kStages), b = (int)(j & 1);
+                const int64_t off = (int64_t)(c.neg ? nt - 1 - ti : ti) * kTile;
+                const double *stage = ring + (size_t)st * kSlots * kTile + lane * 2;
+                double ca[kL], cb[kL], f[kL];
+                mbar_wait(full + st, (uint32_t)((j / kStages) & 1));
+                tile_maps<READ_PSI>(stage, stage + kTile, stage + 2 * kTile, stage + (3 + warp) * kTile, c.m, c.two_m, ca, cb);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + st);                     // stage is in registers: release it
+                if (c.neg) tile_solve<true>(ca, cb, carry, f, lane);
+                else tile_solve<false>(ca, cb, carry, f, lane);
+                if (WRITE_PSI && warp < c.nblk) {
+                    double *pout = p.psi_out + c.row + (int64_t)warp * p.Zp + off + lane * 2;
+                    const bool ragged = off + kTile > p.Z;                  // only the last tile holds padding cells
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        double2 v = make_double2(0.5 * f[2 * k], 0.5 * f[2 * k + 1]);
+                        if (ragged) {
+                            const int64_t z = off + lane * kL + 2 * k;
+                            if (z >= p.Z) v.x = 0.0;
+                            if (z + 1 >= p.Z) v.y = 0.0;
+                        }
+                        st_stream(pout + k * 64, v);
+                    }
+                }
+                double *rw = red + b * (AC * kTile) + warp * kTile + lane * 2;
+                mbar_wait(red_empty + b, (uint32_t)(((j >> 1) & 1) ^ 1));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)                                 // 0.5*w_a*(in+out) = w_a*psi_mid, group.py:77
+                    *reinterpret_cast<double2 *>(rw + k * 64) = make_double2(c.hw * f[2 * k], c.hw * f[2 * k + 1]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(red_full + b);
             }
-            const int st = (int)(j % kStages), b = (int)(j & 1);
-            const int64_t off = (int64_t)(c.neg ? nt - 1 - ti : ti) * kTile;
-            const double *stage = ring + (size_t)st * kSlots * kTile + lane * 2;
-            double *rw = red + b * (kAC * kTile) + warp * kTile + lane * 2;
-            mbar_wait(full + st, (uint32_t)((j / kStages) & 1));
-            double acc[kL];
-            if (c.neg)
-                tile_body<NA, READ_PSI, WRITE_PSI, true>(stage, c, carry, acc, p.psi_out, off, p.Z, p.Zp, warp, lane);
-            else
-                tile_body<NA, READ_PSI, WRITE_PSI, false>(stage, c, carry, acc, p.psi_out, off, p.Z, p.Zp, warp, lane);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + st);                         // this warp is done with the stage
-            mbar_wait(red_empty + b, (uint32_t)(((j >> 1) & 1) ^ 1));
-#pragma unroll
-            for (int k = 0; k < 4; ++k) *reinterpret_cast<double2 *>(rw + k * 64) = make_double2(acc[2 * k], acc[2 * k + 1]);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(red_full + b);
-            // hand the carries to the CTA that continues this row (its range starts where ours ends)
-            if (publishes && j == cur.len_last - 1 && lane == 0) {
-#pragma unroll
-                for (int i = 0; i < NA; ++i) {
-                    const int idx = i * kAC + warp;
-                    if (idx < c.nblk) {
-                        sy->carry[cta][idx] = carry[i];
-                        st_release(&sy->flag[cta][idx], stamp);
-                    }
-                }
+            // after the head piece: hand the carries to the CTA that continues this row
+            if (piece == 0 && publishes && lane == 0 && warp < c.nblk) {
+                sy->carry[cta][warp] = carry;
+                st_release(&sy->flag[cta][warp], stamp);
             }
         }
     }
@@ -430,24 +400,30 @@ __global__ void reduce_partials_kernel(const double *partial, int P, int64_t Z, 
 }
 
 // angles per warp: 2 when a direction has enough angles to fill 16-angle blocks
-int angles_per_warp(int A, int n_neg)
+// Row-block shape.  AC = compute warps (angles) per CTA.  16-warp CTAs halve the per-update
+// traffic of the shared inputs (hs, q, cdt: 24/AC B) and of the partial flux (8/AC B) when a direction has
+// the angles to fill them; AE_ANGLES_PER_CTA (8 | 16) overrides for tuning.
+int block_angles(int A, int n_neg)
 {
-    static const char *force = getenv("AE_ANGLES_PER_WARP");             // tuning knob (1 or 2)
-    if (force && (force[0] == '1' || force[0] == '2')) return force[0] - '0';
-    (void)A; (void)n_neg;
-    return 1;
+    static const char *force = getenv("AE_ANGLES_PER_CTA");
+    const int side = n_neg > A - n_neg ? n_neg : A - n_neg;
+    int ac = side >= kACbig ? kACbig : kACsmall;
+    if (force && atoi(force) == kACsmall) ac = kACsmall;
+    if (force && atoi(force) == kACbig) ac = kACbig;
+    return ac;
 }
 
-template <int NA, bool RD, bool WR>
+template <int AC, bool RD, bool WR>
 static int launch_variant(const SweepArgs &p, const ae_ctrl *ctrl, int gate, cudaStream_t st)
 {
-    constexpr int slots = RD ? 3 + kAC * NA : 2;
-    const size_t smem = (size_t)(StageCfg<NA>::stages * slots + 2 * kAC) * kTileBytes + (2 * StageCfg<NA>::stages + 4) * sizeof(uint64_t);
+    constexpr int slots = RD ? 3 + AC : 2;
+    constexpr int threads = (AC + 2) * 32;
+    const size_t smem = (size_t)(StageCfg<AC>::stages * slots + 2 * AC) * kTileBytes + (2 * StageCfg<AC>::stages + 4) * sizeof(uint64_t);
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
-        AE_CUDA(cudaFuncSetAttribute((const void *)sweep_kernel<NA, RD, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AE_CUDA(cudaFuncSetAttribute((const void *)sweep_kernel<AC, RD, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int n = 0;
-        AE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sweep_kernel<NA, RD, WR>, kThreads, smem));
+        AE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sweep_kernel<AC, RD, WR>, threads, smem));
         if (n < 1) { set_error("sweep kernel does not fit on an SM"); return AE_CUDA_ERROR; }
         ctas_per_sm = n;
     }
@@ -459,19 +435,19 @@ static int launch_variant(const SweepArgs &p, const ae_ctrl *ctrl, int gate, cud
     const int64_t min_tiles = 4;                        // do not slice tiny problems thinner than this
     if (grid > (p.total_tiles + min_tiles - 1) / min_tiles) grid = (p.total_tiles + min_tiles - 1) / min_tiles;
     if (grid < 1) grid = 1;
-    sweep_kernel<NA, RD, WR><<<(unsigned)grid, kThreads, smem, st>>>(p, ctrl, gate);
+    sweep_kernel<AC, RD, WR><<<(unsigned)grid, threads, smem, st>>>(p, ctrl, gate);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }
 
-template <int NA>
-static int launch_na(const SweepArgs &p, const ae_ctrl *ctrl, int gate, cudaStream_t st)
+template <int AC>
+static int launch_shape(const SweepArgs &p, const ae_ctrl *ctrl, int gate, cudaStream_t st)
 {
     const bool rd = p.psi_in != nullptr, wr = p.psi_out != nullptr;
-    if (rd && wr) return launch_variant<NA, true, true>(p, ctrl, gate, st);
-    if (rd) return launch_variant<NA, true, false>(p, ctrl, gate, st);
-    if (wr) return launch_variant<NA, false, true>(p, ctrl, gate, st);
-    return launch_variant<NA, false, false>(p, ctrl, gate, st);
+    if (rd && wr) return launch_variant<AC, true, true>(p, ctrl, gate, st);
+    if (rd) return launch_variant<AC, true, false>(p, ctrl, gate, st);
+    if (wr) return launch_variant<AC, false, true>(p, ctrl, gate, st);
+    return launch_variant<AC, false, false>(p, ctrl, gate, st);
 }
 
 // internal launcher shared with the solver loops (gate: skip when ctrl->inner_done is set)
@@ -483,8 +459,8 @@ int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double
         return AE_BAD_ARG;
     }
     if (psi_in && !s->cdt) { set_error("ae_sweep_set: psi_in given but slab has no cdt"); return AE_BAD_ARG; }
-    const int na = angles_per_warp(s->A, s->n_neg);
-    const int blk = kAC * na;
+    const int ac = block_angles(s->A, s->n_neg);
+    const int blk = ac;
     SweepArgs p;
     p.hs = s->hs; p.cdt = s->cdt; p.q = q; p.mu_ihx = s->mu_ihx; p.wgt = s->wgt;
     p.psi_in = psi_in; p.psi_out = psi_out; p.partial = partial; p.sync = (SweepSync *)sync;
@@ -492,14 +468,14 @@ int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double
     p.nb_neg = (s->n_neg + blk - 1) / blk;
     p.nbg = p.nb_neg + (s->A - s->n_neg + blk - 1) / blk;
     p.total_tiles = (int64_t)s->G * p.nbg * (s->Zp / kTile);
-    return na == 2 ? launch_na<2>(p, ctrl, gate, st) : launch_na<1>(p, ctrl, gate, st);
+    return ac == kACbig ? launch_shape<kACbig>(p, ctrl, gate, st) : launch_shape<kACsmall>(p, ctrl, gate, st);
 }
 
 }  // namespace ae
 
 extern "C" int32_t ae_partial_count(int32_t A, int32_t n_neg)
 {
-    const int blk = ae::kAC * ae::angles_per_warp(A, n_neg);
+    const int blk = ae::block_angles(A, n_neg);
     return (n_neg + blk - 1) / blk + (A - n_neg + blk - 1) / blk;
 }
 

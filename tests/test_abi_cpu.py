@@ -45,8 +45,8 @@ def test_partial_count():
     assert lib.ae_partial_count(4, 2) == 2
     assert lib.ae_partial_count(16, 8) == 2
     assert lib.ae_sweep_sync_bytes() > 0
-    assert lib.ae_partial_count(196, 98) == 26
-    assert lib.ae_partial_count(64, 32) == 8
+    assert lib.ae_partial_count(196, 98) == 14
+    assert lib.ae_partial_count(64, 32) == 4
     assert lib.ae_partial_count(3, 0) == 1
 
 
