@@ -24,19 +24,20 @@ template <class Fin>
 __device__ __forceinline__ void grid_sum2(double num, double den, double *scratch, ae_ctrl *ctrl, double *sm, Fin fin)
 {
     __shared__ bool is_last;
+    const unsigned nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
     block_sum2(num, den, sm);
     if (threadIdx.x == 0) {
-        scratch[2 * blockIdx.x] = num;
-        scratch[2 * blockIdx.x + 1] = den;
+        scratch[2 * bid] = num;
+        scratch[2 * bid + 1] = den;
         __threadfence();
         const unsigned t = atomicAdd(&ctrl->ticket, 1u);
-        is_last = (t == gridDim.x - 1);
+        is_last = (t == nblocks - 1);
     }
     __syncthreads();
     if (is_last) {
         __threadfence();
         double a = 0.0, b = 0.0;
-        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+        for (int i = threadIdx.x; i < (int)nblocks; i += blockDim.x) {
             a += __ldcg(scratch + 2 * i);
             b += __ldcg(scratch + 2 * i + 1);
         }
@@ -136,34 +137,48 @@ __global__ void __launch_bounds__(kCB) finalize_small_kernel(const FinArgs p)
     if (!p.init) publish_change(p, num, den, red);
 }
 
-// G > kGSmall, step 1: phi := sum of partials (or cold), norm.  Elementwise over [G][Zp], 2 doubles/thread.
+// G > kGSmall, step 1: phi := sum of partials (or cold), norm.  Grid (x over cell pairs, y = group),
+// 2 doubles per thread and iteration; only the last tile of a row can hold padding cells.
+template <int PT>     // PT > 0: number of partials known at compile time (all loads in flight at once); 0: generic
 __global__ void __launch_bounds__(256) flux_assemble_kernel(const FinArgs p)
 {
     __shared__ double red[64];
     if (p.gate && p.ctrl->inner_done) return;
-    if (p.init && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (p.init && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
         p.ctrl->inner_done = 0;
         p.ctrl->inner_iters = 0;
         p.ctrl->ticket = 0;
     }
-    const int64_t n = (int64_t)p.G * p.Zp, n2 = n / 2;       // Zp is even
+    const int64_t n = (int64_t)p.G * p.Zp;
+    const int64_t row = (int64_t)blockIdx.y * p.Zp;
+    const int64_t half = p.Zp / 2;                           // Zp is even
     double num = 0.0, den = 0.0;
-    for (int64_t i2 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i2 < n2; i2 += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = 2 * i2;
+    for (int64_t s2 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s2 < half; s2 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t sidx = 2 * s2, i = row + sidx;
         double2 x;
         if (p.init) {
             x = make_double2(p.cold, p.cold);
         } else {
-            x = *reinterpret_cast<const double2 *>(p.partial + i);
-            for (int pp = 1; pp < p.P; ++pp) {
-                const double2 y = *reinterpret_cast<const double2 *>(p.partial + (int64_t)pp * n + i);
-                x.x += y.x; x.y += y.y;
+            if (PT > 0) {
+                double2 y[PT > 0 ? PT : 1];
+#pragma unroll
+                for (int u = 0; u < PT; ++u) y[u] = __ldcs(reinterpret_cast<const double2 *>(p.partial + (int64_t)u * n + i));
+                x = y[0];
+#pragma unroll
+                for (int u = 1; u < PT; ++u) { x.x += y[u].x; x.y += y[u].y; }      // block order
+            } else {
+                x = *reinterpret_cast<const double2 *>(p.partial + i);
+                for (int pp = 1; pp < p.P; ++pp) {
+                    const double2 y = *reinterpret_cast<const double2 *>(p.partial + (int64_t)pp * n + i);
+                    x.x += y.x; x.y += y.y;
+                }
             }
         }
-        const int64_t sidx = i % p.Zp;                       // both halves are cells lane*8+2k, +1 of one lane
-        const int64_t z = logical_cell(sidx);
-        if (z >= p.Z) x.x = 0.0;
-        if (z + 1 >= p.Z) x.y = 0.0;
+        if (sidx >= p.Zp - kTile) {                          // last tile: mask the padding cells
+            const int64_t z = logical_cell(sidx);            // the pair is cells z, z+1 of one lane
+            if (z >= p.Z) x.x = 0.0;
+            if (z + 1 >= p.Z) x.y = 0.0;
+        }
         if (!p.init) {
             const double2 o = *reinterpret_cast<const double2 *>(p.phi + i);
             const double dx = x.x - o.x, dy = x.y - o.y;     // group.py:78
@@ -175,43 +190,91 @@ __global__ void __launch_bounds__(256) flux_assemble_kernel(const FinArgs p)
     if (!p.init) publish_change(p, num, den, red);
 }
 
-// G > kGSmall, step 2: q_next[g][s] = base[g][s] + 0.5 * sum_g' phi[g'][s] * sigma_s[m(s)][g'][g].
-// Thread (x = cell, y = block of kGB output groups).  The phi column of a cell is shared by the
-// threadIdx.y threads of the CTA through L1; the scatter rows are warp-uniform L1 hits whenever
-// the 32 cells of a warp share a material (always, except at the 4 region interfaces).
+// G > kGSmall, step 2: q_next[g][s] = base[g][s] + 0.5 * sum_g' phi[g'][s] * sigma_s[m(s)][g'][g]
+// (group.py:73 / time_unit.py:53 with the scatter matrix of zone.py:48-51).
+// CTA = 128 consecutive cells x all groups; warp y owns the block of kGB = 8 output groups y and every lane
+// 4 cells (lane, +32, +64, +96), i.e. 32 accumulators per thread: per source group g' a thread issues 4
+// coalesced phi loads (shared by the warps of the CTA through L1) and 4 broadcast LDS.128 of the scatter
+// row, for 32 FMAs -- FP64-pipe bound instead of load-issue bound.  The scatter matrix of the tile's
+// material is staged once per CTA in shared memory (row stride padded to a multiple of 8); the rare
+// tile that straddles a material interface takes the per-cell global-memory path.
 constexpr int kGB = 8;
-__global__ void __launch_bounds__(256) scatter_source_kernel(const FinArgs p)
+constexpr int kSC = 128;                // cells per CTA
+constexpr int kSWarps = 10;             // warps per CTA (each loops over its group blocks)
+__global__ void __launch_bounds__(32 * kSWarps, 2) scatter_source_kernel(const FinArgs p)
 {
+    extern __shared__ double stab[];                            // [G][Gp] scatter matrix, then [G][kSC] phi tile
+    __shared__ int s_uniform;
     if (p.gate && p.ctrl->inner_done) return;
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int g0 = (blockIdx.y * blockDim.y + threadIdx.y) * kGB;
-    if (s >= p.Zp || g0 >= p.G) return;
-    const double *sc = p.scat + (size_t)p.mat[s] * p.G * p.G + g0;
-    const int ng = min(kGB, p.G - g0);
-    double acc[kGB];
-#pragma unroll
-    for (int j = 0; j < kGB; ++j) acc[j] = 0.0;
-    if (ng == kGB) {
-#pragma unroll 2
-        for (int gp = 0; gp < p.G; ++gp) {
-            const double x = p.phi[(int64_t)gp * p.Zp + s];
-#pragma unroll
-            for (int j = 0; j < kGB; ++j) acc[j] = fma(x, __ldg(sc + gp * p.G + j), acc[j]);
-        }
-    } else {
-        for (int gp = 0; gp < p.G; ++gp) {
-            const double x = p.phi[(int64_t)gp * p.Zp + s];
-#pragma unroll
-            for (int j = 0; j < kGB; ++j)
-                if (j < ng) acc[j] = fma(x, __ldg(sc + gp * p.G + j), acc[j]);
-        }
+    const int lane = threadIdx.x, gb = threadIdx.y, tid = gb * 32 + lane, nthr = blockDim.y * 32;
+    const int Gp = (p.G + kGB - 1) / kGB * kGB;
+    const int64_t s0 = (int64_t)blockIdx.x * kSC;
+    const int m0 = p.mat[s0];
+    if (tid == 0) s_uniform = 1;
+    __syncthreads();
+    for (int c = tid; c < kSC; c += nthr)
+        if (p.mat[s0 + c] != m0) s_uniform = 0;                 // benign race: everyone writes 0
+    const double *gtab = p.scat + (size_t)m0 * p.G * p.G;
+    for (int i = tid; i < p.G * Gp; i += nthr) {
+        const int gp = i / Gp, g = i % Gp;
+        stab[i] = g < p.G ? gtab[gp * p.G + g] : 0.0;
     }
+    double *sphi = stab + p.G * Gp;                             // [G][kSC]
+    for (int i = tid; i < p.G * (kSC / 2); i += nthr) {         // coalesced double2 rows of 128 cells
+        const int gp = i / (kSC / 2), c2 = i % (kSC / 2);
+        *reinterpret_cast<double2 *>(sphi + gp * kSC + 2 * c2) =
+            *reinterpret_cast<const double2 *>(p.phi + (int64_t)gp * p.Zp + s0 + 2 * c2);
+    }
+    __syncthreads();
+    const int gblocks = Gp / kGB;
+    const double *phi = sphi + lane;
+    for (int blk = gb; blk < gblocks; blk += blockDim.y) {
+        const int g0 = blk * kGB;
+        const int ng = min(kGB, p.G - g0);
+        double acc[4][kGB];
 #pragma unroll
-    for (int j = 0; j < kGB; ++j)
-        if (j < ng) {
-            const int64_t i = (int64_t)(g0 + j) * p.Zp + s;
-            p.q_next[i] = p.base[i] + 0.5 * acc[j];          // group.py:73 / time_unit.py:53
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int j = 0; j < kGB; ++j) acc[c][j] = 0.0;
+        if (s_uniform) {
+#pragma unroll 2
+            for (int gp = 0; gp < p.G; ++gp) {
+                double x[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) x[c] = phi[gp * kSC + 32 * c];
+                const double2 *row = reinterpret_cast<const double2 *>(stab + gp * Gp + g0);
+#pragma unroll
+                for (int j2 = 0; j2 < kGB / 2; ++j2) {
+                    const double2 t = row[j2];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        acc[c][2 * j2] = fma(x[c], t.x, acc[c][2 * j2]);
+                        acc[c][2 * j2 + 1] = fma(x[c], t.y, acc[c][2 * j2 + 1]);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double *sc = p.scat + (size_t)p.mat[s0 + lane + 32 * c] * p.G * p.G + g0;
+                for (int gp = 0; gp < p.G; ++gp) {
+                    const double x = phi[gp * kSC + 32 * c];
+#pragma unroll
+                    for (int j = 0; j < kGB; ++j)
+                        if (j < ng) acc[c][j] = fma(x, __ldg(sc + gp * p.G + j), acc[c][j]);
+                }
+            }
         }
+#pragma unroll
+        for (int j = 0; j < kGB; ++j)
+            if (j < ng) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int64_t i = (int64_t)(g0 + j) * p.Zp + s0 + lane + 32 * c;
+                    p.q_next[i] = p.base[i] + 0.5 * acc[c][j];
+                }
+            }
+    }
 }
 
 // base[g][s] = s_ext[g][s] + 0.5*chi[m][g] * sum_g' nusf[m][g'] * phi[g'][s]
@@ -312,17 +375,28 @@ int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, 
         AE_CUDA(cudaGetLastError());
         return AE_OK;
     }
-    const int64_t n2 = (int64_t)s->G * s->Zp / 2;
-    int blocks = (int)((n2 + 255) / 256);
-    const int cap = per_cell_blocks(s->Zp) * 2;          // norm_scratch holds 4 doubles per per-cell block
-    if (blocks > cap) blocks = cap;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    flux_assemble_kernel<<<blocks, 256, 0, st>>>(p);
+    // norm_scratch holds 4 doubles per per-cell block = room for 2*per_cell_blocks (num, den) pairs
+    int bx = (int)((s->Zp / 2 + 255) / 256);
+    const int cap = 2 * per_cell_blocks(s->Zp) / s->G;
+    if (bx > cap) bx = cap;
+    if (bx > (148 * 24 + s->G - 1) / s->G) bx = (148 * 24 + s->G - 1) / s->G;
+    if (bx < 1) bx = 1;
+    const dim3 ag(bx, s->G);
+    switch (init ? 0 : P) {
+        case 1: flux_assemble_kernel<1><<<ag, 256, 0, st>>>(p); break;
+        case 2: flux_assemble_kernel<2><<<ag, 256, 0, st>>>(p); break;
+        case 4: flux_assemble_kernel<4><<<ag, 256, 0, st>>>(p); break;
+        case 8: flux_assemble_kernel<8><<<ag, 256, 0, st>>>(p); break;
+        case 16: flux_assemble_kernel<16><<<ag, 256, 0, st>>>(p); break;
+        default: flux_assemble_kernel<0><<<ag, 256, 0, st>>>(p); break;
+    }
     AE_CUDA(cudaGetLastError());
     const int gblocks = (s->G + kGB - 1) / kGB;
-    const int by = gblocks < 8 ? gblocks : 8;            // 32 cells x by group-blocks per CTA
-    dim3 block(32, by), grid((unsigned)((s->Zp + 31) / 32), (gblocks + by - 1) / by);
-    scatter_source_kernel<<<grid, block, 0, st>>>(p);
+    const size_t smem = (size_t)s->G * (gblocks * kGB + kSC) * sizeof(double);
+    if (smem > 220 * 1024) { set_error("flux update: scatter matrix of G=%d does not fit in shared memory", s->G); return AE_BAD_ARG; }
+    if (smem > 48 * 1024)
+        AE_CUDA(cudaFuncSetAttribute((const void *)scatter_source_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scatter_source_kernel<<<(unsigned)(s->Zp / kSC), dim3(32, gblocks < kSWarps ? gblocks : kSWarps), smem, st>>>(p);   // Zp % 256 == 0
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }

@@ -432,8 +432,10 @@ static int launch_variant(const SweepArgs &p, const ae_ctrl *ctrl, int gate, cud
     AE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int64_t grid = (int64_t)sms * ctas_per_sm;
     if (grid > kMaxCtas) grid = kMaxCtas;
-    const int64_t min_tiles = 4;                        // do not slice tiny problems thinner than this
-    if (grid > (p.total_tiles + min_tiles - 1) / min_tiles) grid = (p.total_tiles + min_tiles - 1) / min_tiles;
+    // small problems: at least one CTA per row block (rows are the only parallelism), else >= 4 tiles per CTA
+    const int64_t rows = (int64_t)p.G * p.nbg, quarter = (p.total_tiles + 3) / 4;
+    const int64_t want = rows > quarter ? rows : quarter;
+    if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     sweep_kernel<AC, RD, WR><<<(unsigned)grid, threads, smem, st>>>(p, ctrl, gate);
     AE_CUDA(cudaGetLastError());

@@ -122,7 +122,7 @@ class SlabDevice:
         self.q0 = torch.zeros(n, **f64)
         self.q1 = torch.zeros(n, **f64)
         self.partial = torch.zeros(self.P * n, **f64)
-        self.scratch = torch.zeros(4 * int(self.lib.ae_norm_blocks(self.Zp)), **f64)
+        self.scratch = torch.zeros(4 * int(self.lib.ae_norm_blocks(self.Zp)) + 2 * self.G, **f64)
         self.sync = torch.zeros(int(self.lib.ae_sweep_sync_bytes()), dtype=torch.uint8, device=self.dev)
         self.ctrl = torch.zeros(C.sizeof(_lib.AeCtrl), dtype=torch.uint8, device=self.dev)
         self.ctrl_host = torch.zeros(C.sizeof(_lib.AeCtrl), dtype=torch.uint8).pin_memory()

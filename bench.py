@@ -184,12 +184,20 @@ def main():
         launches += 1
         if comm is not None:
             dev.lib.ae_reduce_partials(dev.slab, dev.partial.data_ptr(), dev.P, dev.partial.data_ptr(), dev.stream)
+            if ev is not None:
+                ev[2].record()
             comm.allreduce_(dev.partial[:n_phi])
+            if ev is not None:
+                ev[3].record()
             dev.flux_update(dev.partial, 1, q[(i + 1) & 1], 0.0, i + 1)
-            launches += 2
+            launches += 4                                   # reduce, (nccl), assemble, scatter
         else:
+            if ev is not None:
+                ev[2].record(); ev[3].record()
             dev.flux_update(dev.partial, dev.P, q[(i + 1) & 1], 0.0, i + 1)
-            launches += 1
+            launches += 2                                   # assemble, scatter
+        if ev is not None:
+            ev[4].record()
 
     def fence():
         if world > 1:
@@ -203,7 +211,7 @@ def main():
     if rank == 0:
         sampler.start()
     launches = 0
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
     t_beg.record()
@@ -213,11 +221,12 @@ def main():
     fence()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = t_beg.elapsed_time(t_end)
-    sweep_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    phase = [float(np.mean([e[k].elapsed_time(e[k + 1]) for e in evs])) for k in range(4)]
     if world > 1:
-        t = torch.tensor([ms_total, sweep_ms], dtype=torch.float64, device=dev.dev)
+        t = torch.tensor([ms_total] + phase, dtype=torch.float64, device=dev.dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, sweep_ms = float(t[0]), float(t[1])
+        ms_total, phase = float(t[0]), [float(x) for x in t[1:]]
+    sweep_ms = phase[0]
     ms_per_step = ms_total / args.steps
     value = updates_per_step / (ms_per_step * 1e-3)
     gpu_launches = launches
@@ -263,6 +272,8 @@ def main():
                          "frac": achieved / hbm_peak, "traffic": None, "kernel": "ae::sweep_kernel<NA,true,true>",
                          "kernel_ms": sweep_ms, "bytes_per_update": bytes_per_update, "peak_source": peak_src,
                          "sweep_share_of_step": sweep_ms / ms_per_step},
+            "breakdown_ms": {"sweep": phase[0], "reduce_partials": phase[1], "allreduce": phase[2],
+                             "flux_update": phase[3]},
             "e2e": {"value": updates_per_step / (e_ms * 1e-3), "unit": "updates/s", "ms_per_step": e_ms,
                     "h2d_bytes_per_step": Z * G * 8, "d2h_bytes_per_step": Z * G * 8,
                     "what": "host q (pinned) -> device, sweep set + flux update on resident psi, phi -> host"},

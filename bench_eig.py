@@ -1,0 +1,161 @@
+#!/usr/bin/env python
+"""Secondary benchmark: k- and alpha-eigenvalue wall time on the B200 path vs the CPU oracle port
+(BASELINE.json metric, second half: "alpha-eig wall time vs CPU"), plus the physics cross-checks.
+
+    python bench_eig.py [--skip-c3] [--out profiles/r01_eig_bench.jsonl]
+
+Cases
+  kp_k      Kornreich-Parsons k eigenvalue at the reference's three golden meshes (through the public classes)
+  kp_alpha  K-P time-dependent march + DMD (TimeUnit), alpha against the reference DMD routine fed the
+            oracle's snapshots, and against the published values of the reference's report (PDF Table 1)
+  c3_alpha  BASELINE configs[2]: synthetic 70-group slab, S64, 100k cells, 200 DMD snapshots on 1 B200
+            (phi snapshots; the angular flux history would need 716 GB)
+Every line is JSON; GPU times are wall-clock around the public call with a device synchronise.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GOLDEN_K = {(50, 4): 0.9358157950764868, (100, 16): 0.9885264464200719, (200, 196): 0.9900590623010896}
+REF_PY_SECONDS = {(50, 4): 2.57, (100, 16): 25.7, (200, 196): 666.7}       # BASELINE.md, literal reference, 1 core
+PDF_ALPHA = (-0.006166847, -0.006475483)                                    # report Table 1 (nu_sigma_f = 0.7)
+
+
+def sync():
+    import torch
+    torch.cuda.synchronize()
+
+
+def kp_group(cpm, A):
+    from alpha_eigen_modules.group import OneGroup
+    from alpha_eigen_modules.material import SimpleMaterial
+    from alpha_eigen_modules.slab import SymmetricHeterogeneousSlab
+    np.random.seed(2021)
+    f, m, a = SimpleMaterial('fuel', 1), SimpleMaterial('moderator', 1), SimpleMaterial('absorber', 1)
+    s = SymmetricHeterogeneousSlab(9, cpm, A, m, fuel_mat=f, abs_mat=a)
+    g = OneGroup(slab=s)
+    g.create_zones()
+    return s, g
+
+
+def case_kp_k(out):
+    from oracle import ae_oracle as orc
+    from tests.kp import kp_problem
+    for (cpm, A), gold in GOLDEN_K.items():
+        for rep in range(2):                                        # first call pays context / module load
+            s, g = kp_group(cpm, A)
+            sync(); t0 = time.perf_counter()
+            k = g.perform_power_iteration(quiet=True)
+            sync(); gpu_s = time.perf_counter() - t0
+        p = kp_problem(9, cpm, A)
+        t0 = time.perf_counter()
+        r = orc.power_iteration(p["mu"], p["weight"], p["hx"], p["tables"], p["phi0"])
+        cpu_s = time.perf_counter() - t0
+        out({"case": "kp_k", "cells_per_mfp": cpm, "num_angles": A, "k": k.old, "k_minus_golden": k.old - gold,
+             "k_minus_oracle": k.old - r["k_old"], "gpu_wall_s": gpu_s, "oracle_port_1core_s": cpu_s,
+             "reference_python_1core_s": REF_PY_SECONDS[(cpm, A)],
+             "updates": int(p["Z"] * A * sum(r["si_hist"]))})
+
+
+def case_kp_alpha(out, cpm, A, steps, check_oracle=True):
+    from alpha_eigen_modules.time_unit import TimeUnit
+    from oracle import ae_oracle as orc
+    from tests.kp import kp_problem, kp_psi0
+    for rep in range(2):
+        s, g = kp_group(cpm, A)
+        tu = TimeUnit(slab=s, group=g, num_steps=steps, dt=0.1)
+        sync(); t0 = time.perf_counter()
+        tu.calculate_time_dependent_flux()
+        sync(); t1 = time.perf_counter()
+        al, info = tu.compute_alpha_eigenvalues(return_info=True)
+        sync(); t2 = time.perf_counter()
+    srt = lambda a: np.asarray(a)[np.lexsort((np.asarray(a).imag, -np.asarray(a).real))]
+    al = srt(al)
+    line = {"case": "kp_alpha", "cells_per_mfp": cpm, "num_angles": A, "steps": steps, "dt": 0.1,
+            "alpha0": float(al[0].real), "alpha1": float(al[1].real) if len(al) > 1 else None, "rank": int(info["rank"]),
+            "gpu_march_s": t1 - t0, "gpu_dmd_s": t2 - t1,
+            "sweep_sets": int(np.sum(tu.inner_iterations)) + steps,
+            "pdf_table1_alpha": PDF_ALPHA}
+    if check_oracle:
+        p = kp_problem(9, cpm, A)
+        t0 = time.perf_counter()
+        res = orc.time_march(p["mu"], p["weight"], p["hx"], p["tables"], np.zeros((p["Z"], 1)), kp_psi0(p), 0.1, steps)
+        t1 = time.perf_counter()
+        ref = srt(orc.dmd_alpha_from_psi(res["psi_snap"], steps, 0.1))
+        t2 = time.perf_counter()
+        line.update({"oracle_march_1core_s": t1 - t0, "oracle_dmd_s": t2 - t1, "oracle_alpha0": float(ref[0].real),
+                     "oracle_rank": len(ref), "alpha0_rel_diff": float(abs(al[0] - ref[0]) / abs(ref[0])),
+                     "iterations_match": bool(np.array_equal(res["inner"], tu.inner_iterations)),
+                     "psi_rel_err": float(np.max(np.abs(tu.psi - res["psi_snap"])) / np.max(np.abs(res["psi_snap"])))})
+    out(line)
+
+
+def case_c3_alpha(out, Z=100_000, A=64, G=70, steps=200):
+    import torch
+    from alpha_eigen_b200.device import SlabDevice
+    from alpha_eigen_b200.synthetic import synthetic_problem
+    from alpha_eigen_b200.time_unit import dmd_window
+    p = synthetic_problem(Z, A, G)
+    dev = SlabDevice(Z, p["hx"], p["mu"], p["weight"], p["mat"], p["total"], p["scat"], p["chi"], p["nusf"],
+                     p["invspeed"], dt=0.1)
+    rs = np.random.RandomState(2021)
+    half = rs.rand(Z, G)
+    phi0 = half + half[::-1]                                         # phi.py:10-11
+    psi = torch.empty(dev.G * dev.A * dev.Zp, dtype=torch.float64, device=dev.dev)
+    iso = dev.cells_to_device(0.5 * phi0).view(G, 1, dev.Zp)
+    psi.view(G, dev.A, dev.Zp).copy_(iso.expand(G, dev.A, dev.Zp))   # isotropic psi0 = phi0/2
+    phi_snap = torch.zeros(steps * dev.G * dev.Zp, dtype=torch.float64, device=dev.dev)
+    sync(); t0 = time.perf_counter()
+    st, outer, inner = dev.time_march(psi, steps, 1e-10, None, phi_snap)
+    sync(); t1 = time.perf_counter()
+    first, K = dmd_window(steps)
+    R = dev.tsqr(phi_snap, dev.G * dev.Zp, first, K + 1)
+    al, sig, r = dev.dmd_from_r(R, K, 0.1)
+    sync(); t2 = time.perf_counter()
+    gram = dev.gram(phi_snap, dev.G * dev.Zp, first, K + 1)
+    alg, sigg, rg = dev.dmd_from_gram(gram, K, 0.1)
+    sync(); t3 = time.perf_counter()
+    srt = lambda a: np.asarray(a)[np.lexsort((np.asarray(a).imag, -np.asarray(a).real))]
+    sweeps = int(np.sum(inner)) + steps
+    out({"case": "c3_alpha", "Z": Z, "A": A, "G": G, "steps": steps, "status": int(st), "snapshots": "phi",
+         "outer_per_step": float(np.mean(outer)), "inner_per_step": float(np.mean(inner)), "sweep_sets": sweeps,
+         "updates": float(sweeps) * Z * A * G, "gpu_march_s": t1 - t0, "updates_per_s": float(sweeps) * Z * A * G / (t1 - t0),
+         "gpu_dmd_tsqr_s": t2 - t1, "gpu_dmd_gram_s": t3 - t2, "alpha0_tsqr": complex(srt(al)[0]).real,
+         "alpha0_gram": complex(srt(alg)[0]).real, "rank_tsqr": int(r), "rank_gram": int(rg),
+         "sigma_rel": [float(x) for x in (sig[:8] / sig[0])]})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "eig_bench.jsonl"))
+    ap.add_argument("--skip-c3", action="store_true")
+    ap.add_argument("--skip-long", action="store_true")
+    args = ap.parse_args()
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    f = open(args.out, "w")
+
+    def out(d):
+        s = json.dumps(d)
+        print(s, flush=True)
+        f.write(s + "\n")
+        f.flush()
+
+    case_kp_k(out)
+    case_kp_alpha(out, 10, 4, 50)
+    case_kp_alpha(out, 50, 16, 200)
+    if not args.skip_long:
+        case_kp_alpha(out, 200, 64, 200, check_oracle=False)
+    if not args.skip_c3:
+        case_c3_alpha(out)
+    f.close()
+
+
+if __name__ == "__main__":
+    main()

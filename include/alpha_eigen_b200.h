@@ -74,7 +74,7 @@ typedef struct ae_work {
     double *base;            /* [G][Zp] source that is fixed during the inner iteration */
     double *q0, *q1;         /* [G][Zp] ping-pong isotropic sweep source */
     double *partial;         /* [P][G][Zp] per-angle-block partial scalar flux */
-    double *norm_scratch;    /* [4 * ae_norm_blocks(Zp)] */
+    double *norm_scratch;    /* [4 * ae_norm_blocks(Zp) + 2 * G] */
     ae_ctrl *ctrl;           /* device */
     ae_ctrl *ctrl_host;      /* pinned host */
     void *sweep_sync;        /* device, ae_sweep_sync_bytes() bytes, zero-filled once */
