@@ -31,8 +31,9 @@ class AeSlab(C.Structure):
 
 
 class AeWork(C.Structure):
-    _fields_ = [("phi", C.c_void_p), ("phi_outer", C.c_void_p), ("base", C.c_void_p), ("q0", C.c_void_p),
-                ("q1", C.c_void_p), ("partial", C.c_void_p), ("norm_scratch", C.c_void_p), ("ctrl", C.c_void_p),
+    _fields_ = [("phi", C.c_void_p), ("phi_alt", C.c_void_p), ("phi_outer", C.c_void_p), ("base", C.c_void_p),
+                ("q0", C.c_void_p), ("q1", C.c_void_p), ("partial", C.c_void_p), ("reduced", C.c_void_p),
+                ("norm_scratch", C.c_void_p), ("ctrl", C.c_void_p),
                 ("ctrl_host", C.c_void_p), ("sweep_sync", C.c_void_p), ("comm", C.c_void_p), ("P", C.c_int32), ("batch", C.c_int32)]
 
 

@@ -10,8 +10,8 @@
 namespace ae {
 int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double *psi_out, double *partial,
                  void *sync, const ae_ctrl *ctrl, int gate, cudaStream_t st);
-int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, double *q_next, int init,
-                    double cold, double tol, int iteration, int gate, cudaStream_t st);
+int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, const double *phi_in, double *phi_out,
+                    double *q_next, int init, double cold, double tol, int iteration, int gate, cudaStream_t st);
 int launch_fission_base(const ae_slab *s, const double *phi, double *base, cudaStream_t st);
 int launch_k_update(const ae_slab *s, ae_work *w, double tol, int iteration, cudaStream_t st);
 int launch_outer_check(const ae_slab *s, ae_work *w, cudaStream_t st);
@@ -26,54 +26,55 @@ static int poll_ctrl(ae_work *w, cudaStream_t st)
 
 static int check_work(const ae_slab *s, const ae_work *w, const char *who)
 {
-    if (!s || !w || !w->phi || !w->phi_outer || !w->base || !w->q0 || !w->q1 || !w->partial || !w->norm_scratch ||
+    if (!s || !w || !w->phi || !w->phi_alt || !w->phi_outer || !w->base || !w->q0 || !w->q1 || !w->partial || !w->norm_scratch ||
         !w->ctrl || !w->ctrl_host || !w->sweep_sync || w->P != ae_partial_count(s->A, s->n_neg)) {
         set_error("%s: incomplete ae_work / ae_slab", who);
         return AE_BAD_ARG;
     }
+    if (w->comm && !w->reduced) { set_error("%s: multi-GPU work needs the `reduced` buffer", who); return AE_BAD_ARG; }
     return AE_OK;
 }
 
-// group.py:62-81 / time_unit.py:44-59
+// group.py:62-81 / time_unit.py:44-59.  The flux iterate ping-pongs between w->phi and w->phi_alt (the
+// update kernel must not read and write the same buffer); on return w->phi is the converged flux.
 static int source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, double cold, double tol,
                             int max_iterations, int *iters, int *last_q, cudaStream_t st)
 {
     double *q[2] = {w->q0, w->q1};
+    double *phi[2] = {w->phi, w->phi_alt};
     const int batch = w->batch > 0 ? w->batch : 1;
     // phi_old = cold (group.py:66 / time_unit.py:45); q0 = base + 0.5*sigma_s*phi_old (group.py:73)
-    AE_TRY(launch_finalize(s, w, nullptr, 0, q[0], 1, cold, tol, 0, 0, st));
+    AE_TRY(launch_finalize(s, w, nullptr, 0, nullptr, phi[0], q[0], 1, cold, tol, 0, 0, st));
     int it = 0;         // iterations launched so far
+    int status = AE_OK, n_done = 0;
     for (;;) {
         // `assert iteration < max_iterations` (group.py:72) fires when iteration reaches the cap
         const int room = (max_iterations - 1) - it;
-        if (room <= 0) {
-            if (iters) *iters = it;
-            if (last_q) *last_q = (it - 1) & 1;
-            return AE_NOT_CONVERGED;
-        }
+        if (room <= 0) { status = AE_NOT_CONVERGED; n_done = it; break; }
         const int nb = batch < room ? batch : room;
         for (int b = 0; b < nb; ++b) {
             const int i = it + b;                       // 0-based; reference iteration number is i+1
             const int gate = b > 0;                     // first of a batch always runs
             AE_TRY(launch_sweep(s, q[i & 1], psi_in, nullptr, w->partial, w->sweep_sync, w->ctrl, gate, st));
             if (w->comm) {
-                // angle-sharded ranks: local partial sum -> NCCL sum over ranks -> same finalize on every rank
-                AE_TRY(ae_reduce_partials(s, w->partial, w->P, w->partial, st));
-                AE_TRY(ae_comm_allreduce_sum(w->comm, w->partial, (int64_t)s->G * s->Zp, st));
-                AE_TRY(launch_finalize(s, w, w->partial, 1, q[(i + 1) & 1], 0, cold, tol, i + 1, gate, st));
+                // angle-sharded ranks: local partial sum -> NCCL sum over ranks -> same update on every rank
+                AE_TRY(ae_reduce_partials(s, w->partial, w->P, w->reduced, st));
+                AE_TRY(ae_comm_allreduce_sum(w->comm, w->reduced, (int64_t)s->G * s->Zp, st));
+                AE_TRY(launch_finalize(s, w, w->reduced, 1, phi[i & 1], phi[(i + 1) & 1], q[(i + 1) & 1], 0, cold, tol,
+                                       i + 1, gate, st));
             } else {
-                AE_TRY(launch_finalize(s, w, w->partial, w->P, q[(i + 1) & 1], 0, cold, tol, i + 1, gate, st));
+                AE_TRY(launch_finalize(s, w, w->partial, w->P, phi[i & 1], phi[(i + 1) & 1], q[(i + 1) & 1], 0, cold, tol,
+                                       i + 1, gate, st));
             }
         }
         AE_TRY(poll_ctrl(w, st));
-        if (w->ctrl_host->inner_done) {
-            const int n = w->ctrl_host->inner_iters;
-            if (iters) *iters = n;
-            if (last_q) *last_q = (n - 1) & 1;          // the sweep of iteration n read q[(n-1)&1]
-            return AE_OK;
-        }
+        if (w->ctrl_host->inner_done) { n_done = w->ctrl_host->inner_iters; break; }
         it += nb;
     }
+    if (iters) *iters = n_done;
+    if (last_q) *last_q = (n_done - 1) & 1;             // the sweep of iteration n read q[(n-1)&1]
+    if (n_done & 1) { w->phi = phi[1]; w->phi_alt = phi[0]; }   // iteration n wrote phi[n&1]
+    return status;
 }
 
 }  // namespace ae
@@ -85,7 +86,9 @@ extern "C" int ae_flux_update(const ae_slab *s, ae_work *w, const double *partia
 {
     AE_TRY(check_work(s, w, "ae_flux_update"));
     if (!partial || !q_next || P < 1) { set_error("ae_flux_update: bad argument"); return AE_BAD_ARG; }
-    return launch_finalize(s, w, partial, P, q_next, 0, 0.0, tol, iteration, 0, (cudaStream_t)stream);
+    AE_TRY(launch_finalize(s, w, partial, P, w->phi, w->phi_alt, q_next, 0, 0.0, tol, iteration, 0, (cudaStream_t)stream));
+    double *t = w->phi; w->phi = w->phi_alt; w->phi_alt = t;      // w->phi is always the newest iterate
+    return AE_OK;
 }
 
 extern "C" int ae_source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, double cold_start, double tol,

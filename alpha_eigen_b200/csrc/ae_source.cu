@@ -10,6 +10,7 @@
 // fission chi_g * sum_g' nu_sigma_f_g' phi_g').  All per-cell arrays are [G][Zp] in the
 // lane-blocked storage order; none of these kernels couples neighbouring cells, so the order
 // is irrelevant here and every access is stride-1 across the threads of a warp.
+#include <stdlib.h>
 #include "ae_common.cuh"
 
 namespace ae {
@@ -54,7 +55,9 @@ struct FinArgs {
     const double *base;         // [G][Zp]
     const int32_t *mat;         // [Zp]
     const double *scat;         // [M][G][G]
-    double *phi;                // [G][Zp] in: previous iterate, out: new iterate
+    const double *phi_in;       // [G][Zp] previous iterate
+    double *phi;                // [G][Zp] new iterate.  A different buffer: on B200 reading and then writing the
+                                // same addresses in one streaming kernel runs at 2.4 TB/s instead of 6.8 (tools/stride_probe.cu)
     double *q_next;             // [G][Zp]
     double *scratch;
     ae_ctrl *ctrl;
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(kCB) finalize_small_kernel(const FinArgs p)
                 }
                 if (!valid) x = 0.0;
                 if (!p.init) {
-                    const double d = x - p.phi[i];      // group.py:78
+                    const double d = x - p.phi_in[i];   // group.py:78
                     num = fma(d, d, num);
                     den = fma(x, x, den);
                 }
@@ -137,57 +140,43 @@ __global__ void __launch_bounds__(kCB) finalize_small_kernel(const FinArgs p)
     if (!p.init) publish_change(p, num, den, red);
 }
 
-// G > kGSmall, step 1: phi := sum of partials (or cold), norm.  Grid (x over cell pairs, y = group),
-// 2 doubles per thread and iteration; only the last tile of a row can hold padding cells.
-template <int PT>     // PT > 0: number of partials known at compile time (all loads in flight at once); 0: generic
-__global__ void __launch_bounds__(256) flux_assemble_kernel(const FinArgs p)
+// G > kGSmall, step 1: phi := sum of partials (or cold), norm.  Flat grid-stride over [G][Zp], one double2
+// per thread and iteration, <= 32 registers so 64 warps per SM with ~4 loads each are in flight: a P-buffer
+// sum needs ~100 KB per SM in flight to stream at 6.5-7 TB/s on B200 (tools/stride_probe.cu).  Padding
+// cells need no masking here: the sweep writes exact zeros there.
+__global__ void __launch_bounds__(256, 6) flux_assemble_kernel(const FinArgs p)
 {
     __shared__ double red[64];
     if (p.gate && p.ctrl->inner_done) return;
-    if (p.init && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    const int64_t n = (int64_t)p.G * p.Zp;
+    double num = 0.0, den = 0.0;
+    for (int64_t i = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 2 * (int64_t)gridDim.x * blockDim.x) {
+        double2 x = *reinterpret_cast<const double2 *>(p.partial + i);
+#pragma unroll 4
+        for (int pp = 1; pp < p.P; ++pp) {                       // block order (group.py:77 over angle blocks)
+            const double2 y = *reinterpret_cast<const double2 *>(p.partial + (int64_t)pp * n + i);
+            x.x += y.x; x.y += y.y;
+        }
+        const double2 o = *reinterpret_cast<const double2 *>(p.phi_in + i);
+        const double dx = x.x - o.x, dy = x.y - o.y;             // group.py:78
+        num = fma(dx, dx, fma(dy, dy, num));
+        den = fma(x.x, x.x, fma(x.y, x.y, den));
+        *reinterpret_cast<double2 *>(p.phi + i) = x;             // group.py:80
+    }
+    publish_change(p, num, den, red);
+}
+
+// Cold start of the inner iteration: phi := cold on real cells, 0 on padding (group.py:66 / time_unit.py:45).
+__global__ void flux_init_kernel(const FinArgs p)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.ctrl->inner_done = 0;
         p.ctrl->inner_iters = 0;
         p.ctrl->ticket = 0;
     }
     const int64_t n = (int64_t)p.G * p.Zp;
-    const int64_t row = (int64_t)blockIdx.y * p.Zp;
-    const int64_t half = p.Zp / 2;                           // Zp is even
-    double num = 0.0, den = 0.0;
-    for (int64_t s2 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s2 < half; s2 += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t sidx = 2 * s2, i = row + sidx;
-        double2 x;
-        if (p.init) {
-            x = make_double2(p.cold, p.cold);
-        } else {
-            if (PT > 0) {
-                double2 y[PT > 0 ? PT : 1];
-#pragma unroll
-                for (int u = 0; u < PT; ++u) y[u] = __ldcs(reinterpret_cast<const double2 *>(p.partial + (int64_t)u * n + i));
-                x = y[0];
-#pragma unroll
-                for (int u = 1; u < PT; ++u) { x.x += y[u].x; x.y += y[u].y; }      // block order
-            } else {
-                x = *reinterpret_cast<const double2 *>(p.partial + i);
-                for (int pp = 1; pp < p.P; ++pp) {
-                    const double2 y = *reinterpret_cast<const double2 *>(p.partial + (int64_t)pp * n + i);
-                    x.x += y.x; x.y += y.y;
-                }
-            }
-        }
-        if (sidx >= p.Zp - kTile) {                          // last tile: mask the padding cells
-            const int64_t z = logical_cell(sidx);            // the pair is cells z, z+1 of one lane
-            if (z >= p.Z) x.x = 0.0;
-            if (z + 1 >= p.Z) x.y = 0.0;
-        }
-        if (!p.init) {
-            const double2 o = *reinterpret_cast<const double2 *>(p.phi + i);
-            const double dx = x.x - o.x, dy = x.y - o.y;     // group.py:78
-            num = fma(dx, dx, fma(dy, dy, num));
-            den = fma(x.x, x.x, fma(x.y, x.y, den));
-        }
-        *reinterpret_cast<double2 *>(p.phi + i) = x;         // group.py:80
-    }
-    if (!p.init) publish_change(p, num, den, red);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p.phi[i] = logical_cell(i % p.Zp) < p.Z ? p.cold : 0.0;
 }
 
 // G > kGSmall, step 2: q_next[g][s] = base[g][s] + 0.5 * sum_g' phi[g'][s] * sigma_s[m(s)][g'][g]
@@ -208,72 +197,80 @@ __global__ void __launch_bounds__(32 * kSWarps, 2) scatter_source_kernel(const F
     if (p.gate && p.ctrl->inner_done) return;
     const int lane = threadIdx.x, gb = threadIdx.y, tid = gb * 32 + lane, nthr = blockDim.y * 32;
     const int Gp = (p.G + kGB - 1) / kGB * kGB;
-    const int64_t s0 = (int64_t)blockIdx.x * kSC;
-    const int m0 = p.mat[s0];
-    if (tid == 0) s_uniform = 1;
-    __syncthreads();
-    for (int c = tid; c < kSC; c += nthr)
-        if (p.mat[s0 + c] != m0) s_uniform = 0;                 // benign race: everyone writes 0
-    const double *gtab = p.scat + (size_t)m0 * p.G * p.G;
-    for (int i = tid; i < p.G * Gp; i += nthr) {
-        const int gp = i / Gp, g = i % Gp;
-        stab[i] = g < p.G ? gtab[gp * p.G + g] : 0.0;
-    }
-    double *sphi = stab + p.G * Gp;                             // [G][kSC]
-    for (int i = tid; i < p.G * (kSC / 2); i += nthr) {         // coalesced double2 rows of 128 cells
-        const int gp = i / (kSC / 2), c2 = i % (kSC / 2);
-        *reinterpret_cast<double2 *>(sphi + gp * kSC + 2 * c2) =
-            *reinterpret_cast<const double2 *>(p.phi + (int64_t)gp * p.Zp + s0 + 2 * c2);
-    }
-    __syncthreads();
     const int gblocks = Gp / kGB;
+    double *sphi = stab + p.G * Gp;                             // [G][kSC]
     const double *phi = sphi + lane;
-    for (int blk = gb; blk < gblocks; blk += blockDim.y) {
-        const int g0 = blk * kGB;
-        const int ng = min(kGB, p.G - g0);
-        double acc[4][kGB];
+    int staged = -1;                                            // material whose matrix is in stab
+    // persistent CTA: the scatter matrix is restaged only when the tile's material changes (5 regions)
+    for (int64_t tile = blockIdx.x; tile < p.Zp / kSC; tile += gridDim.x) {
+        const int64_t s0 = tile * kSC;
+        const int m0 = p.mat[s0];
+        __syncthreads();                                        // previous tile fully consumed
+        if (tid == 0) s_uniform = 1;
+        __syncthreads();
+        for (int c = tid; c < kSC; c += nthr)
+            if (p.mat[s0 + c] != m0) s_uniform = 0;             // benign race: everyone writes 0
+        if (m0 != staged) {
+            const double *gtab = p.scat + (size_t)m0 * p.G * p.G;
+            for (int i = tid; i < p.G * Gp; i += nthr) {
+                const int gp = i / Gp, g = i % Gp;
+                stab[i] = g < p.G ? gtab[gp * p.G + g] : 0.0;
+            }
+            staged = m0;
+        }
+        for (int i = tid; i < p.G * (kSC / 2); i += nthr) {     // coalesced double2 rows of 128 cells
+            const int gp = i / (kSC / 2), c2 = i % (kSC / 2);
+            *reinterpret_cast<double2 *>(sphi + gp * kSC + 2 * c2) =
+                *reinterpret_cast<const double2 *>(p.phi + (int64_t)gp * p.Zp + s0 + 2 * c2);
+        }
+        __syncthreads();
+        for (int blk = gb; blk < gblocks; blk += blockDim.y) {
+            const int g0 = blk * kGB;
+            const int ng = min(kGB, p.G - g0);
+            double acc[4][kGB];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int j = 0; j < kGB; ++j) acc[c][j] = 0.0;
-        if (s_uniform) {
+                for (int j = 0; j < kGB; ++j) acc[c][j] = 0.0;
+            if (s_uniform) {
 #pragma unroll 2
-            for (int gp = 0; gp < p.G; ++gp) {
-                double x[4];
+                for (int gp = 0; gp < p.G; ++gp) {
+                    double x[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) x[c] = phi[gp * kSC + 32 * c];
-                const double2 *row = reinterpret_cast<const double2 *>(stab + gp * Gp + g0);
+                    for (int c = 0; c < 4; ++c) x[c] = phi[gp * kSC + 32 * c];
+                    const double2 *row = reinterpret_cast<const double2 *>(stab + gp * Gp + g0);
 #pragma unroll
-                for (int j2 = 0; j2 < kGB / 2; ++j2) {
-                    const double2 t = row[j2];
+                    for (int j2 = 0; j2 < kGB / 2; ++j2) {
+                        const double2 t = row[j2];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        acc[c][2 * j2] = fma(x[c], t.x, acc[c][2 * j2]);
-                        acc[c][2 * j2 + 1] = fma(x[c], t.y, acc[c][2 * j2 + 1]);
+                        for (int c = 0; c < 4; ++c) {
+                            acc[c][2 * j2] = fma(x[c], t.x, acc[c][2 * j2]);
+                            acc[c][2 * j2 + 1] = fma(x[c], t.y, acc[c][2 * j2 + 1]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double *sc = p.scat + (size_t)p.mat[s0 + lane + 32 * c] * p.G * p.G + g0;
+                    for (int gp = 0; gp < p.G; ++gp) {
+                        const double x = phi[gp * kSC + 32 * c];
+#pragma unroll
+                        for (int j = 0; j < kGB; ++j)
+                            if (j < ng) acc[c][j] = fma(x, __ldg(sc + gp * p.G + j), acc[c][j]);
                     }
                 }
             }
-        } else {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const double *sc = p.scat + (size_t)p.mat[s0 + lane + 32 * c] * p.G * p.G + g0;
-                for (int gp = 0; gp < p.G; ++gp) {
-                    const double x = phi[gp * kSC + 32 * c];
+            for (int j = 0; j < kGB; ++j)
+                if (j < ng) {
 #pragma unroll
-                    for (int j = 0; j < kGB; ++j)
-                        if (j < ng) acc[c][j] = fma(x, __ldg(sc + gp * p.G + j), acc[c][j]);
+                    for (int c = 0; c < 4; ++c) {
+                        const int64_t i = (int64_t)(g0 + j) * p.Zp + s0 + lane + 32 * c;
+                        p.q_next[i] = p.base[i] + 0.5 * acc[c][j];
+                    }
                 }
-            }
         }
-#pragma unroll
-        for (int j = 0; j < kGB; ++j)
-            if (j < ng) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int64_t i = (int64_t)(g0 + j) * p.Zp + s0 + lane + 32 * c;
-                    p.q_next[i] = p.base[i] + 0.5 * acc[c][j];
-                }
-            }
     }
 }
 
@@ -363,11 +360,12 @@ __global__ void ctrl_init_kernel(ae_ctrl *ctrl)
 
 static int per_cell_blocks(int64_t Zp) { return (int)((Zp + kCB - 1) / kCB); }
 
-int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, double *q_next, int init,
-                    double cold, double tol, int iteration, int gate, cudaStream_t st)
+int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, const double *phi_in, double *phi_out,
+                    double *q_next, int init, double cold, double tol, int iteration, int gate, cudaStream_t st)
 {
     FinArgs p;
-    p.partial = partial; p.base = w->base; p.mat = s->mat; p.scat = s->scat; p.phi = w->phi; p.q_next = q_next;
+    p.partial = partial; p.base = w->base; p.mat = s->mat; p.scat = s->scat; p.phi_in = phi_in; p.phi = phi_out;
+    p.q_next = q_next;
     p.scratch = w->norm_scratch; p.ctrl = w->ctrl; p.Z = s->Z; p.Zp = s->Zp; p.P = P; p.G = s->G; p.M = s->M;
     p.init = init; p.gate = gate; p.iteration = iteration; p.cold = cold; p.tol = tol;
     if (s->G <= kGSmall) {
@@ -376,27 +374,21 @@ int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, 
         return AE_OK;
     }
     // norm_scratch holds 4 doubles per per-cell block = room for 2*per_cell_blocks (num, den) pairs
-    int bx = (int)((s->Zp / 2 + 255) / 256);
-    const int cap = 2 * per_cell_blocks(s->Zp) / s->G;
+    int64_t bx = ((int64_t)s->G * s->Zp / 2 + 255) / 256;
+    const int64_t cap = 2 * (int64_t)per_cell_blocks(s->Zp);    // norm_scratch holds that many (num, den) pairs
     if (bx > cap) bx = cap;
-    if (bx > (148 * 24 + s->G - 1) / s->G) bx = (148 * 24 + s->G - 1) / s->G;
-    if (bx < 1) bx = 1;
-    const dim3 ag(bx, s->G);
-    switch (init ? 0 : P) {
-        case 1: flux_assemble_kernel<1><<<ag, 256, 0, st>>>(p); break;
-        case 2: flux_assemble_kernel<2><<<ag, 256, 0, st>>>(p); break;
-        case 4: flux_assemble_kernel<4><<<ag, 256, 0, st>>>(p); break;
-        case 8: flux_assemble_kernel<8><<<ag, 256, 0, st>>>(p); break;
-        case 16: flux_assemble_kernel<16><<<ag, 256, 0, st>>>(p); break;
-        default: flux_assemble_kernel<0><<<ag, 256, 0, st>>>(p); break;
-    }
+    if (bx > 148 * 32) bx = 148 * 32;
+    if (init) flux_init_kernel<<<(unsigned)bx, 256, 0, st>>>(p);
+    else flux_assemble_kernel<<<(unsigned)bx, 256, 0, st>>>(p);
     AE_CUDA(cudaGetLastError());
     const int gblocks = (s->G + kGB - 1) / kGB;
     const size_t smem = (size_t)s->G * (gblocks * kGB + kSC) * sizeof(double);
     if (smem > 220 * 1024) { set_error("flux update: scatter matrix of G=%d does not fit in shared memory", s->G); return AE_BAD_ARG; }
     if (smem > 48 * 1024)
         AE_CUDA(cudaFuncSetAttribute((const void *)scatter_source_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    scatter_source_kernel<<<(unsigned)(s->Zp / kSC), dim3(32, gblocks < kSWarps ? gblocks : kSWarps), smem, st>>>(p);   // Zp % 256 == 0
+    int64_t sgrid = s->Zp / kSC;                         // Zp % 256 == 0
+    if (sgrid > 148 * 2) sgrid = 148 * 2;
+    scatter_source_kernel<<<(unsigned)sgrid, dim3(32, gblocks < kSWarps ? gblocks : kSWarps), smem, st>>>(p);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }

@@ -350,19 +350,15 @@ __global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_k
                 if (lane == 0) mbar_arrive(empty + st);                     // stage is in registers: release it
                 if (c.neg) tile_solve<true>(ca, cb, carry, f, lane);
                 else tile_solve<false>(ca, cb, carry, f, lane);
+                if (off + kTile > p.Z) {                                    // only the last tile holds padding cells:
+#pragma unroll
+                    for (int jj = 0; jj < kL; ++jj)                         // exact zeros there, in psi and in the flux
+                        if (off + lane * kL + jj >= p.Z) f[jj] = 0.0;
+                }
                 if (WRITE_PSI && warp < c.nblk) {
                     double *pout = p.psi_out + c.row + (int64_t)warp * p.Zp + off + lane * 2;
-                    const bool ragged = off + kTile > p.Z;                  // only the last tile holds padding cells
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        double2 v = make_double2(0.5 * f[2 * k], 0.5 * f[2 * k + 1]);
-                        if (ragged) {
-                            const int64_t z = off + lane * kL + 2 * k;
-                            if (z >= p.Z) v.x = 0.0;
-                            if (z + 1 >= p.Z) v.y = 0.0;
-                        }
-                        st_stream(pout + k * 64, v);
-                    }
+                    for (int k = 0; k < 4; ++k) st_stream(pout + k * 64, make_double2(0.5 * f[2 * k], 0.5 * f[2 * k + 1]));
                 }
                 double *rw = red + b * (AC * kTile) + warp * kTile + lane * 2;
                 mbar_wait(red_empty + b, (uint32_t)(((j >> 1) & 1) ^ 1));
@@ -387,19 +383,21 @@ __global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_k
     }
 }
 
-// phi[g][s] = sum_p partial[p][g][s]; padding cells -> 0
-__global__ void reduce_partials_kernel(const double *partial, int P, int64_t Z, int64_t Zp, int G,
-                                       double *phi)   // phi may alias partial[0]
+// phi[g][s] = sum_p partial[p][g][s] (padding cells are already exact zeros in every partial).  Flat, low
+// register count for high occupancy (see flux_assemble_kernel).  phi may alias partial[0].
+__global__ void __launch_bounds__(256, 8) reduce_partials_kernel(const double *partial, int P, int64_t n, double *phi)
 {
-    const int64_t n = (int64_t)G * Zp;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double s = partial[i];
-        for (int p = 1; p < P; ++p) s += partial[(int64_t)p * n + i];
-        phi[i] = logical_cell(i % Zp) < Z ? s : 0.0;
+    for (int64_t i = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 2 * (int64_t)gridDim.x * blockDim.x) {
+        double2 x = *reinterpret_cast<const double2 *>(partial + i);
+#pragma unroll 4
+        for (int pp = 1; pp < P; ++pp) {
+            const double2 y = *reinterpret_cast<const double2 *>(partial + (int64_t)pp * n + i);
+            x.x += y.x; x.y += y.y;
+        }
+        *reinterpret_cast<double2 *>(phi + i) = x;
     }
 }
 
-// angles per warp: 2 when a direction has enough angles to fill 16-angle blocks
 // Row-block shape.  AC = compute warps (angles) per CTA.  16-warp CTAs halve the per-update
 // traffic of the shared inputs (hs, q, cdt: 24/AC B) and of the partial flux (8/AC B) when a direction has
 // the angles to fill them; AE_ANGLES_PER_CTA (8 | 16) overrides for tuning.
@@ -493,8 +491,9 @@ extern "C" int ae_reduce_partials(const ae_slab *s, const double *partial, int32
 {
     if (!s || !partial || !phi || P < 1) { ae::set_error("ae_reduce_partials: bad argument"); return AE_BAD_ARG; }
     const int64_t n = (int64_t)s->G * s->Zp;
-    const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-    ae::reduce_partials_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(partial, P, s->Z, s->Zp, s->G, phi);
+    int64_t bx = (n / 2 + 255) / 256;
+    if (bx > 148 * 32) bx = 148 * 32;
+    ae::reduce_partials_kernel<<<(unsigned)bx, 256, 0, (cudaStream_t)stream>>>(partial, P, n, phi);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }

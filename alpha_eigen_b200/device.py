@@ -116,8 +116,9 @@ class SlabDevice:
         self.P = int(self.lib.ae_partial_count(self.A, self.n_neg))
         n = self.G * self.Zp
         f64 = dict(dtype=torch.float64, device=self.dev)
-        self.phi = torch.zeros(n, **f64)
+        self._phi_bufs = [torch.zeros(n, **f64), torch.zeros(n, **f64)]      # ping-pong pair, see `phi`
         self.phi_outer = torch.zeros(n, **f64)
+        self.reduced = torch.zeros(n, **f64) if comm is not None else None
         self.base = torch.zeros(n, **f64)
         self.q0 = torch.zeros(n, **f64)
         self.q1 = torch.zeros(n, **f64)
@@ -133,9 +134,9 @@ class SlabDevice:
                                 self.t_chi.data_ptr(), self.t_nusf.data_ptr(), self.t_hs.data_ptr(),
                                 self.t_cdt.data_ptr() if self.t_cdt is not None else None,
                                 self.t_sext.data_ptr() if self.t_sext is not None else None)
-        self.work = _lib.AeWork(self.phi.data_ptr(), self.phi_outer.data_ptr(), self.base.data_ptr(),
-                                self.q0.data_ptr(), self.q1.data_ptr(), self.partial.data_ptr(),
-                                self.scratch.data_ptr(), self.ctrl.data_ptr(), self.ctrl_host.data_ptr(),
+        self.work = _lib.AeWork(self._phi_bufs[0].data_ptr(), self._phi_bufs[1].data_ptr(), self.phi_outer.data_ptr(),
+                                self.base.data_ptr(), self.q0.data_ptr(), self.q1.data_ptr(), self.partial.data_ptr(),
+                                self.reduced.data_ptr() if self.reduced is not None else None, self.scratch.data_ptr(), self.ctrl.data_ptr(), self.ctrl_host.data_ptr(),
                                 self.sync.data_ptr(), comm.handle.value if comm is not None else None, self.P, int(batch))
         self.last_q_index = 0
 
@@ -151,6 +152,13 @@ class SlabDevice:
         return dev
 
     # ---- plumbing ------------------------------------------------------------------------
+    @property
+    def phi(self):
+        """[G][Zp] newest scalar-flux iterate.  The C side ping-pongs two buffers and keeps work.phi on
+        the newest one; this returns the tensor that pointer refers to."""
+        a, b = self._phi_bufs
+        return a if self.work.phi == a.data_ptr() else b
+
     def _upload(self, a):
         return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
 

@@ -166,6 +166,8 @@ def main():
     n_phi = dev.G * dev.Zp
     psi = torch.empty(dev.G * dev.A * dev.Zp, dtype=torch.float64, device=dev.dev)
     psi.uniform_(0.5, 1.5, generator=torch.Generator(device=dev.dev).manual_seed(2021 + rank))
+    # experiment knob: out-of-place psi update (needs a second psi buffer; the headline run is in place)
+    psis = [psi, torch.empty_like(psi)] if os.environ.get("AE_BENCH_PSI_PINGPONG") == "1" else None
     dev.base.zero_()
     q = [dev.q0, dev.q1]
     q[0].uniform_(0.0, 1.0, generator=torch.Generator(device=dev.dev).manual_seed(7))
@@ -177,19 +179,20 @@ def main():
         nonlocal launches
         if ev is not None:
             ev[0].record()
-        dev.lib.ae_sweep_set(dev.slab, q[i & 1].data_ptr(), psi.data_ptr(), psi.data_ptr(), dev.partial.data_ptr(),
+        pin, pout = (psis[i & 1], psis[(i + 1) & 1]) if psis is not None else (psi, psi)
+        dev.lib.ae_sweep_set(dev.slab, q[i & 1].data_ptr(), pin.data_ptr(), pout.data_ptr(), dev.partial.data_ptr(),
                              dev.sync.data_ptr(), dev.stream)
         if ev is not None:
             ev[1].record()
         launches += 1
         if comm is not None:
-            dev.lib.ae_reduce_partials(dev.slab, dev.partial.data_ptr(), dev.P, dev.partial.data_ptr(), dev.stream)
+            dev.lib.ae_reduce_partials(dev.slab, dev.partial.data_ptr(), dev.P, dev.reduced.data_ptr(), dev.stream)
             if ev is not None:
                 ev[2].record()
-            comm.allreduce_(dev.partial[:n_phi])
+            comm.allreduce_(dev.reduced)
             if ev is not None:
                 ev[3].record()
-            dev.flux_update(dev.partial, 1, q[(i + 1) & 1], 0.0, i + 1)
+            dev.flux_update(dev.reduced, 1, q[(i + 1) & 1], 0.0, i + 1)
             launches += 4                                   # reduce, (nccl), assemble, scatter
         else:
             if ev is not None:

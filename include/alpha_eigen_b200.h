@@ -70,10 +70,14 @@ typedef struct ae_slab {
 /* Mutable buffers, all caller-allocated (torch owns the memory). */
 typedef struct ae_work {
     double *phi;             /* [G][Zp] current scalar-flux iterate (phi_old of group.py:80) */
+    double *phi_alt;         /* [G][Zp] the other half of the ping-pong: the flux-update kernel reads one and writes
+                                the other, and the solver entry points SWAP these two pointers so that `phi`
+                                is the newest iterate when they return */
     double *phi_outer;       /* [G][Zp] power-iteration phi.old / time-step outer phi */
     double *base;            /* [G][Zp] source that is fixed during the inner iteration */
     double *q0, *q1;         /* [G][Zp] ping-pong isotropic sweep source */
     double *partial;         /* [P][G][Zp] per-angle-block partial scalar flux */
+    double *reduced;         /* [G][Zp] sum of the partials, allreduced over ranks (multi-GPU only, else NULL) */
     double *norm_scratch;    /* [4 * ae_norm_blocks(Zp) + 2 * G] */
     ae_ctrl *ctrl;           /* device */
     ae_ctrl *ctrl_host;      /* pinned host */
@@ -107,8 +111,8 @@ int64_t ae_sweep_sync_bytes(void);
 int ae_reduce_partials(const ae_slab *s, const double *partial, int32_t P, double *phi, void *stream);
 
 /* Scalar-flux assembly after a sweep set (group.py:77-80 + group.py:73 for the next iterate):
- *   phi_new = sum_p partial[p] (padding zeroed); change = ||phi_new - w->phi|| / ||phi_new||;
- *   w->phi = phi_new; q_next = w->base + 0.5 * sum_g' sigma_s(g'->g) phi_new(g').
+ *   phi_new = sum_p partial[p]; change = ||phi_new - w->phi|| / ||phi_new||; phi_new is written to
+ *   w->phi_alt and the two pointers are swapped; q_next = w->base + 0.5 * sum_g' sigma_s(g'->g) phi_new(g').
  * ctrl.change / inner_iters / inner_done are updated on the device (done when change < tol).
  * The solver loops below are this call alternated with ae_sweep_set. */
 int ae_flux_update(const ae_slab *s, ae_work *w, const double *partial, int32_t P, double *q_next,

@@ -26,7 +26,7 @@ def test_struct_sizes_match_header():
     import ctypes as C
     assert C.sizeof(_lib.AeCtrl) == 64
     assert C.sizeof(_lib.AeSlab) == 16 + 16 + 9 * 8
-    assert C.sizeof(_lib.AeWork) == 11 * 8 + 8
+    assert C.sizeof(_lib.AeWork) == 13 * 8 + 8
 
 
 @pytest.mark.parametrize("Z", [1, 7, 255, 256, 257, 450, 1800, 5000])
