@@ -43,6 +43,7 @@ SYMBOLS = {
     "ae_abi_version": (C.c_int, []),
     "ae_last_error": (C.c_char_p, []),
     "ae_padded_cells": (C.c_int64, [C.c_int64]),
+    "ae_padded_cells_sharded": (C.c_int64, [C.c_int64, C.c_int32]),
     "ae_cell_offset": (C.c_int64, [C.c_int64]),
     "ae_partial_count": (C.c_int32, [C.c_int32, C.c_int32]),
     "ae_norm_blocks": (C.c_int64, [C.c_int64]),
@@ -50,10 +51,11 @@ SYMBOLS = {
     "ae_sweep_sync_bytes": (C.c_int64, []),
     "ae_reduce_partials": (C.c_int, [C.POINTER(AeSlab), _P, C.c_int32, _P, _P]),
     "ae_flux_update": (C.c_int, [C.POINTER(AeSlab), C.POINTER(AeWork), _P, C.c_int32, _P, C.c_double, C.c_int32, _P]),
-    "ae_pack_cells": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
-    "ae_unpack_cells": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
-    "ae_pack_psi": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
-    "ae_unpack_psi": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
+    "ae_exchange_partials": (C.c_int, [C.POINTER(AeSlab), C.POINTER(AeWork), _P]),
+    "ae_pack_cells": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, _P]),
+    "ae_unpack_cells": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, _P]),
+    "ae_pack_psi": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
+    "ae_unpack_psi": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
     "ae_source_iteration": (C.c_int, [C.POINTER(AeSlab), C.POINTER(AeWork), _P, C.c_double, C.c_double, C.c_int32,
                                       c_ip, c_ip, _P]),
     "ae_power_iteration": (C.c_int, [C.POINTER(AeSlab), C.POINTER(AeWork), C.c_double, C.c_int32, C.c_double,
@@ -69,6 +71,7 @@ SYMBOLS = {
     "ae_comm_unique_id": (C.c_int, [_P]),
     "ae_comm_init": (C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32, _P]),
     "ae_comm_allreduce_sum": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "ae_comm_gather_rows": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P]),
     "ae_comm_destroy": (C.c_int, [_P]),
 }
 

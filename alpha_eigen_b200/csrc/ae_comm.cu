@@ -19,11 +19,23 @@ struct Nccl {
     int (*GetUniqueId)(ncclUniqueId *) = nullptr;
     int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*ReduceScatter)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 
 static Nccl g_nccl;
+
+// What an ae_comm handle points to.
+struct Comm {
+    ncclComm_t nccl;
+    int rank, nranks;
+    double *pair_local;     // device [2]: this rank's (num, den) of a sharded norm
+    double *pairs;          // device [nranks][2]: everybody's, after the all-gather
+};
 
 static int load_nccl()
 {
@@ -31,12 +43,19 @@ static int load_nccl()
     void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
     if (!h) { set_error("NCCL not found: %s", dlerror()); return AE_CUDA_ERROR; }
-    g_nccl.GetUniqueId = (int (*)(ncclUniqueId *))dlsym(h, "ncclGetUniqueId");
-    g_nccl.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
-    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
-    g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
-    g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+#define AE_SYM(field, name) *(void **)(&g_nccl.field) = dlsym(h, name)
+    AE_SYM(GetUniqueId, "ncclGetUniqueId");
+    AE_SYM(CommInitRank, "ncclCommInitRank");
+    AE_SYM(AllReduce, "ncclAllReduce");
+    AE_SYM(ReduceScatter, "ncclReduceScatter");
+    AE_SYM(AllGather, "ncclAllGather");
+    AE_SYM(GroupStart, "ncclGroupStart");
+    AE_SYM(GroupEnd, "ncclGroupEnd");
+    AE_SYM(CommDestroy, "ncclCommDestroy");
+    AE_SYM(GetErrorString, "ncclGetErrorString");
+#undef AE_SYM
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.ReduceScatter || !g_nccl.AllGather ||
+        !g_nccl.GroupStart || !g_nccl.GroupEnd || !g_nccl.CommDestroy) {
         set_error("NCCL symbols missing");
         return AE_CUDA_ERROR;
     }
@@ -48,6 +67,46 @@ static int nccl_fail(int rc, const char *what)
 {
     set_error("%s failed: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "nccl error");
     return AE_CUDA_ERROR;
+}
+#define AE_NCCL(call)                                    \
+    do {                                                 \
+        const int rc_ = (call);                          \
+        if (rc_) return nccl_fail(rc_, #call);           \
+    } while (0)
+
+int comm_rank(const void *comm) { return comm ? ((const Comm *)comm)->rank : 0; }
+int comm_size(const void *comm) { return comm ? ((const Comm *)comm)->nranks : 1; }
+double *comm_pair_local(void *comm) { return ((Comm *)comm)->pair_local; }
+double *comm_pairs(void *comm) { return ((Comm *)comm)->pairs; }
+
+// rows[g][Zp]: sum over ranks of every row, rank r keeping cells [r*Zs, (r+1)*Zs) of each row (in place).
+int comm_reduce_scatter_rows(void *comm, double *rows, int G, int64_t Zp, cudaStream_t st)
+{
+    Comm *c = (Comm *)comm;
+    const int64_t Zs = Zp / c->nranks;
+    AE_NCCL(g_nccl.GroupStart());
+    for (int g = 0; g < G; ++g) {
+        double *row = rows + (int64_t)g * Zp;
+        AE_NCCL(g_nccl.ReduceScatter(row, row + c->rank * Zs, (size_t)Zs, ncclFloat64, ncclSum, c->nccl, st));
+    }
+    AE_NCCL(g_nccl.GroupEnd());
+    return AE_OK;
+}
+
+// rows[g][Zp]: every rank contributes its cell range of every row (in place); optionally the (num, den)
+// pairs of a sharded norm travel in the same group.
+int comm_all_gather_rows(void *comm, double *rows, int G, int64_t Zp, int with_pairs, cudaStream_t st)
+{
+    Comm *c = (Comm *)comm;
+    const int64_t Zs = Zp / c->nranks;
+    AE_NCCL(g_nccl.GroupStart());
+    for (int g = 0; g < G && rows; ++g) {
+        double *row = rows + (int64_t)g * Zp;
+        AE_NCCL(g_nccl.AllGather(row + c->rank * Zs, row, (size_t)Zs, ncclFloat64, c->nccl, st));
+    }
+    if (with_pairs) AE_NCCL(g_nccl.AllGather(c->pair_local, c->pairs, 2, ncclFloat64, c->nccl, st));
+    AE_NCCL(g_nccl.GroupEnd());
+    return AE_OK;
 }
 
 }  // namespace ae
@@ -69,9 +128,12 @@ extern "C" int ae_comm_init(void **comm, int32_t rank, int32_t nranks, const voi
     AE_TRY(load_nccl());
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
-    ncclComm_t c = nullptr;
-    const int rc = g_nccl.CommInitRank(&c, nranks, id, rank);
+    ncclComm_t nc = nullptr;
+    const int rc = g_nccl.CommInitRank(&nc, nranks, id, rank);
     if (rc) return nccl_fail(rc, "ncclCommInitRank");
+    Comm *c = new Comm{nc, rank, nranks, nullptr, nullptr};
+    AE_CUDA(cudaMalloc((void **)&c->pair_local, 2 * sizeof(double)));
+    AE_CUDA(cudaMalloc((void **)&c->pairs, 2 * sizeof(double) * nranks));
     *comm = c;
     return AE_OK;
 }
@@ -79,15 +141,24 @@ extern "C" int ae_comm_init(void **comm, int32_t rank, int32_t nranks, const voi
 extern "C" int ae_comm_allreduce_sum(void *comm, double *buf, int64_t count, void *stream)
 {
     if (!comm || !g_nccl.h) { set_error("ae_comm_allreduce_sum: no communicator"); return AE_BAD_ARG; }
-    const int rc = g_nccl.AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclSum, (ncclComm_t)comm, (cudaStream_t)stream);
-    if (rc) return nccl_fail(rc, "ncclAllReduce");
+    AE_NCCL(g_nccl.AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclSum, ((Comm *)comm)->nccl, (cudaStream_t)stream));
     return AE_OK;
+}
+
+extern "C" int ae_comm_gather_rows(void *comm, double *rows, int32_t G, int64_t Zp, void *stream)
+{
+    if (!comm || !g_nccl.h) { set_error("ae_comm_gather_rows: no communicator"); return AE_BAD_ARG; }
+    return comm_all_gather_rows(comm, rows, G, Zp, 0, (cudaStream_t)stream);
 }
 
 extern "C" int ae_comm_destroy(void *comm)
 {
     if (!comm || !g_nccl.h) return AE_OK;
-    const int rc = g_nccl.CommDestroy((ncclComm_t)comm);
+    Comm *c = (Comm *)comm;
+    const int rc = g_nccl.CommDestroy(c->nccl);
+    cudaFree(c->pair_local);
+    cudaFree(c->pairs);
+    delete c;
     if (rc) return nccl_fail(rc, "ncclCommDestroy");
     return AE_OK;
 }

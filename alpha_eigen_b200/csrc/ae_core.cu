@@ -26,6 +26,11 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 extern "C" int ae_abi_version(void) { return AE_ABI_VERSION; }
 extern "C" const char *ae_last_error(void) { return ae::g_err; }
 extern "C" int64_t ae_padded_cells(int64_t Z) { return (Z + AE_TILE - 1) / AE_TILE * AE_TILE; }
+extern "C" int64_t ae_padded_cells_sharded(int64_t Z, int32_t nranks)
+{
+    const int64_t unit = (int64_t)AE_TILE * (nranks > 0 ? nranks : 1);
+    return (Z + unit - 1) / unit * unit;
+}
 extern "C" int64_t ae_cell_offset(int64_t z)
 {
     const int64_t tile = z / AE_TILE;
@@ -75,36 +80,32 @@ static int grid_for(int64_t n) { int64_t b = (n + 255) / 256; return (int)(b < 1
 
 }  // namespace ae
 
-extern "C" int ae_pack_cells(const double *logical, int64_t Z, int32_t G, double *storage, void *stream)
+extern "C" int ae_pack_cells(const double *logical, int64_t Z, int64_t Zp, int32_t G, double *storage, void *stream)
 {
-    const int64_t Zp = ae_padded_cells(Z);
     ae::pack_cells_kernel<<<ae::grid_for(G * Zp), 256, 0, (cudaStream_t)stream>>>(logical, Z, Zp, G, storage);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }
 
-extern "C" int ae_unpack_cells(const double *storage, int64_t Z, int32_t G, double *logical, void *stream)
+extern "C" int ae_unpack_cells(const double *storage, int64_t Z, int64_t Zp, int32_t G, double *logical, void *stream)
 {
-    const int64_t Zp = ae_padded_cells(Z);
     ae::unpack_cells_kernel<<<ae::grid_for(G * Zp), 256, 0, (cudaStream_t)stream>>>(storage, Z, Zp, G, logical);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }
 
-extern "C" int ae_pack_psi(const double *logical, int64_t Z, int32_t A_total, int32_t G, const int32_t *angle_index,
-                           int32_t A, double *storage, void *stream)
+extern "C" int ae_pack_psi(const double *logical, int64_t Z, int64_t Zp, int32_t A_total, int32_t G,
+                           const int32_t *angle_index, int32_t A, double *storage, void *stream)
 {
-    const int64_t Zp = ae_padded_cells(Z);
     ae::pack_psi_kernel<<<ae::grid_for((int64_t)G * A * Zp), 256, 0, (cudaStream_t)stream>>>(logical, Z, Zp, A_total, G,
                                                                                             angle_index, A, storage, 0);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }
 
-extern "C" int ae_unpack_psi(const double *storage, int64_t Z, int32_t A_total, int32_t G, const int32_t *angle_index,
-                             int32_t A, double *logical, void *stream)
+extern "C" int ae_unpack_psi(const double *storage, int64_t Z, int64_t Zp, int32_t A_total, int32_t G,
+                             const int32_t *angle_index, int32_t A, double *logical, void *stream)
 {
-    const int64_t Zp = ae_padded_cells(Z);
     ae::pack_psi_kernel<<<ae::grid_for((int64_t)G * A * Zp), 256, 0, (cudaStream_t)stream>>>(logical, Z, Zp, A_total, G,
                                                                                             angle_index, A,
                                                                                             const_cast<double *>(storage), 1);

@@ -12,7 +12,17 @@ int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double
                  void *sync, const ae_ctrl *ctrl, int gate, cudaStream_t st);
 int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, const double *phi_in, double *phi_out,
                     double *q_next, int init, double cold, double tol, int iteration, int gate, cudaStream_t st);
-int launch_fission_base(const ae_slab *s, const double *phi, double *base, cudaStream_t st);
+int launch_fission_base(const ae_slab *s, ae_work *w, const double *phi, double *base, int with_ext, cudaStream_t st);
+int comm_reduce_scatter_rows(void *comm, double *rows, int G, int64_t Zp, cudaStream_t st);
+int comm_all_gather_rows(void *comm, double *rows, int G, int64_t Zp, int with_pairs, cudaStream_t st);
+
+// multi-GPU: local sum of the angle-block partials, then reduce-scatter by rows so that this rank holds the
+// rank-summed flux of ITS cell range in w->reduced (the one exchange of the solve)
+static int exchange_partials(const ae_slab *s, ae_work *w, cudaStream_t st)
+{
+    AE_TRY(ae_reduce_partials(s, w->partial, w->P, w->reduced, st));
+    return comm_reduce_scatter_rows(w->comm, w->reduced, s->G, s->Zp, st);
+}
 int launch_k_update(const ae_slab *s, ae_work *w, double tol, int iteration, cudaStream_t st);
 int launch_outer_check(const ae_slab *s, ae_work *w, cudaStream_t st);
 int launch_ctrl_init(ae_work *w, cudaStream_t st);
@@ -57,9 +67,9 @@ static int source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, 
             const int gate = b > 0;                     // first of a batch always runs
             AE_TRY(launch_sweep(s, q[i & 1], psi_in, nullptr, w->partial, w->sweep_sync, w->ctrl, gate, st));
             if (w->comm) {
-                // angle-sharded ranks: local partial sum -> NCCL sum over ranks -> same update on every rank
-                AE_TRY(ae_reduce_partials(s, w->partial, w->P, w->reduced, st));
-                AE_TRY(ae_comm_allreduce_sum(w->comm, w->reduced, (int64_t)s->G * s->Zp, st));
+                // angle-sharded sweeps, cell-sharded update: reduce-scatter the flux, update 1/N of the cells,
+                // all-gather the new source (inside launch_finalize)
+                AE_TRY(exchange_partials(s, w, st));
                 AE_TRY(launch_finalize(s, w, w->reduced, 1, phi[i & 1], phi[(i + 1) & 1], q[(i + 1) & 1], 0, cold, tol,
                                        i + 1, gate, st));
             } else {
@@ -74,12 +84,20 @@ static int source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, 
     if (iters) *iters = n_done;
     if (last_q) *last_q = (n_done - 1) & 1;             // the sweep of iteration n read q[(n-1)&1]
     if (n_done & 1) { w->phi = phi[1]; w->phi_alt = phi[0]; }   // iteration n wrote phi[n&1]
+    if (w->comm) AE_TRY(comm_all_gather_rows(w->comm, w->phi, s->G, s->Zp, 0, st));     // callers see the whole flux
     return status;
 }
 
 }  // namespace ae
 
 using namespace ae;
+
+extern "C" int ae_exchange_partials(const ae_slab *s, ae_work *w, void *stream)
+{
+    AE_TRY(check_work(s, w, "ae_exchange_partials"));
+    if (!w->comm) { set_error("ae_exchange_partials: no communicator"); return AE_BAD_ARG; }
+    return exchange_partials(s, w, (cudaStream_t)stream);
+}
 
 extern "C" int ae_flux_update(const ae_slab *s, ae_work *w, const double *partial, int32_t P, double *q_next, double tol,
                               int32_t iteration, void *stream)
@@ -112,9 +130,7 @@ extern "C" int ae_power_iteration(const ae_slab *s, ae_work *w, double tol, int3
     for (;;) {
         iteration += 1;
         if (!(iteration < max_iterations)) { status = AE_NOT_CONVERGED; iteration -= 1; break; }   // group.py:102
-        ae_slab steady = *s;
-        steady.s_ext = nullptr;                          // group.py:104: source = zeros + fission
-        AE_TRY(launch_fission_base(&steady, w->phi_outer, w->base, st));
+        AE_TRY(launch_fission_base(s, w, w->phi_outer, w->base, 0, st));    // group.py:104: source = zeros + fission
         int si = 0;
         status = source_iteration(s, w, nullptr, 1e-12, si_tol, si_max_iterations, &si, &last_q, st);
         if (si_hist) si_hist[iteration - 1] = si;
@@ -152,7 +168,7 @@ extern "C" int ae_time_step(const ae_slab *s, ae_work *w, const double *psi_prev
     for (;;) {
         outer += 1;
         if (!(outer < 100)) { status = AE_NOT_CONVERGED; break; }               // time_unit.py:35
-        AE_TRY(launch_fission_base(s, w->phi_outer, w->base, st));              // time_unit.py:37-39
+        AE_TRY(launch_fission_base(s, w, w->phi_outer, w->base, 1, st));        // time_unit.py:37-39
         int si = 0;
         status = source_iteration(s, w, psi_prev, 0.0, tol, 100, &si, &last_q, st);     // time_unit.py:40
         inner_total += si;

@@ -10,6 +10,12 @@
 // fission chi_g * sum_g' nu_sigma_f_g' phi_g').  All per-cell arrays are [G][Zp] in the
 // lane-blocked storage order; none of these kernels couples neighbouring cells, so the order
 // is irrelevant here and every access is stride-1 across the threads of a warp.
+//
+// Multi-GPU: every kernel works on a CELL RANGE [c0, c0+cn) of every group row.  With one GPU the
+// range is the whole row.  With N ranks each rank owns Zp/N cells: the partial fluxes are
+// reduce-scattered by rows so that rank r receives the summed flux of its cells only, does 1/N of
+// the update work, and the new sources are all-gathered; the two sums of a norm travel as a
+// (num, den) pair in the same NCCL group and are combined in rank order on every rank.
 #include <stdlib.h>
 #include "ae_common.cuh"
 
@@ -17,21 +23,49 @@ namespace ae {
 
 constexpr int kCB = 128;        // cells (threads) per block in the per-cell kernels
 
-__device__ __forceinline__ bool cell_valid(int64_t s, int64_t Z, int64_t Zp) { return s < Zp && logical_cell(s) < Z; }
+enum NormMode { kNormInner = 0, kNormK = 1, kNormOuter = 2 };
+
+// What a finished norm does to the control block (thread 0 of the last block, or norm_finalize_kernel).
+__device__ __forceinline__ void apply_norm(int mode, double a, double b, ae_ctrl *ctrl, double tol, int iteration)
+{
+    if (mode == kNormInner) {
+        const double change = sqrt(a) / sqrt(b);        // group.py:78
+        ctrl->change = change;
+        ctrl->inner_iters = iteration;
+        if (change < tol) ctrl->inner_done = 1;         // group.py:79
+    } else if (mode == kNormK) {
+        const double k_new = sqrt(a) / sqrt(b);         // group.py:108
+        const double dk = fabs(k_new - ctrl->k_old);
+        ctrl->k_new = k_new;
+        ctrl->k_change = dk;
+        ctrl->power_iters = iteration;
+        ctrl->power_done = dk < tol ? 1 : 0;            // group.py:109
+        ctrl->k_old = k_new;                            // group.py:114
+    } else {
+        ctrl->outer_change = sqrt(a) / sqrt(b);         // time_unit.py:41
+    }
+}
+
+struct NormOut {                // where a norm goes
+    double *scratch;            // per-block partials
+    ae_ctrl *ctrl;
+    double *pair_local;         // != NULL: sharded, publish this rank's (num, den) here instead of finishing
+    double tol;
+    int mode, iteration;
+};
 
 // Deterministic grid-wide reduction of (num, den): per-block partials to scratch, last block sums them
-// in a fixed order and calls `fin(num, den)` from thread 0.
-template <class Fin>
-__device__ __forceinline__ void grid_sum2(double num, double den, double *scratch, ae_ctrl *ctrl, double *sm, Fin fin)
+// in a fixed order.
+__device__ __forceinline__ void grid_sum2(double num, double den, const NormOut &o, double *sm)
 {
     __shared__ bool is_last;
     const unsigned nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
     block_sum2(num, den, sm);
     if (threadIdx.x == 0) {
-        scratch[2 * bid] = num;
-        scratch[2 * bid + 1] = den;
+        o.scratch[2 * bid] = num;
+        o.scratch[2 * bid + 1] = den;
         __threadfence();
-        const unsigned t = atomicAdd(&ctrl->ticket, 1u);
+        const unsigned t = atomicAdd(&o.ctrl->ticket, 1u);
         is_last = (t == nblocks - 1);
     }
     __syncthreads();
@@ -39,19 +73,30 @@ __device__ __forceinline__ void grid_sum2(double num, double den, double *scratc
         __threadfence();
         double a = 0.0, b = 0.0;
         for (int i = threadIdx.x; i < (int)nblocks; i += blockDim.x) {
-            a += __ldcg(scratch + 2 * i);
-            b += __ldcg(scratch + 2 * i + 1);
+            a += __ldcg(o.scratch + 2 * i);
+            b += __ldcg(o.scratch + 2 * i + 1);
         }
         block_sum2(a, b, sm);
         if (threadIdx.x == 0) {
-            ctrl->ticket = 0;
-            fin(a, b);
+            o.ctrl->ticket = 0;
+            if (o.pair_local) { o.pair_local[0] = a; o.pair_local[1] = b; }
+            else apply_norm(o.mode, a, b, o.ctrl, o.tol, o.iteration);
         }
     }
 }
 
+// Sharded norms: combine the ranks' pairs in rank order (identical on every rank).
+__global__ void norm_finalize_kernel(const double *pairs, int nranks, int mode, ae_ctrl *ctrl, double tol, int iteration,
+                                     int gate)
+{
+    if (gate && ctrl->inner_done) return;
+    double a = 0.0, b = 0.0;
+    for (int r = 0; r < nranks; ++r) { a += pairs[2 * r]; b += pairs[2 * r + 1]; }
+    apply_norm(mode, a, b, ctrl, tol, iteration);
+}
+
 struct FinArgs {
-    const double *partial;      // [P][G][Zp] (P may be 1 when phi was already reduced / allreduced)
+    const double *partial;      // [P][G][Zp] (P may be 1 when phi was already reduced over angle blocks / ranks)
     const double *base;         // [G][Zp]
     const int32_t *mat;         // [Zp]
     const double *scat;         // [M][G][G]
@@ -59,28 +104,14 @@ struct FinArgs {
     double *phi;                // [G][Zp] new iterate.  A different buffer: on B200 reading and then writing the
                                 // same addresses in one streaming kernel runs at 2.4 TB/s instead of 6.8 (tools/stride_probe.cu)
     double *q_next;             // [G][Zp]
-    double *scratch;
-    ae_ctrl *ctrl;
+    NormOut norm;
     int64_t Z, Zp;
+    int64_t c0, cn;             // cell range of this rank (multiples of 256)
     int P, G, M;
     int init;                   // 1: phi := cold (no norm), 0: phi := sum of partials
     int gate;
-    int iteration;
-    double cold, tol;
+    double cold;
 };
-
-__device__ __forceinline__ void publish_change(const FinArgs &p, double num, double den, double *red)
-{
-    const int iteration = p.iteration;
-    const double tol = p.tol;
-    ae_ctrl *ctrl = p.ctrl;
-    grid_sum2(num, den, p.scratch, ctrl, red, [=](double a, double b) {
-        const double change = sqrt(a) / sqrt(b);        // group.py:78
-        ctrl->change = change;
-        ctrl->inner_iters = iteration;
-        if (change < tol) ctrl->inner_done = 1;         // group.py:79
-    });
-}
 
 constexpr int kGSmall = 8;      // up to this many groups one thread owns a whole cell
 
@@ -89,18 +120,19 @@ constexpr int kGSmall = 8;      // up to this many groups one thread owns a whol
 __global__ void __launch_bounds__(kCB) finalize_small_kernel(const FinArgs p)
 {
     __shared__ double red[64];
-    if (p.gate && p.ctrl->inner_done) return;
+    if (p.gate && p.norm.ctrl->inner_done) return;
     const int tid = threadIdx.x;
     if (p.init && blockIdx.x == 0 && tid == 0) {
-        p.ctrl->inner_done = 0;
-        p.ctrl->inner_iters = 0;
-        p.ctrl->ticket = 0;
+        p.norm.ctrl->inner_done = 0;
+        p.norm.ctrl->inner_iters = 0;
+        p.norm.ctrl->ticket = 0;
     }
-    const int64_t s = (int64_t)blockIdx.x * kCB + tid;
-    const bool valid = cell_valid(s, p.Z, p.Zp);
+    const int64_t s = p.c0 + (int64_t)blockIdx.x * kCB + tid;
+    const bool inside = s < p.c0 + p.cn;
+    const bool valid = inside && logical_cell(s) < p.Z;
     const int64_t n = (int64_t)p.G * p.Zp;
     double num = 0.0, den = 0.0;
-    if (s < p.Zp) {
+    if (inside) {
         double v[kGSmall];
 #pragma unroll
         for (int g = 0; g < kGSmall; ++g) {
@@ -137,42 +169,46 @@ __global__ void __launch_bounds__(kCB) finalize_small_kernel(const FinArgs p)
             }
         }
     }
-    if (!p.init) publish_change(p, num, den, red);
+    if (!p.init) grid_sum2(num, den, p.norm, red);
 }
 
-// G > kGSmall, step 1: phi := sum of partials (or cold), norm.  Flat grid-stride over [G][Zp], one double2
-// per thread and iteration, <= 32 registers so 64 warps per SM with ~4 loads each are in flight: a P-buffer
-// sum needs ~100 KB per SM in flight to stream at 6.5-7 TB/s on B200 (tools/stride_probe.cu).  Padding
-// cells need no masking here: the sweep writes exact zeros there.
+// G > kGSmall, step 1: phi := sum of partials, norm.  Grid (x over cell pairs of the range, y = group), one
+// double2 per thread and iteration, 40 registers so 48 warps per SM with ~4 loads each are in flight: a
+// P-buffer sum needs ~100 KB per SM in flight to stream at 6.5-7 TB/s on B200 (tools/stride_probe.cu).
+// Padding cells need no masking here: the sweep writes exact zeros there.
 __global__ void __launch_bounds__(256, 6) flux_assemble_kernel(const FinArgs p)
 {
     __shared__ double red[64];
-    if (p.gate && p.ctrl->inner_done) return;
+    if (p.gate && p.norm.ctrl->inner_done) return;
     const int64_t n = (int64_t)p.G * p.Zp;
+    const int64_t row = (int64_t)blockIdx.y * p.Zp + p.c0;
+    const double *part = p.partial + row;
+    const double *old = p.phi_in + row;
+    double *out = p.phi + row;
     double num = 0.0, den = 0.0;
-    for (int64_t i = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 2 * (int64_t)gridDim.x * blockDim.x) {
-        double2 x = *reinterpret_cast<const double2 *>(p.partial + i);
+    for (int64_t i = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); i < p.cn; i += 2 * (int64_t)gridDim.x * blockDim.x) {
+        double2 x = *reinterpret_cast<const double2 *>(part + i);
 #pragma unroll 4
         for (int pp = 1; pp < p.P; ++pp) {                       // block order (group.py:77 over angle blocks)
-            const double2 y = *reinterpret_cast<const double2 *>(p.partial + (int64_t)pp * n + i);
+            const double2 y = *reinterpret_cast<const double2 *>(part + (int64_t)pp * n + i);
             x.x += y.x; x.y += y.y;
         }
-        const double2 o = *reinterpret_cast<const double2 *>(p.phi_in + i);
+        const double2 o = *reinterpret_cast<const double2 *>(old + i);
         const double dx = x.x - o.x, dy = x.y - o.y;             // group.py:78
         num = fma(dx, dx, fma(dy, dy, num));
         den = fma(x.x, x.x, fma(x.y, x.y, den));
-        *reinterpret_cast<double2 *>(p.phi + i) = x;             // group.py:80
+        *reinterpret_cast<double2 *>(out + i) = x;               // group.py:80
     }
-    publish_change(p, num, den, red);
+    grid_sum2(num, den, p.norm, red);
 }
 
 // Cold start of the inner iteration: phi := cold on real cells, 0 on padding (group.py:66 / time_unit.py:45).
 __global__ void flux_init_kernel(const FinArgs p)
 {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        p.ctrl->inner_done = 0;
-        p.ctrl->inner_iters = 0;
-        p.ctrl->ticket = 0;
+        p.norm.ctrl->inner_done = 0;
+        p.norm.ctrl->inner_iters = 0;
+        p.norm.ctrl->ticket = 0;
     }
     const int64_t n = (int64_t)p.G * p.Zp;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -194,7 +230,7 @@ __global__ void __launch_bounds__(32 * kSWarps, 2) scatter_source_kernel(const F
 {
     extern __shared__ double stab[];                            // [G][Gp] scatter matrix, then [G][kSC] phi tile
     __shared__ int s_uniform;
-    if (p.gate && p.ctrl->inner_done) return;
+    if (p.gate && p.norm.ctrl->inner_done) return;
     const int lane = threadIdx.x, gb = threadIdx.y, tid = gb * 32 + lane, nthr = blockDim.y * 32;
     const int Gp = (p.G + kGB - 1) / kGB * kGB;
     const int gblocks = Gp / kGB;
@@ -202,8 +238,8 @@ __global__ void __launch_bounds__(32 * kSWarps, 2) scatter_source_kernel(const F
     const double *phi = sphi + lane;
     int staged = -1;                                            // material whose matrix is in stab
     // persistent CTA: the scatter matrix is restaged only when the tile's material changes (5 regions)
-    for (int64_t tile = blockIdx.x; tile < p.Zp / kSC; tile += gridDim.x) {
-        const int64_t s0 = tile * kSC;
+    for (int64_t tile = blockIdx.x; tile < p.cn / kSC; tile += gridDim.x) {
+        const int64_t s0 = p.c0 + tile * kSC;
         const int m0 = p.mat[s0];
         __syncthreads();                                        // previous tile fully consumed
         if (tid == 0) s_uniform = 1;
@@ -278,11 +314,11 @@ __global__ void __launch_bounds__(32 * kSWarps, 2) scatter_source_kernel(const F
 // (group.py:104-105, time_unit.py:37-39, zone.py:38-42)
 __global__ void __launch_bounds__(kCB) fission_base_kernel(const double *__restrict__ phi, const double *__restrict__ s_ext,
                                                            const int32_t *__restrict__ mat, const double *__restrict__ chi,
-                                                           const double *__restrict__ nusf, int64_t Zp, int G,
-                                                           double *__restrict__ base)
+                                                           const double *__restrict__ nusf, int64_t Zp, int64_t c0, int64_t cn,
+                                                           int G, double *__restrict__ base)
 {
-    const int64_t s = (int64_t)blockIdx.x * kCB + threadIdx.x;
-    if (s >= Zp) return;
+    const int64_t s = c0 + (int64_t)blockIdx.x * kCB + threadIdx.x;
+    if (s >= c0 + cn) return;
     const int m = mat[s];
     double acc = 0.0;
     for (int gp = 0; gp < G; ++gp) acc = fma(nusf[m * G + gp], phi[(int64_t)gp * Zp + s], acc);
@@ -296,13 +332,12 @@ __global__ void __launch_bounds__(kCB) fission_base_kernel(const double *__restr
 // k.new = ||nusf*phi_new|| / ||nusf*phi_old||  (group.py:108), convergence flag (group.py:109)
 __global__ void __launch_bounds__(kCB) k_update_kernel(const double *__restrict__ phi_new, const double *__restrict__ phi_old,
                                                        const int32_t *__restrict__ mat, const double *__restrict__ nusf,
-                                                       int64_t Z, int64_t Zp, int G, double tol, int iteration,
-                                                       double *scratch, ae_ctrl *ctrl)
+                                                       int64_t Z, int64_t Zp, int64_t c0, int64_t cn, int G, NormOut norm)
 {
     __shared__ double red[64];
-    const int64_t s = (int64_t)blockIdx.x * kCB + threadIdx.x;
+    const int64_t s = c0 + (int64_t)blockIdx.x * kCB + threadIdx.x;
     double num = 0.0, den = 0.0;
-    if (cell_valid(s, Z, Zp)) {
+    if (s < c0 + cn && logical_cell(s) < Z) {
         const int m = mat[s];
         for (int g = 0; g < G; ++g) {
             const double f = nusf[m * G + g];
@@ -311,15 +346,7 @@ __global__ void __launch_bounds__(kCB) k_update_kernel(const double *__restrict_
             den = fma(b, b, den);
         }
     }
-    grid_sum2(num, den, scratch, ctrl, red, [=](double a, double b) {
-        const double k_new = sqrt(a) / sqrt(b);
-        const double dk = fabs(k_new - ctrl->k_old);
-        ctrl->k_new = k_new;
-        ctrl->k_change = dk;
-        ctrl->power_iters = iteration;
-        ctrl->power_done = dk < tol ? 1 : 0;            // group.py:109
-        ctrl->k_old = k_new;                            // group.py:114
-    });
+    grid_sum2(num, den, norm, red);
 }
 
 // phi.old = phi.new / k.new  (group.py:115)
@@ -332,12 +359,12 @@ __global__ void scale_by_k_kernel(const double *__restrict__ phi_new, const ae_c
 
 // time_unit.py:41 outer change; also phi_outer := phi for the next outer iteration (time_unit.py:36)
 __global__ void __launch_bounds__(kCB) outer_check_kernel(const double *__restrict__ phi, double *__restrict__ phi_outer,
-                                                          int64_t Zp, int G, double *scratch, ae_ctrl *ctrl)
+                                                          int64_t Zp, int64_t c0, int64_t cn, int G, NormOut norm)
 {
     __shared__ double red[64];
-    const int64_t s = (int64_t)blockIdx.x * kCB + threadIdx.x;
+    const int64_t s = c0 + (int64_t)blockIdx.x * kCB + threadIdx.x;
     double num = 0.0, den = 0.0;
-    if (s < Zp) {
+    if (s < c0 + cn) {
         for (int g = 0; g < G; ++g) {
             const int64_t i = (int64_t)g * Zp + s;
             const double v = phi[i], d = v - phi_outer[i];      // padding cells are 0 in both
@@ -346,7 +373,7 @@ __global__ void __launch_bounds__(kCB) outer_check_kernel(const double *__restri
             phi_outer[i] = v;
         }
     }
-    grid_sum2(num, den, scratch, ctrl, red, [=](double a, double b) { ctrl->outer_change = sqrt(a) / sqrt(b); });
+    grid_sum2(num, den, norm, red);
 }
 
 __global__ void ctrl_init_kernel(ae_ctrl *ctrl)
@@ -358,53 +385,101 @@ __global__ void ctrl_init_kernel(ae_ctrl *ctrl)
     ctrl->ticket = 0; ctrl->reserved = 0;
 }
 
-static int per_cell_blocks(int64_t Zp) { return (int)((Zp + kCB - 1) / kCB); }
+// ---- host side -----------------------------------------------------------------------------------
+int comm_rank(const void *comm);
+int comm_size(const void *comm);
+double *comm_pair_local(void *comm);
+double *comm_pairs(void *comm);
+int comm_all_gather_rows(void *comm, double *rows, int G, int64_t Zp, int with_pairs, cudaStream_t st);
 
-int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, const double *phi_in, double *phi_out,
-                    double *q_next, int init, double cold, double tol, int iteration, int gate, cudaStream_t st)
+static int per_cell_blocks(int64_t cells) { return (int)((cells + kCB - 1) / kCB); }
+
+struct Shard { int64_t c0, cn; };
+static Shard shard_of(const ae_slab *s, const ae_work *w)
 {
-    FinArgs p;
-    p.partial = partial; p.base = w->base; p.mat = s->mat; p.scat = s->scat; p.phi_in = phi_in; p.phi = phi_out;
-    p.q_next = q_next;
-    p.scratch = w->norm_scratch; p.ctrl = w->ctrl; p.Z = s->Z; p.Zp = s->Zp; p.P = P; p.G = s->G; p.M = s->M;
-    p.init = init; p.gate = gate; p.iteration = iteration; p.cold = cold; p.tol = tol;
-    if (s->G <= kGSmall) {
-        finalize_small_kernel<<<per_cell_blocks(s->Zp), kCB, 0, st>>>(p);
-        AE_CUDA(cudaGetLastError());
-        return AE_OK;
-    }
-    // norm_scratch holds 4 doubles per per-cell block = room for 2*per_cell_blocks (num, den) pairs
-    int64_t bx = ((int64_t)s->G * s->Zp / 2 + 255) / 256;
-    const int64_t cap = 2 * (int64_t)per_cell_blocks(s->Zp);    // norm_scratch holds that many (num, den) pairs
-    if (bx > cap) bx = cap;
-    if (bx > 148 * 32) bx = 148 * 32;
-    if (init) flux_init_kernel<<<(unsigned)bx, 256, 0, st>>>(p);
-    else flux_assemble_kernel<<<(unsigned)bx, 256, 0, st>>>(p);
-    AE_CUDA(cudaGetLastError());
-    const int gblocks = (s->G + kGB - 1) / kGB;
-    const size_t smem = (size_t)s->G * (gblocks * kGB + kSC) * sizeof(double);
-    if (smem > 220 * 1024) { set_error("flux update: scatter matrix of G=%d does not fit in shared memory", s->G); return AE_BAD_ARG; }
-    if (smem > 48 * 1024)
-        AE_CUDA(cudaFuncSetAttribute((const void *)scatter_source_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t sgrid = s->Zp / kSC;                         // Zp % 256 == 0
-    if (sgrid > 148 * 2) sgrid = 148 * 2;
-    scatter_source_kernel<<<(unsigned)sgrid, dim3(32, gblocks < kSWarps ? gblocks : kSWarps), smem, st>>>(p);
+    const int n = comm_size(w->comm), r = comm_rank(w->comm);
+    const int64_t cn = s->Zp / n;
+    return Shard{r * cn, cn};
+}
+
+static NormOut norm_out(ae_work *w, int mode, double tol, int iteration)
+{
+    return NormOut{w->norm_scratch, w->ctrl, w->comm ? comm_pair_local(w->comm) : nullptr, tol, mode, iteration};
+}
+
+// after a sharded norm kernel: all-gather the pairs (and, for the inner iteration, the new source rows in the
+// same NCCL group), then let every rank apply the combined norm to its control block
+static int finish_sharded_norm(const ae_slab *s, ae_work *w, double *rows, int mode, double tol, int iteration, int gate,
+                               cudaStream_t st)
+{
+    AE_TRY(comm_all_gather_rows(w->comm, rows, s->G, s->Zp, 1, st));
+    norm_finalize_kernel<<<1, 1, 0, st>>>(comm_pairs(w->comm), comm_size(w->comm), mode, w->ctrl, tol, iteration, gate);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }
 
-int launch_fission_base(const ae_slab *s, const double *phi, double *base, cudaStream_t st)
+int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, const double *phi_in, double *phi_out,
+                    double *q_next, int init, double cold, double tol, int iteration, int gate, cudaStream_t st)
 {
-    fission_base_kernel<<<per_cell_blocks(s->Zp), kCB, 0, st>>>(phi, s->s_ext, s->mat, s->chi, s->nusf, s->Zp, s->G, base);
+    const Shard sh = shard_of(s, w);
+    if (s->Zp % (kTile * comm_size(w->comm))) { set_error("Zp must be a multiple of 256 * ranks"); return AE_BAD_ARG; }
+    FinArgs p;
+    p.partial = partial; p.base = w->base; p.mat = s->mat; p.scat = s->scat; p.phi_in = phi_in; p.phi = phi_out;
+    p.q_next = q_next; p.norm = norm_out(w, kNormInner, tol, iteration);
+    p.Z = s->Z; p.Zp = s->Zp; p.c0 = sh.c0; p.cn = sh.cn; p.P = P; p.G = s->G; p.M = s->M;
+    p.init = init; p.gate = gate; p.cold = cold;
+    if (s->G <= kGSmall) {
+        finalize_small_kernel<<<per_cell_blocks(sh.cn), kCB, 0, st>>>(p);
+        AE_CUDA(cudaGetLastError());
+    } else {
+        if (init) {
+            const int64_t n = (int64_t)s->G * s->Zp;
+            int64_t bi = (n + 255) / 256;
+            if (bi > 148 * 32) bi = 148 * 32;
+            flux_init_kernel<<<(unsigned)bi, 256, 0, st>>>(p);
+        } else {
+            // norm_scratch holds 2*per_cell_blocks(Zp) + G (num, den) pairs
+            int64_t bx = (sh.cn / 2 + 255) / 256;
+            const int64_t cap = (2 * (int64_t)per_cell_blocks(s->Zp)) / s->G;
+            if (bx > cap) bx = cap;
+            if (bx > (148 * 48 + s->G - 1) / s->G) bx = (148 * 48 + s->G - 1) / s->G;
+            if (bx < 1) bx = 1;
+            flux_assemble_kernel<<<dim3((unsigned)bx, s->G), 256, 0, st>>>(p);
+        }
+        AE_CUDA(cudaGetLastError());
+        const int gblocks = (s->G + kGB - 1) / kGB;
+        const size_t smem = (size_t)s->G * (gblocks * kGB + kSC) * sizeof(double);
+        if (smem > 220 * 1024) { set_error("flux update: scatter matrix of G=%d does not fit in shared memory", s->G); return AE_BAD_ARG; }
+        if (smem > 48 * 1024)
+            AE_CUDA(cudaFuncSetAttribute((const void *)scatter_source_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int64_t sgrid = sh.cn / kSC;                         // the range is a multiple of 256 cells
+        if (sgrid > 148 * 2) sgrid = 148 * 2;
+        scatter_source_kernel<<<(unsigned)sgrid, dim3(32, gblocks < kSWarps ? gblocks : kSWarps), smem, st>>>(p);
+        AE_CUDA(cudaGetLastError());
+    }
+    if (w->comm) {
+        if (init) AE_TRY(comm_all_gather_rows(w->comm, q_next, s->G, s->Zp, 0, st));
+        else AE_TRY(finish_sharded_norm(s, w, q_next, kNormInner, tol, iteration, gate, st));
+    }
+    return AE_OK;
+}
+
+int launch_fission_base(const ae_slab *s, ae_work *w, const double *phi, double *base, int with_ext, cudaStream_t st)
+{
+    const Shard sh = shard_of(s, w);
+    fission_base_kernel<<<per_cell_blocks(sh.cn), kCB, 0, st>>>(phi, with_ext ? s->s_ext : nullptr, s->mat, s->chi, s->nusf,
+                                                                 s->Zp, sh.c0, sh.cn, s->G, base);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }
 
 int launch_k_update(const ae_slab *s, ae_work *w, double tol, int iteration, cudaStream_t st)
 {
-    k_update_kernel<<<per_cell_blocks(s->Zp), kCB, 0, st>>>(w->phi, w->phi_outer, s->mat, s->nusf, s->Z, s->Zp, s->G, tol,
-                                                            iteration, w->norm_scratch, w->ctrl);
+    const Shard sh = shard_of(s, w);
+    k_update_kernel<<<per_cell_blocks(sh.cn), kCB, 0, st>>>(w->phi, w->phi_outer, s->mat, s->nusf, s->Z, s->Zp, sh.c0, sh.cn,
+                                                             s->G, norm_out(w, kNormK, tol, iteration));
     AE_CUDA(cudaGetLastError());
+    if (w->comm) AE_TRY(finish_sharded_norm(s, w, nullptr, kNormK, tol, iteration, 0, st));
     const int64_t n = (int64_t)s->G * s->Zp;
     const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
     scale_by_k_kernel<<<blocks, 256, 0, st>>>(w->phi, w->ctrl, n, w->phi_outer);
@@ -414,8 +489,11 @@ int launch_k_update(const ae_slab *s, ae_work *w, double tol, int iteration, cud
 
 int launch_outer_check(const ae_slab *s, ae_work *w, cudaStream_t st)
 {
-    outer_check_kernel<<<per_cell_blocks(s->Zp), kCB, 0, st>>>(w->phi, w->phi_outer, s->Zp, s->G, w->norm_scratch, w->ctrl);
+    const Shard sh = shard_of(s, w);
+    outer_check_kernel<<<per_cell_blocks(sh.cn), kCB, 0, st>>>(w->phi, w->phi_outer, s->Zp, sh.c0, sh.cn, s->G,
+                                                                norm_out(w, kNormOuter, 0.0, 0));
     AE_CUDA(cudaGetLastError());
+    if (w->comm) AE_TRY(finish_sharded_norm(s, w, nullptr, kNormOuter, 0.0, 0, 0, st));
     return AE_OK;
 }
 

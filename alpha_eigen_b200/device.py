@@ -85,7 +85,8 @@ class SlabDevice:
             angles = shard_angles(mu, 0, 1)
         self.angles = np.asarray(angles, dtype=np.int64)              # device angle a <-> reference angle angles[a]
         self.Z, self.hx = int(Z), float(hx)
-        self.Zp = layout.padded_cells(self.Z)
+        world = comm.world if comm is not None else 1
+        self.Zp = layout.padded_cells(self.Z, world)                  # equal 256-cell-aligned cell ranges per rank
         self.A_total = len(mu)
         self.A = len(self.angles)
         total = np.asarray(total, dtype=np.float64)
@@ -105,7 +106,7 @@ class SlabDevice:
         self.t_mu = up(mu_loc * ihx)
         self.t_w = up(w_loc)
         self.t_aidx = up(self.angles.astype(np.int32))
-        self.t_mat = up(layout.to_storage(mat.astype(np.int32), self.Z))
+        self.t_mat = up(layout.to_storage(mat.astype(np.int32), self.Z, self.Zp))
         self.t_scat = up(np.asarray(scat, dtype=np.float64).reshape(self.M, self.G, self.G))
         self.t_chi = up(np.asarray(chi, dtype=np.float64).reshape(self.M, self.G))
         self.t_nusf = up(np.asarray(nusf, dtype=np.float64).reshape(self.M, self.G))
@@ -174,14 +175,14 @@ class SlabDevice:
         d = a.to(self.dev, non_blocking=True)
         if out is None:
             out = torch.empty(self.G * self.Zp, dtype=torch.float64, device=self.dev)
-        _lib.check(self.lib.ae_pack_cells(d.data_ptr(), self.Z, self.G, out.data_ptr(), self.stream))
+        _lib.check(self.lib.ae_pack_cells(d.data_ptr(), self.Z, self.Zp, self.G, out.data_ptr(), self.stream))
         return out
 
     def cells_to_host(self, t, out=None):
         """[G][Zp] storage tensor -> (Z,G) logical ndarray (or into the pinned host tensor `out`)."""
         torch = self.torch
         d = torch.empty(self.Z * self.G, dtype=torch.float64, device=self.dev)
-        _lib.check(self.lib.ae_unpack_cells(t.data_ptr(), self.Z, self.G, d.data_ptr(), self.stream))
+        _lib.check(self.lib.ae_unpack_cells(t.data_ptr(), self.Z, self.Zp, self.G, d.data_ptr(), self.stream))
         if out is not None:
             out.copy_(d.view(out.shape), non_blocking=True)
             torch.cuda.current_stream(self.dev).synchronize()
@@ -194,7 +195,7 @@ class SlabDevice:
         h = torch.from_numpy(np.ascontiguousarray(np.asarray(psi, dtype=np.float64).reshape(self.Z, self.A_total, self.G)))
         d = h.to(self.dev)
         out = torch.empty(self.G * self.A * self.Zp, dtype=torch.float64, device=self.dev)
-        _lib.check(self.lib.ae_pack_psi(d.data_ptr(), self.Z, self.A_total, self.G, self.t_aidx.data_ptr(), self.A,
+        _lib.check(self.lib.ae_pack_psi(d.data_ptr(), self.Z, self.Zp, self.A_total, self.G, self.t_aidx.data_ptr(), self.A,
                                         out.data_ptr(), self.stream))
         return out
 
@@ -202,7 +203,7 @@ class SlabDevice:
         """[G][A][Zp] -> (Z, A, G) for the local angles (device angle order)."""
         torch = self.torch
         d = torch.zeros(self.Z * self.A_total * self.G, dtype=torch.float64, device=self.dev)
-        _lib.check(self.lib.ae_unpack_psi(t.data_ptr(), self.Z, self.A_total, self.G, self.t_aidx.data_ptr(), self.A,
+        _lib.check(self.lib.ae_unpack_psi(t.data_ptr(), self.Z, self.Zp, self.A_total, self.G, self.t_aidx.data_ptr(), self.A,
                                           d.data_ptr(), self.stream))
         full = d.cpu().numpy().reshape(self.Z, self.A_total, self.G)
         return np.ascontiguousarray(full[:, self.angles, :])
@@ -280,24 +281,25 @@ class SlabDevice:
         return st, np.array(outer[:], dtype=np.int32), np.array(inner[:], dtype=np.int32)
 
     # ---- DMD ---------------------------------------------------------------------------------
-    def gram(self, snap, row_len, first, count):
+    def gram(self, snap, row_len, first, count, sharded=True):
         """Gram matrix [count][count] of snapshot rows first..first+count-1 of `snap` [steps][row_len];
         summed over ranks when the rows are sharded."""
         g = self.torch.empty(count * count, dtype=self.torch.float64, device=self.dev)
         _lib.check(self.lib.ae_gram(snap.data_ptr() + 8 * first * row_len, row_len, row_len, count, g.data_ptr(),
                                     self.stream))
-        if self.comm is not None:
+        if self.comm is not None and sharded:
             self.comm.allreduce_(g)
         return g
 
-    def tsqr(self, snap, row_len, first, count):
+    def tsqr(self, snap, row_len, first, count, sharded=True):
         """Triangular factor R [count][count] of the snapshot window (Householder TSQR, Q never formed).
-        Row-sharded ranks exchange their factors (allreduce of a zero-padded stack) and merge them."""
+        Row-sharded ranks (`sharded`: every rank holds different rows, e.g. the psi rows of its angles)
+        exchange their factors (allreduce of a zero-padded stack) and merge them."""
         torch = self.torch
         r = torch.empty(count * count, dtype=torch.float64, device=self.dev)
         _lib.check(self.lib.ae_tsqr(snap.data_ptr() + 8 * first * row_len, row_len, row_len, count, r.data_ptr(),
                                     self.stream))
-        if self.comm is not None:
+        if self.comm is not None and sharded:
             stack = torch.zeros(self.comm.world * count * count, dtype=torch.float64, device=self.dev)
             stack[self.comm.rank * count * count:(self.comm.rank + 1) * count * count] = r
             self.comm.allreduce_(stack)

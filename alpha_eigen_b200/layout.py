@@ -11,8 +11,10 @@ TILE = 256
 LANE_CELLS = 8
 
 
-def padded_cells(Z: int) -> int:
-    return (Z + TILE - 1) // TILE * TILE
+def padded_cells(Z: int, ranks: int = 1) -> int:
+    """Storage length of a row: a multiple of 256 cells, and of 256*ranks when the cells are sharded."""
+    unit = TILE * max(int(ranks), 1)
+    return (Z + unit - 1) // unit * unit
 
 
 def storage_index(Z: int) -> np.ndarray:
@@ -23,10 +25,10 @@ def storage_index(Z: int) -> np.ndarray:
     return tile * TILE + (j // 2) * 64 + lane * 2 + (j % 2)
 
 
-def to_storage(a: np.ndarray, Z: int) -> np.ndarray:
+def to_storage(a: np.ndarray, Z: int, Zp: int | None = None) -> np.ndarray:
     """(..., Z) logical order -> (..., Zp) storage order, zero padded."""
     a = np.asarray(a)
-    out = np.zeros(a.shape[:-1] + (padded_cells(Z),), dtype=a.dtype)
+    out = np.zeros(a.shape[:-1] + (Zp if Zp is not None else padded_cells(Z),), dtype=a.dtype)
     out[..., storage_index(Z)] = a
     return out
 

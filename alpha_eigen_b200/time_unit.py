@@ -156,16 +156,16 @@ class TimeUnit:
             rows = [dev.psi_to_device(h[..., st]) for st in range(self.num_steps)]
             self._psi_snap = dev.torch.cat(rows)
         if self.snapshots == "psi" and self._psi_snap is not None:
-            snap, row_len = self._psi_snap, dev.G * dev.A * dev.Zp
+            snap, row_len, sharded = self._psi_snap, dev.G * dev.A * dev.Zp, True      # rows of this rank's angles
         else:
-            snap, row_len = self._phi_snap, dev.G * dev.Zp
+            snap, row_len, sharded = self._phi_snap, dev.G * dev.Zp, False            # phi is replicated on every rank
         if snap is None:
             raise RuntimeError("no snapshots: call calculate_time_dependent_flux() first")
         if method == "gram":
-            fac = dev.gram(snap, row_len, first, K + 1)
+            fac = dev.gram(snap, row_len, first, K + 1, sharded)
             alphas, sigma, r = dev.dmd_from_gram(fac, K, self.dt, rank_tol)
         else:
-            fac = dev.tsqr(snap, row_len, first, K + 1)
+            fac = dev.tsqr(snap, row_len, first, K + 1, sharded)
             alphas, sigma, r = dev.dmd_from_r(fac, K, self.dt, rank_tol)
         if return_info:
             return alphas, dict(sigma=sigma, rank=r, first=first, K=K, method=method,

@@ -148,7 +148,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from alpha_eigen_b200 import distributed
+    from alpha_eigen_b200 import _lib, distributed
     from alpha_eigen_b200.device import SlabDevice, shard_angles
     from alpha_eigen_b200.synthetic import synthetic_problem
 
@@ -186,21 +186,18 @@ def main():
             ev[1].record()
         launches += 1
         if comm is not None:
-            dev.lib.ae_reduce_partials(dev.slab, dev.partial.data_ptr(), dev.P, dev.reduced.data_ptr(), dev.stream)
+            _lib.check(dev.lib.ae_exchange_partials(dev.slab, dev.work, dev.stream))   # local sum + reduce-scatter by rows
             if ev is not None:
                 ev[2].record()
-            comm.allreduce_(dev.reduced)
-            if ev is not None:
-                ev[3].record()
-            dev.flux_update(dev.reduced, 1, q[(i + 1) & 1], 0.0, i + 1)
-            launches += 4                                   # reduce, (nccl), assemble, scatter
+            dev.flux_update(dev.reduced, 1, q[(i + 1) & 1], 0.0, i + 1)             # 1/N of the cells + all-gather of q
+            launches += 5                                   # reduce, (nccl), assemble, scatter, (nccl), norm
         else:
             if ev is not None:
-                ev[2].record(); ev[3].record()
+                ev[2].record()
             dev.flux_update(dev.partial, dev.P, q[(i + 1) & 1], 0.0, i + 1)
             launches += 2                                   # assemble, scatter
         if ev is not None:
-            ev[4].record()
+            ev[3].record()
 
     def fence():
         if world > 1:
@@ -214,7 +211,7 @@ def main():
     if rank == 0:
         sampler.start()
     launches = 0
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
     t_beg.record()
@@ -224,7 +221,7 @@ def main():
     fence()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = t_beg.elapsed_time(t_end)
-    phase = [float(np.mean([e[k].elapsed_time(e[k + 1]) for e in evs])) for k in range(4)]
+    phase = [float(np.mean([e[k].elapsed_time(e[k + 1]) for e in evs])) for k in range(3)]
     if world > 1:
         t = torch.tensor([ms_total] + phase, dtype=torch.float64, device=dev.dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -269,14 +266,15 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "Z": Z, "A": A, "G": G, "dt": DT, "rows_per_gpu": dev.A * G,
                        "sharding": f"angle x group rows dealt by angle over {world} rank(s)",
-                       "step": "psi-streaming sweep set (in place) + phi allreduce (N>1) + flux-update kernel",
+                       "step": "psi-streaming sweep set (in place) + flux reduce-scatter (N>1) + flux-update kernels on "
+                               "1/N of the cells + all-gather of the new source (N>1)",
                        "l2": "inputs (psi %.1f GB per GPU) are larger than L2" % (psi.numel() * 8 / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None, "kernel": "ae::sweep_kernel<NA,true,true>",
                          "kernel_ms": sweep_ms, "bytes_per_update": bytes_per_update, "peak_source": peak_src,
                          "sweep_share_of_step": sweep_ms / ms_per_step},
-            "breakdown_ms": {"sweep": phase[0], "reduce_partials": phase[1], "allreduce": phase[2],
-                             "flux_update": phase[3]},
+            "breakdown_ms": {"sweep": phase[0], "exchange_reduce_scatter": phase[1],
+                             "flux_update_and_allgather": phase[2]},
             "e2e": {"value": updates_per_step / (e_ms * 1e-3), "unit": "updates/s", "ms_per_step": e_ms,
                     "h2d_bytes_per_step": Z * G * 8, "d2h_bytes_per_step": Z * G * 8,
                     "what": "host q (pinned) -> device, sweep set + flux update on resident psi, phi -> host"},

@@ -91,6 +91,7 @@ typedef struct ae_work {
 int ae_abi_version(void);
 const char *ae_last_error(void);
 int64_t ae_padded_cells(int64_t Z);
+int64_t ae_padded_cells_sharded(int64_t Z, int32_t nranks);   /* multiple of 256*nranks: equal cell ranges per rank */
 int64_t ae_cell_offset(int64_t z);              /* storage offset of logical cell z */
 int32_t ae_partial_count(int32_t A, int32_t n_neg);
 int64_t ae_norm_blocks(int64_t Zp);
@@ -118,15 +119,21 @@ int ae_reduce_partials(const ae_slab *s, const double *partial, int32_t P, doubl
 int ae_flux_update(const ae_slab *s, ae_work *w, const double *partial, int32_t P, double *q_next,
                    double tol, int32_t iteration, void *stream);
 
+/* Multi-GPU only: w->reduced := sum of the local angle-block partials, then reduce-scattered by rows over
+ * the ranks so that this rank holds the rank-summed flux of its own cell range [r*Zp/N, (r+1)*Zp/N).
+ * Follow with ae_flux_update(s, w, w->reduced, 1, ...), which updates that range and all-gathers the
+ * new source.  Zp must be a multiple of 256*N (ae_padded_cells_sharded). */
+int ae_exchange_partials(const ae_slab *s, ae_work *w, void *stream);
+
 /* ---- layout conversion at the boundary (device to device) ------------------------------- */
 /* cells: logical [Z][G] (phi.new of group.py:18) <-> storage [G][Zp] */
-int ae_pack_cells(const double *logical, int64_t Z, int32_t G, double *storage, void *stream);
-int ae_unpack_cells(const double *storage, int64_t Z, int32_t G, double *logical, void *stream);
+int ae_pack_cells(const double *logical, int64_t Z, int64_t Zp, int32_t G, double *storage, void *stream);
+int ae_unpack_cells(const double *storage, int64_t Z, int64_t Zp, int32_t G, double *logical, void *stream);
 /* psi: logical [Z][A_total][G] (TimeUnit.psi[..., step], time_unit.py:14) <-> storage [G][A][Zp];
  * angle_index [A] (device) maps local angle a to the reference angle number. */
-int ae_pack_psi(const double *logical, int64_t Z, int32_t A_total, int32_t G, const int32_t *angle_index,
+int ae_pack_psi(const double *logical, int64_t Z, int64_t Zp, int32_t A_total, int32_t G, const int32_t *angle_index,
                 int32_t A, double *storage, void *stream);
-int ae_unpack_psi(const double *storage, int64_t Z, int32_t A_total, int32_t G, const int32_t *angle_index,
+int ae_unpack_psi(const double *storage, int64_t Z, int64_t Zp, int32_t A_total, int32_t G, const int32_t *angle_index,
                   int32_t A, double *logical, void *stream);
 
 /* ---- source iteration: OneGroup.source_iteration_for_scalar_flux (group.py:62-81) and
@@ -186,6 +193,8 @@ int ae_dmd_from_r(const double *r, int32_t K, double dt, double rank_tol,
 int ae_comm_unique_id(void *id128);                                     /* host, 128 bytes */
 int ae_comm_init(void **comm, int32_t rank, int32_t nranks, const void *id128);
 int ae_comm_allreduce_sum(void *comm, double *buf, int64_t count, void *stream);
+/* rows [G][Zp]: every rank contributes its cell range of every row, in place (all-gather). */
+int ae_comm_gather_rows(void *comm, double *rows, int32_t G, int64_t Zp, void *stream);
 int ae_comm_destroy(void *comm);
 
 #ifdef __cplusplus
