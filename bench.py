@@ -260,6 +260,8 @@ def main():
         bytes_per_update = 16.0 + 24.0 / dev.A + 8.0 * dev.P / dev.A    # psi r+w, hs/q/cdt over angles, partial
         alg_bytes = bytes_per_update * local_updates
         achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch (profiles/r01_c4_kernel_dram_bytes_v5.csv)
+        traffic = 322.4e9 if (args.workload == "c4" and world == 1 and not args.cells) else None
         line = {
             "metric": "sweep cell*angle*group updates/s", "value": value, "unit": "updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -270,7 +272,8 @@ def main():
                                "1/N of the cells + all-gather of the new source (N>1)",
                        "l2": "inputs (psi %.1f GB per GPU) are larger than L2" % (psi.numel() * 8 / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "kernel": "ae::sweep_kernel<NA,true,true>",
+                         "frac": achieved / hbm_peak, "traffic": traffic,
+                         "algorithmic_bytes": alg_bytes, "kernel": "ae::sweep_kernel<16,true,true> (8 for fewer than 16 angles per direction)",
                          "kernel_ms": sweep_ms, "bytes_per_update": bytes_per_update, "peak_source": peak_src,
                          "sweep_share_of_step": sweep_ms / ms_per_step},
             "breakdown_ms": {"sweep": phase[0], "exchange_reduce_scatter": phase[1],
