@@ -1,0 +1,172 @@
+"""GPU tests of the drop-in surface: the reference's classes, CLI and the boundary helpers of the C ABI."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def _kp(cpm, A):
+    from alpha_eigen_modules.group import OneGroup
+    from alpha_eigen_modules.material import SimpleMaterial
+    from alpha_eigen_modules.slab import SymmetricHeterogeneousSlab
+    np.random.seed(2021)
+    f, m, a = SimpleMaterial('fuel', 1), SimpleMaterial('moderator', 1), SimpleMaterial('absorber', 1)
+    s = SymmetricHeterogeneousSlab(9, cpm, A, m, fuel_mat=f, abs_mat=a)
+    g = OneGroup(slab=s)
+    g.create_zones()
+    return s, g
+
+
+def test_reference_test_body_runs_unchanged():
+    """The body of the reference's own test (tests/test_short_kornreich_parsons.py:17-42), through the
+    alias package, both configurations in one process like the reference does."""
+    from alpha_eigen_modules.group import OneGroup
+    from alpha_eigen_modules.material import SimpleMaterial
+    from alpha_eigen_modules.slab import SymmetricHeterogeneousSlab
+
+    def calculate_k_eigenvalue(length, cells_per_mfp, num_angles):
+        fuel = SimpleMaterial('fuel', num_groups=1)
+        moderator = SimpleMaterial('moderator', num_groups=1)
+        absorber = SimpleMaterial('absorber', num_groups=1)
+        slab = SymmetricHeterogeneousSlab(length, cells_per_mfp, num_angles, moderator, fuel_mat=fuel, abs_mat=absorber)
+        one_group = OneGroup(slab=slab)
+        one_group.create_zones()
+        return one_group.perform_power_iteration(quiet=True)
+
+    np.random.seed(2021)
+    k = calculate_k_eigenvalue(length=9, cells_per_mfp=50, num_angles=4)
+    assert abs(k.old - 0.9358157950764868) < 1e-8
+    k = calculate_k_eigenvalue(length=9, cells_per_mfp=100, num_angles=16)     # RNG state now differs from a fresh process
+    assert abs(k.old - 0.9885264464200719) < 1e-8
+
+
+def test_cli_matches_reference_flags():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), "--problem", "kornreich-parsons-symmetric",
+                          "--length", "9", "--cells_per_mfp", "10", "--num_angles", "4"], capture_output=True, text=True,
+                         cwd=ROOT, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "Initiating k-eigenvalue solver" in out.stdout and "Power Iteration 1 : k =" in out.stdout
+    assert abs(float(out.stdout.strip().splitlines()[-1]) - 0.934364027690702) < 1e-9      # oracle value for this mesh
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), "--problem", "kornreich-parsons-symmetric",
+                          "--cells_per_mfp", "10", "--num_angles", "4", "--steps", "20"], capture_output=True, text=True,
+                         cwd=ROOT, timeout=300)
+    assert out.returncode == 0, out.stderr          # the reference crashes here (defects D1-D5)
+    assert "alphas =" in out.stdout
+
+
+def test_sweep1D_honours_explicit_sigT_in_both_directions():
+    """Repair R5: the reference ignores sigT for mu < 0 (group.py:56); the oracle and the device do not."""
+    from oracle import ae_oracle as orc
+    s, g = _kp(10, 4)
+    rs = np.random.RandomState(1)
+    src = rs.rand(s.num_zones, 1)
+    sigT = g.total_xs + 10.0 * g.inv_speed
+    for n in range(4):
+        psi = g.sweep1D(g.angle[n], src, sigT)
+        assert _rel(psi, orc.sweep(s.mu[n], s.hx, src, sigT)) < 1e-13
+
+
+def test_one_step_flux_matches_oracle_step():
+    """TimeUnit.calculate_one_step_flux with an explicit per-angle source (time_unit.py:29-42)."""
+    from alpha_eigen_modules.time_unit import TimeUnit
+    from oracle import ae_oracle as orc
+    from tests.kp import kp_problem, kp_psi0
+    s, g = _kp(10, 4)
+    tu = TimeUnit(slab=s, group=g, num_steps=1, dt=0.1)
+    p = kp_problem(9, 10, 4)
+    psi0 = kp_psi0(p)
+    source = psi0 * (p["inv_speed"][:, None, :] / 0.1)                  # S + psi_prev*inv_speed/dt with S = 0
+    outer, inner = tu.calculate_one_step_flux(source)
+    res = orc.time_march(p["mu"], p["weight"], p["hx"], p["tables"], np.zeros((p["Z"], 1)), psi0, 0.1, 1)
+    assert (outer, inner) == (int(res["outer"][0]), int(res["inner"][0]))
+    assert _rel(g.phi.new, res["phi_last"]) < 1e-10
+    psi = np.stack([a.psi_midpoint for a in g.angle], axis=1)
+    assert _rel(psi, res["psi_last"]) < 1e-10
+
+
+def test_multigroup_classes_against_oracle():
+    """MultiGroup + TableMaterial on the scaled five-region slab: k and a short time march."""
+    from alpha_eigen_b200.group import MultiGroup
+    from alpha_eigen_b200.slab import ScaledHeterogeneousSlab
+    from alpha_eigen_b200.synthetic import synthetic_materials, synthetic_problem
+    from alpha_eigen_b200.time_unit import TimeUnit
+    from oracle import ae_oracle as orc
+    Z, A, G = 700, 8, 12
+    fuel, mod, absb = synthetic_materials(G)
+    np.random.seed(2021)
+    s = ScaledHeterogeneousSlab(Z, A, mod, fuel, absb)
+    assert s.num_groups == G
+    mg = MultiGroup(s)
+    mg.create_zones()
+    p = synthetic_problem(Z, A, G)
+    np.testing.assert_array_equal(mg._mat_index == 0, p["mat"] == 0)    # same region layout as the array builder
+    tab = orc.Tables(mg._mat_index, *[np.array([getattr(m, n) for m in mg._materials]) for n in
+                                      ("total_xs", "scatter_xs", "chi", "nu_sigmaf", "inv_speed")])
+    phi0 = mg.phi.old.copy()
+    k = mg.perform_power_iteration(quiet=True)
+    ro = orc.power_iteration(s.mu, s.weight, s.hx, tab, phi0)
+    assert ro["status"] == 0 and abs(k.new - ro["k_new"]) < 1e-9
+    assert _rel(mg.phi.new, ro["phi_new"]) < 1e-10
+    steps = 3
+    psi0 = np.repeat(0.5 * mg.phi.new[:, None, :], A, axis=1)
+    tu = TimeUnit(slab=s, group=mg, num_steps=steps, dt=0.1)
+    mg.source = np.zeros((Z, G))
+    tu.calculate_time_dependent_flux()
+    res = orc.time_march(s.mu, s.weight, s.hx, tab, np.zeros((Z, G)), psi0, 0.1, steps)
+    assert list(tu.outer_iterations) == list(res["outer"]) and list(tu.inner_iterations) == list(res["inner"])
+    assert _rel(tu.psi, res["psi_snap"]) < 1e-10
+    assert _rel(tu.phi, res["phi_snap"]) < 1e-10
+
+
+def test_pack_unpack_roundtrip_and_padding():
+    from alpha_eigen_b200.device import SlabDevice
+    Z, A, G = 1000, 6, 3
+    mu, w = np.polynomial.legendre.leggauss(A)
+    one = np.ones((1, G))
+    dev = SlabDevice(Z, 1.0, mu, w, np.zeros(Z, dtype=np.int64), one, np.zeros((1, G, G)), one, one, one)
+    rs = np.random.RandomState(0)
+    a = rs.rand(Z, G)
+    t = dev.cells_to_device(a)
+    np.testing.assert_array_equal(dev.cells_to_host(t), a)
+    raw = t.cpu().numpy().reshape(G, dev.Zp)
+    assert dev.Zp == 1024 and np.count_nonzero(raw) == Z * G            # padding cells are zero
+    psi = rs.rand(Z, A, G)
+    tp = dev.psi_to_device(psi)
+    np.testing.assert_array_equal(dev.psi_to_host(tp), psi[:, dev.angles, :])
+
+
+def test_flux_update_entry_point_matches_numpy():
+    """ae_sweep_set + ae_flux_update as bench.py chains them: phi = sum of partials, change, next source."""
+    from oracle import ae_oracle as orc
+    from tests.test_gpu_parity import _device, _mg_problem
+    Z, A, G = 900, 16, 12
+    p = _mg_problem(Z, A, G, seed=5)
+    t = p["tables"]
+    dev = _device(p)
+    q = p["rs"].rand(Z, G)
+    base = p["rs"].rand(Z, G)
+    phi_prev = p["rs"].rand(Z, G)
+    dev.base.copy_(dev.cells_to_device(base))
+    dev.phi.copy_(dev.cells_to_device(phi_prev))
+    dq = dev.cells_to_device(q)
+    import ctypes as C
+    from alpha_eigen_b200 import _lib
+    _lib.check(dev.lib.ae_sweep_set(C.byref(dev.slab), dq.data_ptr(), None, None, dev.partial.data_ptr(),
+                                    dev.sync.data_ptr(), dev.stream))
+    dev.flux_update(dev.partial, dev.P, dev.q1, tol=1e-30, iteration=7)
+    phi_o = orc.sweep_set(p["mu"], p["weight"], p["hx"], q, t.total[t.mat])
+    assert _rel(dev.cells_to_host(dev.phi), phi_o) < 1e-13
+    q_next = base + 0.5 * np.einsum("zp,zpg->zg", phi_o, t.scat[t.mat])
+    assert _rel(dev.cells_to_host(dev.q1), q_next) < 1e-13
+    ctrl = dev.read_ctrl()
+    change = np.linalg.norm(phi_o - phi_prev) / np.linalg.norm(phi_o)
+    assert abs(ctrl.change - change) < 1e-12 * change and ctrl.inner_iters == 7 and ctrl.inner_done == 0
