@@ -132,11 +132,31 @@ def case_c3_alpha(out, Z=100_000, A=64, G=70, steps=200):
          "sigma_rel": [float(x) for x in (sig[:8] / sig[0])]})
 
 
+def case_c5_sample(out, E=32, Z=2048, A=16, G=12, steps=200, concurrent=12):
+    """BASELINE configs[4] on a sample of the 1024-member ensemble: members/s with `concurrent` members in
+    flight on one GPU (member-parallel mode; every member is an independent solve)."""
+    from alpha_eigen_b200.ensemble import Ensemble, synthetic_ensemble
+    members = synthetic_ensemble(1024, Z, A, G)[:: 1024 // E][:E]
+    Ensemble(members[:2], dt=0.1, num_steps=20, concurrent=2).run()          # warm-up
+    sync(); t0 = time.perf_counter()
+    res = Ensemble(members, dt=0.1, num_steps=steps, concurrent=concurrent).run()
+    sync(); t1 = time.perf_counter()
+    sweeps = sum(int(np.sum(r["inner"])) + steps for r in res)
+    out({"case": "c5_ensemble_sample", "members": E, "of": 1024, "Z": Z, "A": A, "G": G, "steps": steps,
+         "concurrent_members": concurrent, "wall_s": t1 - t0, "members_per_s": E / (t1 - t0),
+         "sweep_sets": sweeps, "updates_per_s": float(sweeps) * Z * A * G / (t1 - t0),
+         "all_converged": all(r["status"] == 0 for r in res),
+         "alpha0_first_last": [float(res[0]["alphas"][0].real), float(res[-1]["alphas"][0].real)],
+         "ranks": [int(res[0]["rank"]), int(res[-1]["rank"])]})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "eig_bench.jsonl"))
     ap.add_argument("--skip-c3", action="store_true")
     ap.add_argument("--skip-long", action="store_true")
+    ap.add_argument("--skip-c5", action="store_true")
+    ap.add_argument("--only-c5", action="store_true")
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     f = open(args.out, "w")
@@ -147,6 +167,10 @@ def main():
         f.write(s + "\n")
         f.flush()
 
+    if args.only_c5:
+        case_c5_sample(out)
+        f.close()
+        return
     case_kp_k(out)
     case_kp_alpha(out, 10, 4, 50)
     case_kp_alpha(out, 50, 16, 200)
@@ -154,6 +178,8 @@ def main():
         case_kp_alpha(out, 200, 64, 200, check_oracle=False)
     if not args.skip_c3:
         case_c3_alpha(out)
+    if not args.skip_c5:
+        case_c5_sample(out)
     f.close()
 
 

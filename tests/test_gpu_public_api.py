@@ -170,3 +170,27 @@ def test_flux_update_entry_point_matches_numpy():
     ctrl = dev.read_ctrl()
     change = np.linalg.norm(phi_o - phi_prev) / np.linalg.norm(phi_o)
     assert abs(ctrl.change - change) < 1e-12 * change and ctrl.inner_iters == 7 and ctrl.inner_done == 0
+
+
+def test_ensemble_members_match_standalone_oracle():
+    """BASELINE configs[4] in miniature: every member of a concurrently solved ensemble equals its own
+    stand-alone oracle solve (iteration counts, psi) and carries its own alpha spectrum."""
+    from alpha_eigen_b200.ensemble import Ensemble, synthetic_ensemble
+    from oracle import ae_oracle as orc
+    E, Z, A, G, steps = 5, 300, 4, 3, 12
+    members = synthetic_ensemble(E, Z, A, G)
+    res = Ensemble(members, dt=0.1, num_steps=steps, concurrent=3).run(keep_snapshots=True)
+    dom = []
+    for p, r in zip(members, res):
+        tab = orc.Tables(p["mat"], p["total"], p["scat"], p["chi"], p["nusf"], p["invspeed"])
+        psi0 = np.repeat(0.5 * p["phi0"][:, None, :], A, axis=1)
+        ro = orc.time_march(p["mu"], p["weight"], p["hx"], tab, np.zeros((Z, G)), psi0, 0.1, steps, want_phi_snap=False)
+        assert r["status"] == 0 and ro["status"] == 0
+        assert list(r["outer"]) == list(ro["outer"]) and list(r["inner"]) == list(ro["inner"])
+        assert _rel(r["psi_last"], ro["psi_last"][:, r["angles"], :]) < 1e-10
+        ref = orc.dmd_alpha(ro["psi_snap"].reshape(-1, steps), steps, 0.1)
+        ref = ref[np.lexsort((ref.imag, -ref.real))]
+        assert r["rank"] == len(ref)
+        assert abs(r["alphas"][0] - ref[0]) < 1e-6 * abs(ref[0])
+        dom.append(r["alphas"][0].real)
+    assert len(set(np.round(dom, 8))) == E          # parameter variation shows up in the spectrum
