@@ -13,6 +13,8 @@ int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double
 int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, const double *phi_in, double *phi_out,
                     double *q_next, int init, double cold, double tol, int iteration, int gate, cudaStream_t st);
 int launch_fission_base(const ae_slab *s, ae_work *w, const double *phi, double *base, int with_ext, cudaStream_t st);
+int launch_small_source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, double cold, double tol,
+                                  int max_iterations, int *launched, cudaStream_t st);
 int comm_reduce_scatter_rows(void *comm, double *rows, int G, int64_t Zp, cudaStream_t st);
 int comm_all_gather_rows(void *comm, double *rows, int G, int64_t Zp, int with_pairs, cudaStream_t st);
 
@@ -53,6 +55,17 @@ static int source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, 
     double *q[2] = {w->q0, w->q1};
     double *phi[2] = {w->phi, w->phi_alt};
     const int batch = w->batch > 0 ? w->batch : 1;
+    // small slabs: the whole loop runs in one cooperative kernel (ae_small.cu), one host read at the end
+    int fused = 0;
+    AE_TRY(launch_small_source_iteration(s, w, psi_in, cold, tol, max_iterations, &fused, st));
+    if (fused) {
+        AE_TRY(poll_ctrl(w, st));
+        const int n = w->ctrl_host->inner_iters;
+        if (iters) *iters = n;
+        if (last_q) *last_q = (n - 1) & 1;
+        if (n & 1) { w->phi = phi[1]; w->phi_alt = phi[0]; }
+        return w->ctrl_host->inner_done ? AE_OK : AE_NOT_CONVERGED;
+    }
     // phi_old = cold (group.py:66 / time_unit.py:45); q0 = base + 0.5*sigma_s*phi_old (group.py:73)
     AE_TRY(launch_finalize(s, w, nullptr, 0, nullptr, phi[0], q[0], 1, cold, tol, 0, 0, st));
     int it = 0;         // iterations launched so far
