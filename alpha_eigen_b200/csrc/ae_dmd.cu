@@ -172,12 +172,21 @@ __global__ void __launch_bounds__(128) tsqr_kernel(const double *__restrict__ in
             const int j = tid;
             if (j == k) W[k * ldw + k] = hh[2];
             if (j > k && j < n && tau != 0.0) {
-                double dot = 0.0;
-                for (int b = 0; b < B; ++b) dot = fma(W[(n + b) * ldw + k], W[(n + b) * ldw + j], dot);
+                double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;             // four chains: the FMA latency, not the LDS
+                int b = 0;                                                  // rate, bounds this loop
+                for (; b + 4 <= B; b += 4) {
+                    d0 = fma(W[(n + b) * ldw + k], W[(n + b) * ldw + j], d0);
+                    d1 = fma(W[(n + b + 1) * ldw + k], W[(n + b + 1) * ldw + j], d1);
+                    d2 = fma(W[(n + b + 2) * ldw + k], W[(n + b + 2) * ldw + j], d2);
+                    d3 = fma(W[(n + b + 3) * ldw + k], W[(n + b + 3) * ldw + j], d3);
+                }
+                for (; b < B; ++b) d0 = fma(W[(n + b) * ldw + k], W[(n + b) * ldw + j], d0);
+                const double dot = (d0 + d1) + (d2 + d3);
                 const double w = tau * fma(inv, dot, W[k * ldw + j]);
                 W[k * ldw + j] -= w;
                 const double wi = w * inv;
-                for (int b = 0; b < B; ++b) W[(n + b) * ldw + j] = fma(-wi, W[(n + b) * ldw + k], W[(n + b) * ldw + j]);
+#pragma unroll 4
+                for (int b2 = 0; b2 < B; ++b2) W[(n + b2) * ldw + j] = fma(-wi, W[(n + b2) * ldw + k], W[(n + b2) * ldw + j]);
             }
             __syncthreads();
         }
@@ -222,6 +231,19 @@ __global__ void atilde_from_svd_kernel(const double *__restrict__ U, int ldu, co
     }
 }
 
+// One cuSOLVER handle per host thread (creation costs milliseconds and synchronises the device, which would
+// serialise the concurrent member solves of an ensemble).
+struct SolverCtx {
+    cusolverDnHandle_t h = nullptr;
+    cusolverDnParams_t params = nullptr;
+    ~SolverCtx()
+    {
+        if (params) cusolverDnDestroyParams(params);
+        if (h) cusolverDnDestroy(h);
+    }
+};
+static thread_local SolverCtx t_solver;
+
 static int cusolver_fail(cusolverStatus_t st, const char *what)
 {
     set_error("%s failed with cusolver status %d", what, (int)st);
@@ -232,6 +254,22 @@ static int cusolver_fail(cusolverStatus_t st, const char *what)
         cusolverStatus_t s_ = (call);                                  \
         if (s_ != CUSOLVER_STATUS_SUCCESS) { status = cusolver_fail(s_, #call); goto done; } \
     } while (0)
+static int solver_ctx(cudaStream_t st, cusolverDnHandle_t *h, cusolverDnParams_t *params)
+{
+    int status = AE_OK;
+    if (!t_solver.h) {
+        cusolverStatus_t s_ = cusolverDnCreate(&t_solver.h);
+        if (s_ != CUSOLVER_STATUS_SUCCESS) return cusolver_fail(s_, "cusolverDnCreate");
+        s_ = cusolverDnCreateParams(&t_solver.params);
+        if (s_ != CUSOLVER_STATUS_SUCCESS) return cusolver_fail(s_, "cusolverDnCreateParams");
+    }
+    cusolverStatus_t s2 = cusolverDnSetStream(t_solver.h, st);
+    if (s2 != CUSOLVER_STATUS_SUCCESS) return cusolver_fail(s2, "cusolverDnSetStream");
+    *h = t_solver.h;
+    *params = t_solver.params;
+    return status;
+}
+
 #define AE_CUDA_G(call)                                                \
     do {                                                               \
         cudaError_t e_ = (call);                                       \
@@ -284,16 +322,15 @@ extern "C" int ae_dmd_from_gram(const double *gram_dev, int32_t K, double dt, do
     double *lam = (double *)malloc(sizeof(double) * K), *sig = (double *)malloc(sizeof(double) * K),
            *inv = (double *)malloc(sizeof(double) * K), *W = (double *)malloc(sizeof(double) * 2 * K);
 
-    AE_CUSOLVER(cusolverDnCreate(&h));
-    AE_CUSOLVER(cusolverDnSetStream(h, st));
-    AE_CUDA_G(cudaMalloc((void **)&dV, sizeof(double) * K * K));
-    AE_CUDA_G(cudaMalloc((void **)&dW, sizeof(double) * K));
-    AE_CUDA_G(cudaMalloc((void **)&dinfo, sizeof(int)));
+    if ((status = solver_ctx(st, &h, &params)) != AE_OK) goto done;
+    AE_CUDA_G(cudaMallocAsync((void **)&dV, sizeof(double) * K * K, st));
+    AE_CUDA_G(cudaMallocAsync((void **)&dW, sizeof(double) * K, st));
+    AE_CUDA_G(cudaMallocAsync((void **)&dinfo, sizeof(int), st));
     // Cxx = gram[0:K,0:K] (symmetric, so row/column-major agree)
     AE_CUDA_G(cudaMemcpy2DAsync(dV, sizeof(double) * K, gram_dev, sizeof(double) * n, sizeof(double) * K, K,
                                 cudaMemcpyDeviceToDevice, st));
     AE_CUSOLVER(cusolverDnDsyevd_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, K, dV, K, dW, &lwork));
-    AE_CUDA_G(cudaMalloc((void **)&dwork, sizeof(double) * (size_t)lwork));
+    AE_CUDA_G(cudaMallocAsync((void **)&dwork, sizeof(double) * (size_t)lwork, st));
     AE_CUSOLVER(cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, K, dV, K, dW, dwork, lwork, dinfo));
     AE_CUDA_G(cudaMemcpyAsync(lam, dW, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
     AE_CUDA_G(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -316,19 +353,18 @@ extern "C" int ae_dmd_from_gram(const double *gram_dev, int32_t K, double dt, do
         for (int j = 0; j < r; ++j) inv[j] = 1.0 / sig[j];
         if (sigma_out) memcpy(sigma_out, sig, sizeof(double) * K);
     }
-    AE_CUDA_G(cudaMalloc((void **)&dT, sizeof(double) * K * r));
-    AE_CUDA_G(cudaMalloc((void **)&dAt, sizeof(double) * r * r));
-    AE_CUDA_G(cudaMalloc((void **)&dInv, sizeof(double) * r));
-    AE_CUDA_G(cudaMalloc((void **)&dEig, sizeof(double) * 2 * r));
+    AE_CUDA_G(cudaMallocAsync((void **)&dT, sizeof(double) * K * r, st));
+    AE_CUDA_G(cudaMallocAsync((void **)&dAt, sizeof(double) * r * r, st));
+    AE_CUDA_G(cudaMallocAsync((void **)&dInv, sizeof(double) * r, st));
+    AE_CUDA_G(cudaMallocAsync((void **)&dEig, sizeof(double) * 2 * r, st));
     AE_CUDA_G(cudaMemcpyAsync(dInv, inv, sizeof(double) * r, cudaMemcpyHostToDevice, st));
     atilde_kernel<<<1, 1024, 0, st>>>(gram_dev, n, dV, dInv, K, r, dT, dAt);
     AE_CUDA_G(cudaGetLastError());
     // eigenvalues of the real non-symmetric r x r matrix (time_unit.py:90)
-    AE_CUSOLVER(cusolverDnCreateParams(&params));
     AE_CUSOLVER(cusolverDnXgeev_bufferSize(h, params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, r, CUDA_R_64F,
                                            dAt, r, CUDA_C_64F, dEig, CUDA_R_64F, nullptr, 1, CUDA_R_64F, nullptr, 1,
                                            CUDA_R_64F, &dbytes, &hbytes));
-    AE_CUDA_G(cudaMalloc(&dbuf, dbytes ? dbytes : 8));
+    AE_CUDA_G(cudaMallocAsync(&dbuf, dbytes ? dbytes : 8, st));
     hbuf = malloc(hbytes ? hbytes : 8);
     AE_CUSOLVER(cusolverDnXgeev(h, params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, r, CUDA_R_64F, dAt, r,
                                 CUDA_C_64F, dEig, CUDA_R_64F, nullptr, 1, CUDA_R_64F, nullptr, 1, CUDA_R_64F, dbuf,
@@ -345,10 +381,8 @@ extern "C" int ae_dmd_from_gram(const double *gram_dev, int32_t K, double dt, do
     }
     *rank = r;
 done:
-    if (params) cusolverDnDestroyParams(params);
-    if (h) cusolverDnDestroy(h);
-    cudaFree(dV); cudaFree(dW); cudaFree(dwork); cudaFree(dT); cudaFree(dAt); cudaFree(dInv); cudaFree(dEig);
-    cudaFree(dbuf); cudaFree(dinfo);
+    cudaFreeAsync(dV, st); cudaFreeAsync(dW, st); cudaFreeAsync(dwork, st); cudaFreeAsync(dT, st); cudaFreeAsync(dAt, st); cudaFreeAsync(dInv, st); cudaFreeAsync(dEig, st);
+    cudaFreeAsync(dbuf, st); cudaFreeAsync(dinfo, st);
     free(hbuf); free(lam); free(sig); free(inv); free(W);
     return status;
 }
@@ -374,13 +408,26 @@ extern "C" int ae_tsqr(const double *snap, int64_t ld, int64_t len, int32_t n, d
     int64_t rows = (len + ncta - 1) / ncta;
     rows = (rows + B - 1) / B * B;
     ncta = (int)((len + rows - 1) / rows);
-    double *parts = nullptr;
+    double *parts = nullptr, *parts2 = nullptr;
     AE_CUDA(cudaMallocAsync((void **)&parts, (size_t)ncta * n * n * sizeof(double), st));
+    AE_CUDA(cudaMallocAsync((void **)&parts2, (size_t)((ncta + 11) / 12) * n * n * sizeof(double), st));
     tsqr_kernel<<<ncta, 128, smem, st>>>(snap, ld, len, n, 0, rows, B, parts);
-    // second level: QR of the stacked triangles (ncta*n x n, row-major) in one CTA
-    tsqr_kernel<<<1, 128, smem, st>>>(parts, n, (int64_t)ncta * n, n, 1, (int64_t)ncta * n, B, r_out);
+    // merge tree: QR of stacked triangles (row-major), 12 per CTA and level, so no CTA ever chews on more
+    // than ~15 blocks (one CTA merging all 148 triangles was 60 % of the run time on small problems)
+    int count = ncta;
+    double *in = parts, *out = parts2;
+    while (count > 1) {
+        const int next = count <= 16 ? 1 : (count + 11) / 12;
+        const int per = (count + next - 1) / next;
+        double *dst = next == 1 ? r_out : out;
+        tsqr_kernel<<<next, 128, smem, st>>>(in, n, (int64_t)count * n, n, 1, (int64_t)per * n, B, dst);
+        count = next;
+        double *t = in; in = out; out = t;
+    }
+    if (ncta == 1) AE_CUDA(cudaMemcpyAsync(r_out, parts, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(parts, st);
+    cudaFreeAsync(parts2, st);
     AE_CUDA(e);
     return AE_OK;
 }
@@ -416,19 +463,18 @@ extern "C" int ae_dmd_from_r(const double *r_dev, int32_t K, double dt, double r
     double *sig = (double *)malloc(sizeof(double) * K), *inv = (double *)malloc(sizeof(double) * K),
            *W = (double *)malloc(sizeof(double) * 2 * K);
 
-    AE_CUSOLVER(cusolverDnCreate(&h));
-    AE_CUSOLVER(cusolverDnSetStream(h, st));
-    AE_CUDA_G(cudaMalloc((void **)&dAx, sizeof(double) * n * K));
-    AE_CUDA_G(cudaMalloc((void **)&dRy, sizeof(double) * n * K));
-    AE_CUDA_G(cudaMalloc((void **)&dS, sizeof(double) * K));
-    AE_CUDA_G(cudaMalloc((void **)&dU, sizeof(double) * n * K));
-    AE_CUDA_G(cudaMalloc((void **)&dVT, sizeof(double) * K * K));
-    AE_CUDA_G(cudaMalloc((void **)&dinfo, sizeof(int)));
+    if ((status = solver_ctx(st, &h, &params)) != AE_OK) goto done;
+    AE_CUDA_G(cudaMallocAsync((void **)&dAx, sizeof(double) * n * K, st));
+    AE_CUDA_G(cudaMallocAsync((void **)&dRy, sizeof(double) * n * K, st));
+    AE_CUDA_G(cudaMallocAsync((void **)&dS, sizeof(double) * K, st));
+    AE_CUDA_G(cudaMallocAsync((void **)&dU, sizeof(double) * n * K, st));
+    AE_CUDA_G(cudaMallocAsync((void **)&dVT, sizeof(double) * K * K, st));
+    AE_CUDA_G(cudaMallocAsync((void **)&dinfo, sizeof(int), st));
     split_r_kernel<<<32, 256, 0, st>>>(r_dev, n, dAx, dRy);
     AE_CUDA_G(cudaGetLastError());
     // thin SVD of the (K+1) x K triangular factor: same singular values and V as X (time_unit.py:72)
     AE_CUSOLVER(cusolverDnDgesvd_bufferSize(h, n, K, &lwork));
-    AE_CUDA_G(cudaMalloc((void **)&dwork, sizeof(double) * (size_t)lwork));
+    AE_CUDA_G(cudaMallocAsync((void **)&dwork, sizeof(double) * (size_t)lwork, st));
     AE_CUSOLVER(cusolverDnDgesvd(h, 'S', 'S', n, K, dAx, n, dS, dU, n, dVT, K, dwork, lwork, nullptr, dinfo));
     AE_CUDA_G(cudaMemcpyAsync(sig, dS, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
     AE_CUDA_G(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -445,18 +491,17 @@ extern "C" int ae_dmd_from_r(const double *r_dev, int32_t K, double dt, double r
         for (int j = 0; j < r; ++j) inv[j] = 1.0 / sig[j];
         if (sigma_out) memcpy(sigma_out, sig, sizeof(double) * K);
     }
-    AE_CUDA_G(cudaMalloc((void **)&dT, sizeof(double) * n * r));
-    AE_CUDA_G(cudaMalloc((void **)&dAt, sizeof(double) * r * r));
-    AE_CUDA_G(cudaMalloc((void **)&dInv, sizeof(double) * r));
-    AE_CUDA_G(cudaMalloc((void **)&dEig, sizeof(double) * 2 * r));
+    AE_CUDA_G(cudaMallocAsync((void **)&dT, sizeof(double) * n * r, st));
+    AE_CUDA_G(cudaMallocAsync((void **)&dAt, sizeof(double) * r * r, st));
+    AE_CUDA_G(cudaMallocAsync((void **)&dInv, sizeof(double) * r, st));
+    AE_CUDA_G(cudaMallocAsync((void **)&dEig, sizeof(double) * 2 * r, st));
     AE_CUDA_G(cudaMemcpyAsync(dInv, inv, sizeof(double) * r, cudaMemcpyHostToDevice, st));
     atilde_from_svd_kernel<<<1, 1024, 0, st>>>(dU, n, dVT, K, dRy, n, dInv, r, dT, dAt);
     AE_CUDA_G(cudaGetLastError());
-    AE_CUSOLVER(cusolverDnCreateParams(&params));
     AE_CUSOLVER(cusolverDnXgeev_bufferSize(h, params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, r, CUDA_R_64F,
                                            dAt, r, CUDA_C_64F, dEig, CUDA_R_64F, nullptr, 1, CUDA_R_64F, nullptr, 1,
                                            CUDA_R_64F, &dbytes, &hbytes));
-    AE_CUDA_G(cudaMalloc(&dbuf, dbytes ? dbytes : 8));
+    AE_CUDA_G(cudaMallocAsync(&dbuf, dbytes ? dbytes : 8, st));
     hbuf = malloc(hbytes ? hbytes : 8);
     AE_CUSOLVER(cusolverDnXgeev(h, params, CUSOLVER_EIG_MODE_NOVECTOR, CUSOLVER_EIG_MODE_NOVECTOR, r, CUDA_R_64F, dAt, r,
                                 CUDA_C_64F, dEig, CUDA_R_64F, nullptr, 1, CUDA_R_64F, nullptr, 1, CUDA_R_64F, dbuf,
@@ -472,10 +517,8 @@ extern "C" int ae_dmd_from_r(const double *r_dev, int32_t K, double dt, double r
     }
     *rank = r;
 done:
-    if (params) cusolverDnDestroyParams(params);
-    if (h) cusolverDnDestroy(h);
-    cudaFree(dAx); cudaFree(dRy); cudaFree(dS); cudaFree(dU); cudaFree(dVT); cudaFree(dwork); cudaFree(dT);
-    cudaFree(dAt); cudaFree(dInv); cudaFree(dEig); cudaFree(dbuf); cudaFree(dinfo);
+    cudaFreeAsync(dAx, st); cudaFreeAsync(dRy, st); cudaFreeAsync(dS, st); cudaFreeAsync(dU, st); cudaFreeAsync(dVT, st); cudaFreeAsync(dwork, st); cudaFreeAsync(dT, st);
+    cudaFreeAsync(dAt, st); cudaFreeAsync(dInv, st); cudaFreeAsync(dEig, st); cudaFreeAsync(dbuf, st); cudaFreeAsync(dinfo, st);
     free(hbuf); free(sig); free(inv); free(W);
     return status;
 }

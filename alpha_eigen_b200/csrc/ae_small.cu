@@ -1,16 +1,21 @@
-// Fused source iteration for small slabs (sm_100a, cooperative launch).
+// Fused solvers for small slabs (sm_100a, cooperative launch).
 //
 // The Kornreich-Parsons problems of the reference (450-1800 cells, 4-196 angles, one group) and the members
 // of a parameter ensemble are far too small to fill a B200: run through the streaming kernels they cost two
-// launches and a host poll per source iteration, ~20 us for a few microseconds of arithmetic.  Here the WHOLE
-// loop of OneGroup.source_iteration_for_scalar_flux (group.py:62-81) / TimeUnit.time_dependent_source_iteration
-// (time_unit.py:44-59) runs in one kernel: one CTA per row block (8 or 16 angles of one group and direction),
-// every warp sweeping its angle tile by tile with the same tile arithmetic as the streaming kernel
-// (ae_tile.cuh), a grid-wide barrier, the flux update (assembly, norm, scatter source) spread over all
-// threads, another grid barrier, the convergence decision taken redundantly by every CTA from the same
-// per-block sums in a fixed order.  The host reads the control block once, at the end.
-// Inputs stay in L2 (a few MB), so plain loads suffice; results are bit-compatible with the streaming path
-// (same maps, same angle order in the flux sum), which the parity tests exercise through both.
+// launches and a host poll per source iteration, ~20 us for a few microseconds of arithmetic.  Here whole
+// loops run in ONE kernel, one CTA per row block (8 or 16 angles of one group and direction):
+//   small_source_iteration_kernel  OneGroup.source_iteration_for_scalar_flux (group.py:62-81) /
+//                                  TimeUnit.time_dependent_source_iteration (time_unit.py:44-59)
+//   small_time_march_kernel        TimeUnit.calculate_time_dependent_flux (time_unit.py:17-42, repairs R2-R5):
+//                                  every step, its outer (fission) and inner (scatter) loops, the committing
+//                                  sweep and the snapshot writes
+// Every warp sweeps its angle tile by tile with the same tile arithmetic as the streaming kernel (ae_tile.cuh);
+// per-cell work (flux assembly, norms, scatter and fission sources) is spread over all threads with a FIXED
+// thread-to-cell map, so consecutive per-cell phases need no barrier; grid-wide barriers separate sweeps from
+// per-cell phases; convergence decisions are taken redundantly by every CTA from the same per-block sums in a
+// fixed order.  The host reads the control block once, at the end.  Inputs stay in L2 (a few MB), so plain
+// loads suffice; results are bit-compatible with the streaming path (same maps, same angle order in the flux
+// sum), which the parity tests exercise through both.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include "ae_common.cuh"
@@ -21,61 +26,96 @@ namespace cg = cooperative_groups;
 namespace ae {
 
 struct SmallArgs {
-    const double *hs, *cdt, *mu_ihx, *wgt, *psi_in, *base, *scat;
+    const double *hs, *cdt, *mu_ihx, *wgt, *scat, *chi, *nusf, *s_ext;
     const int32_t *mat;
-    double *q0, *q1, *phi0, *phi1, *partial, *scratch;
+    double *base, *q0, *q1, *phi0, *phi1, *phi_outer, *partial, *scratch;
     ae_ctrl *ctrl;
     int64_t Z, Zp;
     int A, n_neg, G, nb_neg, nbg;
+    // source iteration
+    const double *psi_in;
     int max_iterations;
     double cold, tol;
+    // time march
+    double *psi, *psi_snap, *phi_snap;
+    int32_t *outer_hist, *inner_hist;
+    int num_steps;
 };
 
-// sum of the per-block (num, den) pairs in block order; every CTA computes the same value
-__device__ __forceinline__ void all_blocks_sum2(const double *scratch, int nblocks, double &a, double &b, double *sm)
-{
-    a = 0.0; b = 0.0;
-    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
-        a += __ldcg(scratch + 2 * i);
-        b += __ldcg(scratch + 2 * i + 1);
-    }
-    block_sum2(a, b, sm);
-    __syncthreads();
-    if (threadIdx.x == 0) { sm[0] = a; sm[1] = b; }
-    __syncthreads();
-    a = sm[0]; b = sm[1];
-    __syncthreads();
-}
-
-template <int AC, bool READ_PSI>
-__global__ void __launch_bounds__(AC * 32) small_source_iteration_kernel(const SmallArgs p)
-{
-    extern __shared__ double red[];                     // [2][AC][kTile]
-    __shared__ double sm[64];
-    cg::grid_group grid = cg::this_grid();
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t nt = p.Zp / kTile;
-    const int64_t n = (int64_t)p.G * p.Zp;
-
+template <int AC>
+struct Small {
+    const SmallArgs &p;
+    cg::grid_group grid;
+    double *red, *sm;
+    int tid, warp, lane;
+    int64_t nt, n, gthreads, gtid;
     // this CTA's row block
-    const int rb = blockIdx.x;
-    const int g = rb / p.nbg, blk = rb % p.nbg;
-    const bool neg = blk < p.nb_neg;
-    const int a0 = neg ? blk * AC : p.n_neg + (blk - p.nb_neg) * AC;
-    const int nblk = min(AC, (neg ? p.n_neg : p.A) - a0);
-    const int a = a0 + (warp < nblk ? warp : 0);
-    const double m = fabs(p.mu_ihx[a]), two_m = 2.0 * m;
-    const double hw = warp < nblk ? 0.5 * p.wgt[a] : 0.0;
-    const int64_t goff = (int64_t)g * p.Zp + lane * 2;
-    const int64_t prow = ((int64_t)g * p.A + a) * p.Zp + lane * 2;
-    double *part = p.partial + ((int64_t)blk * p.G + g) * p.Zp;
+    int g, blk, nblk;
+    bool neg;
+    double m, two_m, hw;
+    int64_t goff, prow;
+    double *part;
 
-    double *q[2] = {p.q0, p.q1};
-    double *phi[2] = {p.phi0, p.phi1};
-    const int64_t gthreads = (int64_t)gridDim.x * blockDim.x, gtid = (int64_t)blockIdx.x * blockDim.x + tid;
+    __device__ Small(const SmallArgs &p_, double *red_, double *sm_) : p(p_), grid(cg::this_grid()), red(red_), sm(sm_)
+    {
+        tid = threadIdx.x; warp = tid >> 5; lane = tid & 31;
+        nt = p.Zp / kTile; n = (int64_t)p.G * p.Zp;
+        gthreads = (int64_t)gridDim.x * blockDim.x; gtid = (int64_t)blockIdx.x * blockDim.x + tid;
+        const int rb = blockIdx.x;
+        g = rb / p.nbg; blk = rb % p.nbg;
+        neg = blk < p.nb_neg;
+        const int a0 = neg ? blk * AC : p.n_neg + (blk - p.nb_neg) * AC;
+        nblk = min(AC, (neg ? p.n_neg : p.A) - a0);
+        const int a = a0 + (warp < nblk ? warp : 0);
+        m = fabs(p.mu_ihx[a]); two_m = 2.0 * m;
+        hw = warp < nblk ? 0.5 * p.wgt[a] : 0.0;
+        goff = (int64_t)g * p.Zp + lane * 2;
+        prow = ((int64_t)g * p.A + a) * p.Zp + lane * 2;
+        part = p.partial + ((int64_t)blk * p.G + g) * p.Zp;
+    }
 
-    // flux update over the cells owned by this thread; it == 0 is the cold start (group.py:66 / time_unit.py:45)
-    auto flux_update = [&](int it, double &num, double &den) {
+    // One sweep of this CTA's row block over the whole slab (group.py:41-60 for each of its angles).
+    template <bool RD, bool WR>
+    __device__ void sweep(const double *q, const double *psi_in, double *psi_out)
+    {
+        const double *qc = q + goff;
+        double carry = 0.0;                             // vacuum boundary: group.py:48,54
+        for (int64_t ti = 0; ti < nt; ++ti) {
+            const int64_t off = (neg ? nt - 1 - ti : ti) * kTile;
+            double ca[kL], cb[kL], f[kL];
+            tile_maps<RD>(p.hs + goff + off, qc + off, RD ? p.cdt + goff + off : nullptr, RD ? psi_in + prow + off : nullptr, m,
+                          two_m, ca, cb);
+            if (neg) tile_solve<true>(ca, cb, carry, f, lane);
+            else tile_solve<false>(ca, cb, carry, f, lane);
+            if (off + kTile > p.Z) {
+#pragma unroll
+                for (int jj = 0; jj < kL; ++jj)
+                    if (off + lane * kL + jj >= p.Z) f[jj] = 0.0;
+            }
+            if (WR && warp < nblk) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    *reinterpret_cast<double2 *>(psi_out + prow + off + k * 64) = make_double2(0.5 * f[2 * k], 0.5 * f[2 * k + 1]);
+            }
+            double *rw = red + (ti & 1) * (AC * kTile) + warp * kTile + lane * 2;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<double2 *>(rw + k * 64) = make_double2(hw * f[2 * k], hw * f[2 * k + 1]);
+            __syncthreads();
+            if (tid < kTile) {
+                const double *rr = red + (ti & 1) * (AC * kTile) + tid;
+                double sum = rr[0];
+#pragma unroll
+                for (int w = 1; w < AC; ++w) sum += rr[w * kTile];      // warps = angles in order (group.py:77)
+                part[off + tid] = sum;
+            }
+        }
+        __syncthreads();                                // red is reused by the next sweep
+    }
+
+    // Flux update over the cells owned by this thread; it == 0 is the cold start (group.py:66 / time_unit.py:45).
+    __device__ void flux_update(int it, double cold, double *const (&q)[2], double *const (&phi)[2], double &num, double &den)
+    {
         const double *phi_in = phi[(it + 1) & 1];
         double *phi_out = phi[it & 1], *q_next = q[it & 1];
         num = 0.0; den = 0.0;
@@ -85,7 +125,7 @@ __global__ void __launch_bounds__(AC * 32) small_source_iteration_kernel(const S
                 const int64_t i = (int64_t)gg * p.Zp + s;
                 double x;
                 if (it == 0) {
-                    x = valid ? p.cold : 0.0;
+                    x = valid ? cold : 0.0;
                 } else {
                     x = p.partial[i];
                     for (int pp = 1; pp < p.nbg; ++pp) x += p.partial[(int64_t)pp * n + i];    // block order (group.py:77)
@@ -103,119 +143,217 @@ __global__ void __launch_bounds__(AC * 32) small_source_iteration_kernel(const S
                 q_next[i] = p.base[i] + 0.5 * acc;                                          // group.py:73 / time_unit.py:53
             }
         }
-    };
-
-    double num, den;
-    flux_update(0, num, den);
-    grid.sync();
-
-    int it = 0, converged = 0;
-    double change = 0.0;
-    while (it < p.max_iterations - 1) {                 // `assert iteration < max_iterations`, group.py:72
-        ++it;
-        const double *qc = q[(it - 1) & 1] + goff;
-        // ---- sweep phase: this CTA's row block over the whole slab ------------------------------------
-        double carry = 0.0;                             // vacuum boundary: group.py:48,54
-        for (int64_t ti = 0; ti < nt; ++ti) {
-            const int64_t off = (neg ? nt - 1 - ti : ti) * kTile;
-            double ca[kL], cb[kL], f[kL];
-            tile_maps<READ_PSI>(p.hs + goff + off, qc + off, READ_PSI ? p.cdt + goff + off : nullptr,
-                                READ_PSI ? p.psi_in + prow + off : nullptr, m, two_m, ca, cb);
-            if (neg) tile_solve<true>(ca, cb, carry, f, lane);
-            else tile_solve<false>(ca, cb, carry, f, lane);
-            if (off + kTile > p.Z) {
-#pragma unroll
-                for (int jj = 0; jj < kL; ++jj)
-                    if (off + lane * kL + jj >= p.Z) f[jj] = 0.0;
-            }
-            double *rw = red + (ti & 1) * (AC * kTile) + warp * kTile + lane * 2;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                *reinterpret_cast<double2 *>(rw + k * 64) = make_double2(hw * f[2 * k], hw * f[2 * k + 1]);
-            __syncthreads();
-            if (tid < kTile) {
-                const double *rr = red + (ti & 1) * (AC * kTile) + tid;
-                double sum = rr[0];
-#pragma unroll
-                for (int w = 1; w < AC; ++w) sum += rr[w * kTile];      // warps = angles in order (group.py:77)
-                part[off + tid] = sum;
-            }
-        }
-        grid.sync();
-        // ---- flux update + norm --------------------------------------------------------------------------
-        flux_update(it, num, den);
-        block_sum2(num, den, sm);
-        if (tid == 0) { p.scratch[2 * blockIdx.x] = num; p.scratch[2 * blockIdx.x + 1] = den; }
-        grid.sync();
-        double sa, sb;
-        all_blocks_sum2(p.scratch, gridDim.x, sa, sb, sm);
-        change = sqrt(sa) / sqrt(sb);                   // group.py:78
-        if (change < p.tol) { converged = 1; break; }   // group.py:79
     }
-    if (blockIdx.x == 0 && tid == 0) {
+
+    // Grid-wide sqrt(sum num)/sqrt(sum den): per-block sums to scratch, barrier, every CTA adds them in block order.
+    // Two scratch halves alternate so that a fast CTA entering the next reduction cannot overwrite sums a slow
+    // CTA is still reading (every reduction contains one grid barrier).
+    int ratio_calls = 0;
+    __device__ double grid_ratio(double num, double den)
+    {
+        double *scr = p.scratch + (ratio_calls++ & 1) * 2 * gridDim.x;
+        block_sum2(num, den, sm);
+        if (tid == 0) { scr[2 * blockIdx.x] = num; scr[2 * blockIdx.x + 1] = den; }
+        grid.sync();
+        double a = 0.0, b = 0.0;
+        for (int i = tid; i < (int)gridDim.x; i += blockDim.x) {
+            a += __ldcg(scr + 2 * i);
+            b += __ldcg(scr + 2 * i + 1);
+        }
+        block_sum2(a, b, sm);
+        __syncthreads();
+        if (tid == 0) { sm[0] = a; sm[1] = b; }
+        __syncthreads();
+        a = sm[0]; b = sm[1];
+        __syncthreads();
+        return sqrt(a) / sqrt(b);
+    }
+
+    // The inner (scatter) iteration.  Iteration n leaves the flux in phi[n & 1] and was fed by q[(n-1) & 1].
+    template <bool RD>
+    __device__ bool source_iteration(const double *psi_in, double cold, double tol, int max_iterations, double *const (&q)[2],
+                                     double *const (&phi)[2], int &it, double &change)
+    {
+        double num, den;
+        flux_update(0, cold, q, phi, num, den);
+        grid.sync();
+        it = 0; change = 0.0;
+        while (it < max_iterations - 1) {               // `assert iteration < max_iterations`, group.py:72
+            ++it;
+            sweep<RD, false>(q[(it - 1) & 1], psi_in, nullptr);
+            grid.sync();
+            flux_update(it, cold, q, phi, num, den);
+            change = grid_ratio(num, den);              // group.py:78
+            if (change < tol) return true;              // group.py:79
+        }
+        return false;
+    }
+};
+
+template <int AC, bool READ_PSI>
+__global__ void __launch_bounds__(AC * 32, AC == 8 ? 2 : 1) small_source_iteration_kernel(const SmallArgs p)
+{
+    extern __shared__ double red[];                     // [2][AC][kTile]
+    __shared__ double sm[64];
+    Small<AC> S(p, red, sm);
+    double *const q[2] = {p.q0, p.q1};
+    double *const phi[2] = {p.phi0, p.phi1};
+    int it;
+    double change;
+    const bool ok = S.template source_iteration<READ_PSI>(p.psi_in, p.cold, p.tol, p.max_iterations, q, phi, it, change);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.ctrl->change = change;
         p.ctrl->inner_iters = it;
-        p.ctrl->inner_done = converged;
+        p.ctrl->inner_done = ok ? 1 : 0;
         p.ctrl->ticket = 0;
     }
 }
 
-// Can the fused kernel run this problem?  One CTA per row block, all co-resident; small enough to be latency bound.
-template <int AC, bool RD>
-static int try_launch(const SmallArgs &p, int rows, cudaStream_t st, bool &launched)
+// ctrl->reserved on exit: 0 ok, 1 inner loop did not converge, 2 outer loop did not converge; power_iters = steps done.
+template <int AC>
+__global__ void __launch_bounds__(AC * 32, AC == 8 ? 2 : 1) small_time_march_kernel(const SmallArgs p)
 {
-    const size_t smem = 2 * AC * kTile * sizeof(double);
-    static int capacity = 0;
-    if (!capacity) {
-        if (smem > 48 * 1024)
-            AE_CUDA(cudaFuncSetAttribute((const void *)small_source_iteration_kernel<AC, RD>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0, dev = 0, sms = 0;
-        AE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, small_source_iteration_kernel<AC, RD>, AC * 32, smem));
-        AE_CUDA(cudaGetDevice(&dev));
-        AE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        capacity = per_sm * sms > 0 ? per_sm * sms : -1;
+    extern __shared__ double red[];
+    __shared__ double sm[64];
+    Small<AC> S(p, red, sm);
+    double *const q[2] = {p.q0, p.q1};
+    double *const phi[2] = {p.phi0, p.phi1};
+    const int64_t n_psi = S.n * p.A;
+    int fail = 0, steps_done = 0, it = 0;
+    double change = 0.0, outer_change = 0.0;
+    for (int step = 0; step < p.num_steps && !fail; ++step) {
+        const double *psi_prev = p.psi_snap ? (step == 0 ? p.psi : p.psi_snap + (int64_t)(step - 1) * n_psi) : p.psi;
+        double *psi_next = p.psi_snap ? p.psi_snap + (int64_t)step * n_psi : p.psi;
+        for (int64_t s = S.gtid; s < p.Zp; s += S.gthreads)                     // time_unit.py:30 phi = zeros
+            for (int gg = 0; gg < p.G; ++gg) p.phi_outer[(int64_t)gg * p.Zp + s] = 0.0;
+        int outer = 0, inner_total = 0;
+        for (;;) {
+            ++outer;
+            if (!(outer < 100)) { fail = 2; break; }                            // time_unit.py:35
+            for (int64_t s = S.gtid; s < p.Zp; s += S.gthreads) {               // time_unit.py:37-39 / zone.py:38-42
+                const int mi = p.mat[s];
+                double acc = 0.0;
+                for (int gp = 0; gp < p.G; ++gp) acc = fma(p.nusf[mi * p.G + gp], p.phi_outer[(int64_t)gp * p.Zp + s], acc);
+                for (int gg = 0; gg < p.G; ++gg) {
+                    const int64_t i = (int64_t)gg * p.Zp + s;
+                    const double f = 0.5 * p.chi[mi * p.G + gg] * acc;
+                    p.base[i] = p.s_ext ? p.s_ext[i] + f : f;
+                }
+            }
+            if (!S.template source_iteration<true>(psi_prev, 0.0, p.tol, 100, q, phi, it, change)) { fail = 1; break; }   // :40
+            inner_total += it;
+            const double *cur = phi[it & 1];
+            double num = 0.0, den = 0.0;
+            for (int64_t s = S.gtid; s < p.Zp; s += S.gthreads)                 // time_unit.py:41, :36 (+R4)
+                for (int gg = 0; gg < p.G; ++gg) {
+                    const int64_t i = (int64_t)gg * p.Zp + s;
+                    const double v = cur[i], d = v - p.phi_outer[i];
+                    num = fma(d, d, num);
+                    den = fma(v, v, den);
+                    p.phi_outer[i] = v;
+                }
+            outer_change = S.grid_ratio(num, den);
+            if (outer_change < p.tol) break;                                    // time_unit.py:42
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { p.outer_hist[step] = outer; p.inner_hist[step] = inner_total; }
+        if (fail) break;
+        // commit: replay the last sweep with its own source, now writing psi (time_unit.py:26-27)
+        S.template sweep<true, true>(q[(it - 1) & 1], psi_prev, psi_next);
+        if (p.phi_snap) {
+            const double *cur = phi[it & 1];
+            double *dst = p.phi_snap + (int64_t)step * S.n;                     // time_unit.py:25
+            for (int64_t s = S.gtid; s < p.Zp; s += S.gthreads)
+                for (int gg = 0; gg < p.G; ++gg) dst[(int64_t)gg * p.Zp + s] = cur[(int64_t)gg * p.Zp + s];
+        }
+        steps_done = step + 1;
+        S.grid.sync();                                  // q / phi / partial are rewritten by the next step
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        p.ctrl->change = change;
+        p.ctrl->outer_change = outer_change;
+        p.ctrl->inner_iters = it;                       // the flux of the last step is in phi[it & 1]
+        p.ctrl->inner_done = fail ? 0 : 1;
+        p.ctrl->power_iters = steps_done;
+        p.ctrl->reserved = fail;
+        p.ctrl->ticket = 0;
+    }
+}
+
+// One CTA per row block, all co-resident (cooperative launch).
+template <class Kernel>
+static int coop_launch(Kernel kernel, int ac, const SmallArgs &p, int rows, cudaStream_t st, bool &launched)
+{
+    const size_t smem = 2 * (size_t)ac * kTile * sizeof(double);
     launched = false;
-    if (capacity < rows) return AE_OK;
+    if (smem > 48 * 1024) AE_CUDA(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, dev = 0, sms = 0;
+    AE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ac * 32, smem));
+    AE_CUDA(cudaGetDevice(&dev));
+    AE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (per_sm * sms < rows) return AE_OK;
     void *args[] = {(void *)&p};
-    AE_CUDA(cudaLaunchCooperativeKernel((const void *)small_source_iteration_kernel<AC, RD>, dim3(rows), dim3(AC * 32), args,
-                                        smem, st));
+    AE_CUDA(cudaLaunchCooperativeKernel((const void *)kernel, dim3(rows), dim3(ac * 32), args, smem, st));
     launched = true;
     return AE_OK;
 }
 
 int block_angles(int A, int n_neg);
 
+// Small enough to be launch-latency bound through the streaming kernels?  Fills the problem part of SmallArgs.
+static bool small_problem(const ae_slab *s, ae_work *w, SmallArgs &p, int &ac, int &rows)
+{
+    static const char *off = getenv("AE_NO_FUSED_SMALL");
+    if (off && off[0] == '1') return false;
+    if (w->comm) return false;                                          // multi-GPU goes through the exchange path
+    const int64_t updates = s->Zp * (int64_t)s->A * s->G;
+    if (updates > (1 << 23) || s->Zp / kTile > 256) return false;       // big enough for the streaming kernels
+    ac = block_angles(s->A, s->n_neg);
+    p.hs = s->hs; p.cdt = s->cdt; p.mu_ihx = s->mu_ihx; p.wgt = s->wgt; p.scat = s->scat; p.chi = s->chi; p.nusf = s->nusf;
+    p.s_ext = s->s_ext; p.mat = s->mat; p.base = w->base; p.q0 = w->q0; p.q1 = w->q1; p.phi0 = w->phi; p.phi1 = w->phi_alt;
+    p.phi_outer = w->phi_outer; p.partial = w->partial; p.scratch = w->norm_scratch; p.ctrl = w->ctrl;
+    p.Z = s->Z; p.Zp = s->Zp; p.A = s->A; p.n_neg = s->n_neg; p.G = s->G;
+    p.nb_neg = (s->n_neg + ac - 1) / ac;
+    p.nbg = p.nb_neg + (s->A - s->n_neg + ac - 1) / ac;
+    p.psi_in = nullptr; p.max_iterations = 0; p.cold = 0.0; p.tol = 0.0;
+    p.psi = nullptr; p.psi_snap = nullptr; p.phi_snap = nullptr; p.outer_hist = nullptr; p.inner_hist = nullptr; p.num_steps = 0;
+    rows = s->G * p.nbg;
+    return 4 * rows <= 4 * (int)ae_norm_blocks(s->Zp) + 2 * s->G;       // two halves of per-block sums must fit norm_scratch
+}
+
 // Returns AE_OK with *launched = 1 when the fused kernel was queued for this source iteration.
 int launch_small_source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, double cold, double tol,
                                   int max_iterations, int *launched, cudaStream_t st)
 {
     *launched = 0;
-    static const char *off = getenv("AE_NO_FUSED_SMALL");
-    if (off && off[0] == '1') return AE_OK;
-    if (w->comm) return AE_OK;                                          // multi-GPU goes through the exchange path
-    const int64_t updates = s->Zp * (int64_t)s->A * s->G;
-    if (updates > (1 << 23) || s->Zp / kTile > 256) return AE_OK;       // big enough for the streaming kernels
-    const int ac = block_angles(s->A, s->n_neg);
     SmallArgs p;
-    p.hs = s->hs; p.cdt = s->cdt; p.mu_ihx = s->mu_ihx; p.wgt = s->wgt; p.psi_in = psi_in; p.base = w->base;
-    p.scat = s->scat; p.mat = s->mat; p.q0 = w->q0; p.q1 = w->q1; p.phi0 = w->phi; p.phi1 = w->phi_alt;
-    p.partial = w->partial; p.scratch = w->norm_scratch; p.ctrl = w->ctrl; p.Z = s->Z; p.Zp = s->Zp; p.A = s->A;
-    p.n_neg = s->n_neg; p.G = s->G;
-    p.nb_neg = (s->n_neg + ac - 1) / ac;
-    p.nbg = p.nb_neg + (s->A - s->n_neg + ac - 1) / ac;
-    p.max_iterations = max_iterations; p.cold = cold; p.tol = tol;
-    const int rows = s->G * p.nbg;
-    if (2 * rows > 4 * (int)ae_norm_blocks(s->Zp) + 2 * s->G) return AE_OK;   // per-block sums must fit norm_scratch
+    int ac = 0, rows = 0;
+    if (!small_problem(s, w, p, ac, rows)) return AE_OK;
+    p.psi_in = psi_in; p.max_iterations = max_iterations; p.cold = cold; p.tol = tol;
     bool ok = false;
     if (ac == 16) {
-        if (psi_in) AE_TRY((try_launch<16, true>(p, rows, st, ok)));
-        else AE_TRY((try_launch<16, false>(p, rows, st, ok)));
+        if (psi_in) AE_TRY(coop_launch(small_source_iteration_kernel<16, true>, 16, p, rows, st, ok));
+        else AE_TRY(coop_launch(small_source_iteration_kernel<16, false>, 16, p, rows, st, ok));
     } else {
-        if (psi_in) AE_TRY((try_launch<8, true>(p, rows, st, ok)));
-        else AE_TRY((try_launch<8, false>(p, rows, st, ok)));
+        if (psi_in) AE_TRY(coop_launch(small_source_iteration_kernel<8, true>, 8, p, rows, st, ok));
+        else AE_TRY(coop_launch(small_source_iteration_kernel<8, false>, 8, p, rows, st, ok));
     }
+    *launched = ok ? 1 : 0;
+    return AE_OK;
+}
+
+// Whole time march in one kernel.  outer_hist / inner_hist are DEVICE arrays of num_steps ints.
+int launch_small_time_march(const ae_slab *s, ae_work *w, double *psi, double *psi_snap, double *phi_snap, int num_steps,
+                            double tol, int32_t *outer_hist, int32_t *inner_hist, int *launched, cudaStream_t st)
+{
+    *launched = 0;
+    SmallArgs p;
+    int ac = 0, rows = 0;
+    if (!small_problem(s, w, p, ac, rows) || !s->cdt) return AE_OK;
+    p.tol = tol; p.psi = psi; p.psi_snap = psi_snap; p.phi_snap = phi_snap; p.outer_hist = outer_hist; p.inner_hist = inner_hist;
+    p.num_steps = num_steps;
+    bool ok = false;
+    if (ac == 16) AE_TRY(coop_launch(small_time_march_kernel<16>, 16, p, rows, st, ok));
+    else AE_TRY(coop_launch(small_time_march_kernel<8>, 8, p, rows, st, ok));
     *launched = ok ? 1 : 0;
     return AE_OK;
 }

@@ -15,6 +15,8 @@ int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, 
 int launch_fission_base(const ae_slab *s, ae_work *w, const double *phi, double *base, int with_ext, cudaStream_t st);
 int launch_small_source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, double cold, double tol,
                                   int max_iterations, int *launched, cudaStream_t st);
+int launch_small_time_march(const ae_slab *s, ae_work *w, double *psi, double *psi_snap, double *phi_snap, int num_steps,
+                            double tol, int32_t *outer_hist, int32_t *inner_hist, int *launched, cudaStream_t st);
 int comm_reduce_scatter_rows(void *comm, double *rows, int G, int64_t Zp, cudaStream_t st);
 int comm_all_gather_rows(void *comm, double *rows, int G, int64_t Zp, int with_pairs, cudaStream_t st);
 
@@ -207,6 +209,30 @@ extern "C" int ae_time_march(const ae_slab *s, ae_work *w, double *psi, double *
     AE_TRY(check_work(s, w, "ae_time_march"));
     if (!psi) { set_error("ae_time_march: psi missing"); return AE_BAD_ARG; }
     const size_t n_phi = (size_t)s->G * s->Zp, n_psi = n_phi * s->A;
+    // small slabs: every step, loop and snapshot in one cooperative kernel (ae_small.cu)
+    if (num_steps > 0) {
+        int32_t *d_hist = nullptr;
+        AE_CUDA(cudaMallocAsync((void **)&d_hist, sizeof(int32_t) * 2 * num_steps, st));
+        AE_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(int32_t) * 2 * num_steps, st));
+        int fused = 0;
+        const int rc = launch_small_time_march(s, w, psi, psi_snap, phi_snap, num_steps, tol, d_hist, d_hist + num_steps, &fused, st);
+        if (rc != AE_OK || !fused) {
+            cudaFreeAsync(d_hist, st);
+            if (rc != AE_OK) return rc;
+        } else {
+            if (outer_hist) AE_CUDA(cudaMemcpyAsync(outer_hist, d_hist, sizeof(int32_t) * num_steps, cudaMemcpyDeviceToHost, st));
+            if (inner_hist) AE_CUDA(cudaMemcpyAsync(inner_hist, d_hist + num_steps, sizeof(int32_t) * num_steps, cudaMemcpyDeviceToHost, st));
+            AE_TRY(poll_ctrl(w, st));
+            cudaFreeAsync(d_hist, st);
+            if (w->ctrl_host->inner_iters & 1) { double *t = w->phi; w->phi = w->phi_alt; w->phi_alt = t; }
+            if (w->ctrl_host->reserved) return AE_NOT_CONVERGED;
+            if (psi_snap)
+                AE_CUDA(cudaMemcpyAsync(psi, psi_snap + (size_t)(num_steps - 1) * n_psi, n_psi * sizeof(double),
+                                        cudaMemcpyDeviceToDevice, st));
+            AE_CUDA(cudaStreamSynchronize(st));
+            return AE_OK;
+        }
+    }
     for (int step = 0; step < num_steps; ++step) {
         const double *prev = psi;
         double *next = psi;
