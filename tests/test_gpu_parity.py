@@ -361,3 +361,77 @@ def test_dmd_march_fixture_conditioning_aware(golden_dir):
     dom = _sorted_c(al)[0]
     assert abs(dom - ref) / abs(ref) < max(10 * sens, 1e-7)
     assert abs(dom - ref) / abs(ref) < 1e-4
+
+
+# ------------------------------------------------------------------ randomized shapes ------
+def test_random_shapes_sweep_source_iteration_and_step():
+    """Seeded sweep over odd shapes: ragged tiles, 1-cell slabs, uneven angle blocks, CTA ranges that cut rows
+    (carry mailbox), thick/thin materials -- sweep set, a source iteration and one time step against the oracle."""
+    from oracle import ae_oracle as orc
+    from oracle.ae_oracle import Tables
+    rs = np.random.RandomState(20261019)
+    shapes = [(1, 2, 1), (7, 2, 2), (255, 4, 1), (513, 6, 3), (1025, 12, 1), (2047, 18, 2), (3000, 34, 1), (4097, 10, 2),
+              (777, 40, 1), (9000, 4, 1), (1300, 2, 5), (640, 66, 1)]
+    for Z, A, G in shapes:
+        M = int(rs.randint(1, 4))
+        mu, w = np.polynomial.legendre.leggauss(A)
+        mat = rs.randint(0, M, Z)
+        total = rs.uniform(0.2, 3.0, (M, G)) * rs.choice([1.0, 1.0, 30.0], (M, 1))
+        scat = rs.uniform(0.0, 1.0, (M, G, G))
+        scat *= (rs.uniform(0.2, 0.6, (M, G, 1)) * total[:, :, None]) / scat.sum(axis=2, keepdims=True)
+        chi = rs.uniform(0.1, 1.0, (M, G)); chi /= chi.sum(axis=1, keepdims=True)
+        nusf = rs.uniform(0.0, 0.2, (M, G))
+        inv = rs.uniform(0.5, 2.0, (M, G))
+        tab = Tables(mat, total, scat, chi, nusf, inv)
+        p = dict(Z=Z, A=A, G=G, hx=rs.uniform(0.01, 0.3), mu=mu, weight=w, tables=tab)
+        dev = _device(p)
+        q = rs.rand(Z, G) + 0.01
+        phi_o, psi_o = orc.sweep_set(mu, w, p["hx"], q, total[mat], want_psi=True)
+        psi = dev.new_psi()
+        phi = dev.sweep_set(dev.cells_to_device(q), psi_out=psi)
+        assert _rel(dev.cells_to_host(phi), phi_o) < 1e-12, (Z, A, G)
+        assert _rel(dev.psi_to_host(psi), psi_o[:, dev.angles, :]) < 1e-12, (Z, A, G)
+        st_o, phi_si, it_o = orc.source_iteration(mu, w, p["hx"], tab, q)
+        st_d, it_d = dev.source_iteration(dev.cells_to_device(q))
+        assert (st_o, it_o) == (st_d, it_d), (Z, A, G)
+        assert _rel(dev.cells_to_host(dev.phi), phi_si) < 1e-10, (Z, A, G)
+        devt = _device(p, dt=0.1)
+        psi0 = rs.rand(Z, A, G)
+        res = orc.time_march(mu, w, p["hx"], tab, np.zeros((Z, G)), psi0, 0.1, 2, want_psi_snap=False, want_phi_snap=False)
+        pt = devt.psi_to_device(psi0)
+        st, outer, inner = devt.time_march(pt, 2, 1e-10)
+        assert st == res["status"] == 0 and list(outer) == list(res["outer"]) and list(inner) == list(res["inner"]), (Z, A, G)
+        assert _rel(devt.psi_to_host(pt), res["psi_last"][:, devt.angles, :]) < 1e-10, (Z, A, G)
+
+
+def test_streaming_and_fused_paths_agree():
+    """The same small problem through the fused cooperative kernels and through the streaming kernels
+    (AE_NO_FUSED_SMALL=1 in a subprocess): identical iteration counts, fluxes equal to rounding."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, json, numpy as np
+sys.path.insert(0, %r)
+from tests.kp import kp_problem, kp_psi0
+from alpha_eigen_b200.device import SlabDevice
+p = kp_problem(9, 20, 8); t = p["tables"]
+dev = SlabDevice(p["Z"], p["hx"], p["mu"], p["weight"], t.mat, t.total, t.scat, t.chi, t.nusf, t.invspeed)
+r = dev.power_iteration(p["phi0"])
+devt = SlabDevice(p["Z"], p["hx"], p["mu"], p["weight"], t.mat, t.total, t.scat, t.chi, t.nusf, t.invspeed, dt=0.1)
+psi = devt.psi_to_device(kp_psi0(p))
+st, outer, inner = devt.time_march(psi, 6, 1e-10)
+print(json.dumps(dict(k=r["k_new"], si=[int(x) for x in r["si_hist"]], phi=r["phi_new"].ravel().tolist(),
+                      outer=[int(x) for x in outer], inner=[int(x) for x in inner], psi=devt.psi_to_host(psi).ravel().tolist())))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, AE_NO_FUSED_SMALL=flag)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        import json
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    a, b = outs
+    assert a["si"] == b["si"] and a["outer"] == b["outer"] and a["inner"] == b["inner"]
+    assert abs(a["k"] - b["k"]) < 1e-14
+    assert _rel(np.array(a["phi"]), np.array(b["phi"])) < 1e-13
+    assert _rel(np.array(a["psi"]), np.array(b["psi"])) < 1e-13
