@@ -506,4 +506,5 @@ int launch_ctrl_init(ae_work *w, cudaStream_t st)
 
 }  // namespace ae
 
-extern "C" int64_t ae_norm_blocks(int64_t Zp) { return ae::per_cell_blocks(Zp); }
+// +512: the fused small-slab kernels keep two (num, den) pairs per CTA of a grid of up to ~600 CTAs there
+extern "C" int64_t ae_norm_blocks(int64_t Zp) { return ae::per_cell_blocks(Zp) + 512; }

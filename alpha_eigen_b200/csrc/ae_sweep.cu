@@ -37,14 +37,6 @@ namespace ae {
 
 constexpr int kACsmall = 8, kACbig = 16; // compute warps (angles) per CTA: small / many-angle problems
 constexpr int kTileBytes = kTile * 8;   // 2 KB
-constexpr int kMaxCtas = 148 * 4;
-
-constexpr int kMaxBlk = 16;             // angles per row block, upper bound
-struct SweepSync {                      // global mailbox, zero-initialised once by the caller
-    unsigned ticket, done, epoch, pad;
-    unsigned flag[kMaxCtas][kMaxBlk];
-    double carry[kMaxCtas][kMaxBlk];
-};
 
 struct SweepArgs {
     const double *hs, *cdt, *q, *mu_ihx, *wgt, *psi_in;
@@ -94,17 +86,6 @@ __device__ __forceinline__ void st_stream(double *p, double2 v)
 {
     asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(unsigned *p, unsigned v)
-{
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // Walks the tiles a CTA processes.  Its range [t0, t1) of the flattened (row block, tile) sequence
 // is visited as: last (head) piece, whole row blocks, first (tail) piece -- see the file header.
 struct Cursor {
