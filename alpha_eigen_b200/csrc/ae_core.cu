@@ -41,23 +41,42 @@ extern "C" int64_t ae_cell_offset(int64_t z)
 // ---- layout conversion kernels (boundary only; not on the iteration path) -------------------
 namespace ae {
 
-__global__ void pack_cells_kernel(const double *__restrict__ logical, int64_t Z, int64_t Zp, int G, double *__restrict__ storage)
+// cells: logical [Z][G] <-> storage [G][Zp].  A 32x32 tile goes through shared memory so that both the
+// logical side (G fastest) and the storage side (cell fastest) are accessed with unit stride.
+__global__ void __launch_bounds__(256) pack_cells_kernel(const double *__restrict__ logical, int64_t Z, int64_t Zp, int G,
+                                                         double *__restrict__ storage, int unpack)
 {
-    const int64_t n = (int64_t)G * Zp;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int g = (int)(i / Zp);
-        const int64_t z = logical_cell(i % Zp);
-        storage[i] = z < Z ? logical[z * G + g] : 0.0;
-    }
-}
-
-__global__ void unpack_cells_kernel(const double *__restrict__ storage, int64_t Z, int64_t Zp, int G, double *__restrict__ logical)
-{
-    const int64_t n = (int64_t)G * Zp;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int g = (int)(i / Zp);
-        const int64_t z = logical_cell(i % Zp);
-        if (z < Z) logical[z * G + g] = storage[i];
+    __shared__ double tile[32][33];
+    const int64_t s0 = (int64_t)blockIdx.x * 32;        // storage cells of this tile
+    const int g0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads
+    double *lw = const_cast<double *>(logical);
+    if (!unpack) {
+        for (int r = ty; r < 32; r += 8) {              // r: cell within tile, tx: group -> coalesced over G
+            const int64_t s = s0 + r;
+            const int64_t z = s < Zp ? logical_cell(s) : Z;
+            const int g = g0 + tx;
+            tile[r][tx] = (z < Z && g < G) ? logical[z * G + g] : 0.0;
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {              // r: group within tile, tx: cell -> coalesced over cells
+            const int g = g0 + r;
+            const int64_t s = s0 + tx;
+            if (g < G && s < Zp) storage[(int64_t)g * Zp + s] = tile[tx][r];
+        }
+    } else {
+        for (int r = ty; r < 32; r += 8) {
+            const int g = g0 + r;
+            const int64_t s = s0 + tx;
+            tile[tx][r] = (g < G && s < Zp) ? storage[(int64_t)g * Zp + s] : 0.0;
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int64_t s = s0 + r;
+            const int64_t z = s < Zp ? logical_cell(s) : Z;
+            const int g = g0 + tx;
+            if (z < Z && g < G) lw[z * G + g] = tile[r][tx];
+        }
     }
 }
 
@@ -82,14 +101,16 @@ static int grid_for(int64_t n) { int64_t b = (n + 255) / 256; return (int)(b < 1
 
 extern "C" int ae_pack_cells(const double *logical, int64_t Z, int64_t Zp, int32_t G, double *storage, void *stream)
 {
-    ae::pack_cells_kernel<<<ae::grid_for(G * Zp), 256, 0, (cudaStream_t)stream>>>(logical, Z, Zp, G, storage);
+    ae::pack_cells_kernel<<<dim3((unsigned)((Zp + 31) / 32), (G + 31) / 32), 256, 0, (cudaStream_t)stream>>>(logical, Z, Zp, G,
+                                                                                                            storage, 0);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }
 
 extern "C" int ae_unpack_cells(const double *storage, int64_t Z, int64_t Zp, int32_t G, double *logical, void *stream)
 {
-    ae::unpack_cells_kernel<<<ae::grid_for(G * Zp), 256, 0, (cudaStream_t)stream>>>(storage, Z, Zp, G, logical);
+    ae::pack_cells_kernel<<<dim3((unsigned)((Zp + 31) / 32), (G + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+        logical, Z, Zp, G, const_cast<double *>(storage), 1);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }

@@ -204,21 +204,32 @@ __global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_k
         }
     } else if (warp == AC) {
         // ================= reducer warp: partial scalar flux of the block ==============================
+        double hwv[AC];                                                     // half quadrature weights of the block's angles
         for (int64_t j = 0; j < W; ++j, cur.advance()) {
-            if (cur.rb != c_rb) { row_setup<AC>(p, cur.rb, 0, c); c_rb = cur.rb; }
+            if (cur.rb != c_rb) {
+                row_setup<AC>(p, cur.rb, 0, c);
+                c_rb = cur.rb;
+                const int a0 = c.neg ? (cur.rb % p.nbg) * AC : p.n_neg + (cur.rb % p.nbg - p.nb_neg) * AC;
+#pragma unroll
+                for (int w = 0; w < AC; ++w) hwv[w] = w < c.nblk ? 0.5 * p.wgt[a0 + w] : 0.0;
+            }
             const int64_t off = (int64_t)(c.neg ? nt - 1 - cur.ti : cur.ti) * kTile;
             const int b = (int)(j & 1);
             const double *rb_ = red + b * (AC * kTile) + lane * 2;
             mbar_wait(red_full + b, (uint32_t)((j >> 1) & 1));
             double2 acc[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc[k] = *reinterpret_cast<const double2 *>(rb_ + k * 64);
+            for (int k = 0; k < 4; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(rb_ + k * 64);
+                acc[k] = make_double2(hwv[0] * v.x, hwv[0] * v.y);
+            }
 #pragma unroll
             for (int w = 1; w < AC; ++w)                                    // warps = angles in order (group.py:77)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const double2 v = *reinterpret_cast<const double2 *>(rb_ + w * kTile + k * 64);
-                    acc[k].x += v.x; acc[k].y += v.y;
+                    acc[k].x = fma(hwv[w], v.x, acc[k].x);                  // 0.5*w_a*(in+out) = w_a*psi_mid
+                    acc[k].y = fma(hwv[w], v.y, acc[k].y);
                 }
             __syncwarp();
             if (lane == 0) mbar_arrive(red_empty + b);
@@ -268,8 +279,8 @@ __global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_k
                 double *rw = red + b * (AC * kTile) + warp * kTile + lane * 2;
                 mbar_wait(red_empty + b, (uint32_t)(((j >> 1) & 1) ^ 1));
 #pragma unroll
-                for (int k = 0; k < 4; ++k)                                 // 0.5*w_a*(in+out) = w_a*psi_mid, group.py:77
-                    *reinterpret_cast<double2 *>(rw + k * 64) = make_double2(c.hw * f[2 * k], c.hw * f[2 * k + 1]);
+                for (int k = 0; k < 4; ++k)                                 // in+out; the reducer applies the weights
+                    *reinterpret_cast<double2 *>(rw + k * 64) = make_double2(f[2 * k], f[2 * k + 1]);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(red_full + b);
             }
