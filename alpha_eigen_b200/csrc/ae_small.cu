@@ -119,8 +119,10 @@ struct Small {
         const double *phi_in = phi[(it + 1) & 1];
         double *phi_out = phi[it & 1], *q_next = q[it & 1];
         num = 0.0; den = 0.0;
+        constexpr int kLocalG = 16;                     // a cell's fluxes stay in registers / L1-resident local memory
         for (int64_t s = gtid; s < p.Zp; s += gthreads) {
             const bool valid = logical_cell(s) < p.Z;
+            double xv[kLocalG];
             for (int gg = 0; gg < p.G; ++gg) {
                 const int64_t i = (int64_t)gg * p.Zp + s;
                 double x;
@@ -134,11 +136,17 @@ struct Small {
                     den = fma(x, x, den);
                 }
                 phi_out[i] = x;                                                             // group.py:80
+                if (gg < kLocalG) xv[gg] = x;
             }
             const double *sc = p.scat + (size_t)p.mat[s] * p.G * p.G;
             for (int gg = 0; gg < p.G; ++gg) {
                 double acc = 0.0;
-                for (int gp = 0; gp < p.G; ++gp) acc = fma(phi_out[(int64_t)gp * p.Zp + s], __ldg(sc + gp * p.G + gg), acc);
+                if (p.G <= kLocalG) {
+                    for (int gp = 0; gp < p.G; ++gp) acc = fma(xv[gp], __ldg(sc + gp * p.G + gg), acc);
+                } else {
+                    for (int gp = 0; gp < p.G; ++gp)
+                        acc = fma(phi_out[(int64_t)gp * p.Zp + s], __ldg(sc + gp * p.G + gg), acc);
+                }
                 const int64_t i = (int64_t)gg * p.Zp + s;
                 q_next[i] = p.base[i] + 0.5 * acc;                                          // group.py:73 / time_unit.py:53
             }

@@ -138,6 +138,22 @@ class TimeUnit:
         g._psi_replay = None
         return outer, inner
 
+    def time_dependent_source_iteration(self, sigT=None, source=None, tolerance=1e-10):
+        """time_unit.py:44-59 (+R3): scatter iteration for an explicit per-angle source Q (Z,A,G) that already
+        holds the external, time and fission parts; cold start 0, at most 99 sweeps.  sigT is implied by
+        (group.total_xs, group.inv_speed, self.dt) as time_unit.py:24 builds it.  The result goes to
+        group.phi.new (the reference assigns it to an attribute of an ndarray and loses it)."""
+        g, s = self.group, self.slab
+        dev = g._device(dt=self.dt, s_ext=None)
+        cdt = (np.asarray(g.inv_speed, dtype=np.float64) / self.dt).reshape(s.num_zones, 1, s.num_groups)
+        psi_in = dev.psi_to_device(np.asarray(source, dtype=np.float64).reshape(s.num_zones, s.num_angles, s.num_groups) / cdt)
+        zero = dev.torch.zeros(dev.G * dev.Zp, dtype=dev.torch.float64, device=dev.dev)
+        st, iters = dev.source_iteration(zero, psi_in, 0.0, tolerance, 100)
+        _lib.check(st, "Warning: source iteration did not converge")
+        g.phi.new = dev.cells_to_host(dev.phi)
+        g._psi_replay = (dev, psi_in)
+        return iters
+
     # ---- DMD ----------------------------------------------------------------------------------
     def compute_alpha_eigenvalues(self, rank_tol=1e-13, return_info=False, method="tsqr"):
         """time_unit.py:61-92 on the device: rank rule `1 - cumsum(S)/sum(S) > 1e-13`, Atilde, eig,

@@ -93,6 +93,34 @@ def test_one_step_flux_matches_oracle_step():
     assert _rel(psi, res["psi_last"]) < 1e-10
 
 
+def test_time_dependent_source_iteration_method():
+    """TimeUnit.time_dependent_source_iteration(sigT, source): inner scatter iteration for an explicit Q."""
+    from alpha_eigen_modules.time_unit import TimeUnit
+    from oracle import ae_oracle as orc
+    from tests.kp import kp_problem
+    s, g = _kp(10, 4)
+    tu = TimeUnit(slab=s, group=g, num_steps=1, dt=0.1)
+    p = kp_problem(9, 10, 4)
+    rs = np.random.RandomState(3)
+    Q = rs.rand(p["Z"], 4, 1) + 0.1
+    iters = tu.time_dependent_source_iteration(None, Q)
+    # oracle: the same loop written out with single sweeps (time_unit.py:47-58)
+    sigT = p["total_xs"] + 1 / 0.1 * p["inv_speed"]
+    phi_old = np.zeros((p["Z"], 1))
+    for it in range(1, 100):
+        phi = np.zeros((p["Z"], 1))
+        for n in range(4):
+            phi[:, 0] += orc.sweep(p["mu"][n], p["hx"], Q[:, n] + phi_old * p["scatter_xs"] * 0.5, sigT) * p["weight"][n]
+        change = np.linalg.norm(phi - phi_old) / np.linalg.norm(phi)
+        phi_old = phi
+        if change < 1e-10:
+            break
+    assert iters == it
+    assert _rel(g.phi.new, phi_old) < 1e-10
+    psi_last = np.stack([a.psi_midpoint[:, 0] for a in g.angle], axis=1)
+    assert psi_last.shape == (p["Z"], 4) and np.all(np.isfinite(psi_last))
+
+
 def test_multigroup_classes_against_oracle():
     """MultiGroup + TableMaterial on the scaled five-region slab: k and a short time march."""
     from alpha_eigen_b200.group import MultiGroup
