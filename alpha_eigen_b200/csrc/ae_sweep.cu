@@ -10,25 +10,26 @@
 // reference's order inside a lane), a 5-step warp-shuffle scan composes the 32 lane maps, and a
 // running carry links consecutive 256-cell tiles.
 //
-// Mapping.  A "row block" is up to 8 angles of one group and one direction; its 8 rows are the
-// 8 warps of a CTA, which therefore share the per-(cell, group) inputs hs, q, cdt and sum their
-// weighted midpoint fluxes through shared memory once per tile (deterministic order) into a
-// per-angle-block partial scalar flux.  The (row block, tile) pairs of the whole sweep set form
-// one sequence that is cut into equal contiguous ranges, one per persistent CTA (grid = resident
-// CTAs), so every SM gets the same number of tiles whatever A, G and the rank count are.  A range
-// that starts / ends inside a row block hands the running carries to its neighbour through a
-// small global mailbox; the piece that PRODUCES a hand-off is processed first and the piece that
-// CONSUMES one last, so the wait is satisfied long before it is reached whenever a CTA owns at
-// least one row block's worth of tiles.
+// Mapping.  A "row block" is up to AC (8 or 16) angles of one group and one direction; its rows are the
+// AC compute warps of a CTA, which therefore share the per-(cell, group) inputs hs, q, cdt; a reducer
+// warp sums their weighted midpoint fluxes once per tile (angle order, deterministic) into a
+// per-angle-block partial scalar flux, and a producer warp feeds the shared-memory ring.  The
+// (row block, tile) pairs of the whole sweep set form one sequence that is cut into equal contiguous
+// ranges, one per persistent CTA (grid = resident CTAs), so every SM gets the same number of tiles
+// whatever A, G and the rank count are.  A range that starts / ends inside a row block hands the
+// running carries to its neighbour through a small global mailbox; the piece that PRODUCES a hand-off is
+// processed first and the piece that CONSUMES one last, so the wait is satisfied long before it is
+// reached whenever a CTA owns at least one row block's worth of tiles.
 //
-// Memory.  Cells are stored in the lane-blocked tile order of alpha_eigen_b200.h, so a tile of
-// any row is one contiguous, 2 KB, 16-byte aligned run.  Tiles are staged by the TMA engine
-// (cp.async.bulk + mbarrier complete_tx) into a 3-stage shared-memory ring: one elected thread
-// issues (3 + 8) bulk copies per tile (hs, q, cdt once per CTA, psi per warp), three tiles
-// ahead of the math, so loads never sit on a warp's scoreboard.  psi is written back with
-// 16-byte streaming stores (in place is safe: a tile is read before it is written and
-// prefetches only run ahead).  Algorithmic bytes per cell-angle-group update:
-//   8 (psi read) + 8 (psi write) + 24/A (hs, q, cdt over the angles) + 8/8 (partial write).
+// Memory.  Cells are stored in the lane-blocked tile order of alpha_eigen_b200.h, so a tile of any row is
+// one contiguous, 2 KB, 16-byte aligned run.  Tiles are staged by the TMA engine (cp.async.bulk +
+// mbarrier complete_tx) into a 3- or 4-stage shared-memory ring: the lanes of the producer warp issue
+// the (3 + AC) bulk copies of a tile (hs, q, cdt once per CTA, psi per compute warp) as soon as every
+// compute warp has pulled the previous occupant of the stage into registers, so loads never sit on a
+// compute warp's scoreboard.  psi is written back with 16-byte streaming stores (in place is safe: a
+// tile is read before it is written and prefetches only run ahead).  Algorithmic bytes per
+// cell-angle-group update: 8 (psi read) + 8 (psi write) + 24/A (hs, q, cdt over the rank's angles)
+// + 8/AC (partial flux write).
 #include <stdlib.h>
 #include "ae_common.cuh"
 #include "ae_tile.cuh"

@@ -1,5 +1,6 @@
-"""Multi-GPU set-up: one process per GPU, rows (angle x group) sharded by angle, one NCCL
-allreduce of the partial scalar flux per source iteration."""
+"""Multi-GPU set-up: one process per GPU, sweep rows (angle x group) sharded by angle, the flux update
+sharded by cells: one NCCL reduce-scatter of the partial scalar flux and one all-gather of the new source
+per source iteration."""
 from __future__ import annotations
 
 import os

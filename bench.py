@@ -5,9 +5,10 @@
 
 One "step" = one time-dependent source iteration over the whole slab: a psi-streaming sweep set
 (read psi^n, write psi^{n+1} in place, accumulate the scalar flux; group.py:41-60,74-77 with the
-angular source of time_unit.py:23), the phi allreduce over NVLink when N > 1, and the flux
-update kernel (norm + scatter source; group.py:73,77-80).  Rows (angle x group) are sharded by
-angle over the ranks; every N runs the SAME named problem (strong scaling).
+angular source of time_unit.py:23), for N > 1 the reduce-scatter of the partial flux rows over NVLink,
+the flux update kernels (norm + scatter source; group.py:73,77-80) on this rank's 1/N of the cells and the
+all-gather of the new source.  Rows (angle x group) are sharded by angle over the ranks; every N runs the
+SAME named problem (strong scaling).
 
 Default workload c4 = BASELINE.json configs[3]: synthetic 70-group slab, S256, 1M cells
 (17 920 rows x 1e6 cells = 1.79e10 updates per step, psi = 143 GB updated in place).

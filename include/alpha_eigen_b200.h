@@ -77,12 +77,12 @@ typedef struct ae_work {
     double *base;            /* [G][Zp] source that is fixed during the inner iteration */
     double *q0, *q1;         /* [G][Zp] ping-pong isotropic sweep source */
     double *partial;         /* [P][G][Zp] per-angle-block partial scalar flux */
-    double *reduced;         /* [G][Zp] sum of the partials, allreduced over ranks (multi-GPU only, else NULL) */
+    double *reduced;         /* [G][Zp] sum of the partials, reduce-scattered over ranks (multi-GPU only, else NULL) */
     double *norm_scratch;    /* [4 * ae_norm_blocks(Zp) + 2 * G] */
     ae_ctrl *ctrl;           /* device */
     ae_ctrl *ctrl_host;      /* pinned host */
     void *sweep_sync;        /* device, ae_sweep_sync_bytes() bytes, zero-filled once */
-    void *comm;              /* ae_comm handle for the phi allreduce, or NULL (single GPU) */
+    void *comm;              /* ae_comm handle for the flux exchange, or NULL (single GPU) */
     int32_t P;               /* ae_partial_count(A, n_neg) */
     int32_t batch;           /* source iterations launched between host polls (>=1) */
 } ae_work;
