@@ -228,6 +228,7 @@ __global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_k
             for (int w = 1; w < AC; ++w)                                    // warps = angles in order (group.py:77)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
+                    if (w >= c.nblk) continue;          // idle warps of a ragged block worked on stale data (may be NaN)
                     const double2 v = *reinterpret_cast<const double2 *>(rb_ + w * kTile + k * 64);
                     acc[k].x = fma(hwv[w], v.x, acc[k].x);                  // 0.5*w_a*(in+out) = w_a*psi_mid
                     acc[k].y = fma(hwv[w], v.y, acc[k].y);

@@ -91,3 +91,20 @@ def test_dmd_window_matches_oracle():
     from oracle.ae_oracle import dmd_window as ow
     for n in (10, 20, 50, 200, 333):
         assert dmd_window(n) == ow(n)
+
+
+def test_synthetic_generators_follow_the_survey_recipe():
+    from alpha_eigen_b200.ensemble import synthetic_ensemble
+    from alpha_eigen_b200.synthetic import region_index, synthetic_problem
+    p = synthetic_problem(900, 8, 12)
+    c = p["scat"].sum(axis=2) / p["total"]
+    np.testing.assert_allclose(c[0], 0.8)
+    np.testing.assert_allclose(c[2], 0.1)                        # absorber (material.py:17-19)
+    assert np.all(p["nusf"][1:] == 0) and np.all(p["nusf"][0] > 0)
+    np.testing.assert_allclose(p["chi"].sum(axis=1), 1.0)
+    idx = region_index(900)                                       # fuel | mod | absorber | mod | fuel at 1,2,7,8 of 9
+    assert list(np.flatnonzero(np.diff(idx))) == [99, 199, 699, 799]
+    ens = synthetic_ensemble(5, 64, 4, 3)
+    scale = [m["nusf"][0, 0] / ens[2]["nusf"][0, 0] for m in ens]
+    np.testing.assert_allclose(scale, [0.9, 0.95, 1.0, 1.05, 1.1])
+    assert np.allclose(ens[0]["phi0"], ens[0]["phi0"][::-1])     # symmetric initial guess (phi.py:11)

@@ -435,3 +435,29 @@ print(json.dumps(dict(k=r["k_new"], si=[int(x) for x in r["si_hist"]], phi=r["ph
     assert abs(a["k"] - b["k"]) < 1e-14
     assert _rel(np.array(a["phi"]), np.array(b["phi"])) < 1e-13
     assert _rel(np.array(a["psi"]), np.array(b["psi"])) < 1e-13
+
+
+def test_ragged_angle_block_ignores_stale_shared_memory():
+    """Idle warps of a ragged angle block (3 angles per direction in an 8-warp CTA) compute on whatever the ring
+    slot holds; poison shared memory with NaNs through a first launch on NaN psi and check the next result."""
+    from oracle import ae_oracle as orc
+    Z, A, G, dt = 600, 6, 2, 0.1
+    p = _mg_problem(Z, A, G, seed=21)
+    t = p["tables"]
+    dev = _device(p, dt=dt)
+    q = p["rs"].rand(Z, G)
+    nan_psi = dev.new_psi()
+    nan_psi.fill_(float("nan"))
+    dev.sweep_set(dev.cells_to_device(q), psi_in=nan_psi)                 # leaves NaNs in every psi slot of the ring
+    psi_prev = p["rs"].rand(Z, A, G)
+    inv_cell = t.invspeed[t.mat]
+    sigT = t.total[t.mat] + 1 / dt * inv_cell
+    phi_o = np.zeros((Z, G))
+    for g in range(G):
+        for n in range(A):
+            src = q[:, g] + psi_prev[:, n, g] * inv_cell[:, g] / dt
+            phi_o[:, g] += orc.sweep(p["mu"][n], p["hx"], src, sigT[:, g]) * p["weight"][n]
+    phi = dev.sweep_set(dev.cells_to_device(q), psi_in=dev.psi_to_device(psi_prev))
+    got = dev.cells_to_host(phi)
+    assert np.all(np.isfinite(got))
+    assert _rel(got, phi_o) < 1e-13

@@ -222,3 +222,29 @@ def test_ensemble_members_match_standalone_oracle():
         assert abs(r["alphas"][0] - ref[0]) < 1e-6 * abs(ref[0])
         dom.append(r["alphas"][0].real)
     assert len(set(np.round(dom, 8))) == E          # parameter variation shows up in the spectrum
+
+
+def test_multi_region_slab_generic_zone_path():
+    """MultiRegionSlab (slab.py:59-68, repaired) + Zone.assign_material (zone.py:16-36): the per-zone Python
+    path of create_zones (no vectorised map) feeding the device, against the oracle."""
+    from alpha_eigen_b200.group import MultiGroup
+    from alpha_eigen_b200.slab import MultiRegionSlab
+    from alpha_eigen_b200.synthetic import synthetic_materials
+    from oracle import ae_oracle as orc
+    G = 4
+    metal, poly, _ = synthetic_materials(G, seed=5)
+    np.random.seed(2021)
+    s = MultiRegionSlab(length=10, cells_per_mfp=1, num_angles=6, reflector_thick=2, inner_thick=2, num_zones=333,
+                        num_groups=G, material1=metal, material2=poly)
+    mg = MultiGroup(s)
+    mg.create_zones()
+    names = [z.region_name for z in mg.zone]
+    assert names[0] == "reflector" and names[166] == "moderator" and "fuel" in names and names[-1] == "reflector"
+    assert mg.zone[0].out_group_scatter_xs.shape == (G, G) and np.all(np.diag(mg.zone[0].out_group_scatter_xs) == 0)
+    tab = orc.Tables(mg._mat_index, *[np.array([getattr(m, n) for m in mg._materials]) for n in
+                                      ("total_xs", "scatter_xs", "chi", "nu_sigmaf", "inv_speed")])
+    phi0 = mg.phi.old.copy()
+    k = mg.perform_power_iteration(quiet=True)
+    ro = orc.power_iteration(s.mu, s.weight, s.hx, tab, phi0)
+    assert ro["status"] == 0 and abs(k.new - ro["k_new"]) < 1e-9
+    assert _rel(mg.phi.new, ro["phi_new"]) < 1e-10
