@@ -54,6 +54,8 @@ SYMBOLS = {
     "ae_exchange_partials": (C.c_int, [C.POINTER(AeSlab), C.POINTER(AeWork), _P]),
     "ae_pack_cells": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, _P]),
     "ae_unpack_cells": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, _P]),
+    "ae_pack_cells_range": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _P, _P]),
+    "ae_unpack_cells_range": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _P, _P]),
     "ae_pack_psi": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
     "ae_unpack_psi": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
     "ae_source_iteration": (C.c_int, [C.POINTER(AeSlab), C.POINTER(AeWork), _P, C.c_double, C.c_double, C.c_int32,

@@ -43,8 +43,9 @@ namespace ae {
 
 // cells: logical [Z][G] <-> storage [G][Zp].  A 32x32 tile goes through shared memory so that both the
 // logical side (G fastest) and the storage side (cell fastest) are accessed with unit stride.
-__global__ void __launch_bounds__(256) pack_cells_kernel(const double *__restrict__ logical, int64_t Z, int64_t Zp, int G,
-                                                         double *__restrict__ storage, int unpack)
+// Z: logical cells of the (sub)range, Zp: its storage cells (whole tiles), ld: row stride of the storage array.
+__global__ void __launch_bounds__(256) pack_cells_kernel(const double *__restrict__ logical, int64_t Z, int64_t Zp, int64_t ld,
+                                                         int G, double *__restrict__ storage, int unpack)
 {
     __shared__ double tile[32][33];
     const int64_t s0 = (int64_t)blockIdx.x * 32;        // storage cells of this tile
@@ -62,13 +63,13 @@ __global__ void __launch_bounds__(256) pack_cells_kernel(const double *__restric
         for (int r = ty; r < 32; r += 8) {              // r: group within tile, tx: cell -> coalesced over cells
             const int g = g0 + r;
             const int64_t s = s0 + tx;
-            if (g < G && s < Zp) storage[(int64_t)g * Zp + s] = tile[tx][r];
+            if (g < G && s < Zp) storage[(int64_t)g * ld + s] = tile[tx][r];
         }
     } else {
         for (int r = ty; r < 32; r += 8) {
             const int g = g0 + r;
             const int64_t s = s0 + tx;
-            tile[tx][r] = (g < G && s < Zp) ? storage[(int64_t)g * Zp + s] : 0.0;
+            tile[tx][r] = (g < G && s < Zp) ? storage[(int64_t)g * ld + s] : 0.0;
         }
         __syncthreads();
         for (int r = ty; r < 32; r += 8) {
@@ -101,8 +102,8 @@ static int grid_for(int64_t n) { int64_t b = (n + 255) / 256; return (int)(b < 1
 
 extern "C" int ae_pack_cells(const double *logical, int64_t Z, int64_t Zp, int32_t G, double *storage, void *stream)
 {
-    ae::pack_cells_kernel<<<dim3((unsigned)((Zp + 31) / 32), (G + 31) / 32), 256, 0, (cudaStream_t)stream>>>(logical, Z, Zp, G,
-                                                                                                            storage, 0);
+    ae::pack_cells_kernel<<<dim3((unsigned)((Zp + 31) / 32), (G + 31) / 32), 256, 0, (cudaStream_t)stream>>>(logical, Z, Zp, Zp,
+                                                                                                            G, storage, 0);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }
@@ -110,7 +111,7 @@ extern "C" int ae_pack_cells(const double *logical, int64_t Z, int64_t Zp, int32
 extern "C" int ae_unpack_cells(const double *storage, int64_t Z, int64_t Zp, int32_t G, double *logical, void *stream)
 {
     ae::pack_cells_kernel<<<dim3((unsigned)((Zp + 31) / 32), (G + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
-        logical, Z, Zp, G, const_cast<double *>(storage), 1);
+        logical, Z, Zp, Zp, G, const_cast<double *>(storage), 1);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }
@@ -130,6 +131,28 @@ extern "C" int ae_unpack_psi(const double *storage, int64_t Z, int64_t Zp, int32
     ae::pack_psi_kernel<<<ae::grid_for((int64_t)G * A * Zp), 256, 0, (cudaStream_t)stream>>>(logical, Z, Zp, A_total, G,
                                                                                             angle_index, A,
                                                                                             const_cast<double *>(storage), 1);
+    AE_CUDA(cudaGetLastError());
+    return AE_OK;
+}
+
+// Cell-range variants for cell-sharded host I/O: `storage` points at the first cell of the range inside rows
+// of stride ld; the range holds `cells` storage cells (whole tiles) of which the first `count` are real.
+extern "C" int ae_pack_cells_range(const double *logical, int64_t count, int64_t cells, int64_t ld, int32_t G,
+                                   double *storage, void *stream)
+{
+    if (cells % AE_TILE || count > cells) { ae::set_error("ae_pack_cells_range: range must be whole tiles"); return AE_BAD_ARG; }
+    ae::pack_cells_kernel<<<dim3((unsigned)((cells + 31) / 32), (G + 31) / 32), 256, 0, (cudaStream_t)stream>>>(logical, count, cells,
+                                                                                                               ld, G, storage, 0);
+    AE_CUDA(cudaGetLastError());
+    return AE_OK;
+}
+
+extern "C" int ae_unpack_cells_range(const double *storage, int64_t count, int64_t cells, int64_t ld, int32_t G,
+                                     double *logical, void *stream)
+{
+    if (cells % AE_TILE || count > cells) { ae::set_error("ae_unpack_cells_range: range must be whole tiles"); return AE_BAD_ARG; }
+    ae::pack_cells_kernel<<<dim3((unsigned)((cells + 31) / 32), (G + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+        logical, count, cells, ld, G, const_cast<double *>(storage), 1);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }

@@ -189,6 +189,35 @@ class SlabDevice:
             return out
         return d.cpu().numpy().reshape(self.Z, self.G)
 
+    # ---- cell-sharded host I/O (several GPUs): this rank feeds / reads only its own cell range ------------
+    def cell_range(self):
+        """(first logical cell, logical cells, storage offset, storage cells) of this rank's share of a row."""
+        world = self.comm.world if self.comm is not None else 1
+        rank = self.comm.rank if self.comm is not None else 0
+        zs = self.Zp // world
+        z0 = rank * zs
+        return z0, max(0, min(self.Z, z0 + zs) - z0), z0, zs
+
+    def shard_to_device(self, shard_host, rows):
+        """shard_host: pinned (count, G) tensor with this rank's cells -> its range of `rows` [G][Zp], then the
+        ranges of all ranks are all-gathered over NVLink so that every rank holds whole rows."""
+        z0, count, s0, cells = self.cell_range()
+        d = shard_host.to(self.dev, non_blocking=True)
+        _lib.check(self.lib.ae_pack_cells_range(d.data_ptr(), count, cells, self.Zp, self.G, rows.data_ptr() + 8 * s0,
+                                                self.stream))
+        if self.comm is not None:
+            _lib.check(self.lib.ae_comm_gather_rows(self.comm.handle, rows.data_ptr(), self.G, self.Zp, self.stream))
+
+    def shard_to_host(self, rows, shard_host):
+        """This rank's cell range of `rows` [G][Zp] -> pinned (count, G) tensor (synchronises)."""
+        torch = self.torch
+        z0, count, s0, cells = self.cell_range()
+        d = torch.empty(max(count, 1) * self.G, dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.ae_unpack_cells_range(rows.data_ptr() + 8 * s0, count, cells, self.Zp, self.G, d.data_ptr(),
+                                                  self.stream))
+        shard_host.copy_(d[:count * self.G].view(shard_host.shape), non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+
     def psi_to_device(self, psi):
         """(Z, A_total, G) logical, reference angle order -> [G][A][Zp] for the local angles."""
         torch = self.torch

@@ -233,15 +233,18 @@ def main():
     gpu_launches = launches
     assert bool(torch.isfinite(dev.phi).all()), "non-finite scalar flux"
 
-    # ---- end to end through host buffers: q from pinned host memory, phi back to the host -------
-    q_host = torch.rand(Z, G, dtype=torch.float64).pin_memory()
-    phi_host = torch.empty(Z, G, dtype=torch.float64).pin_memory()
+    # ---- end to end through host buffers: the source comes from pinned host memory, the flux goes back ---------
+    # Several GPUs: host I/O is sharded by cells like the flux update -- every rank uploads the source of ITS cell
+    # range (1/N of the array), the ranges are all-gathered over NVLink, and every rank reads back its range of the flux.
+    z0, zcount, _, _ = dev.cell_range()
+    q_host = torch.rand(max(zcount, 1), G, dtype=torch.float64)[:zcount].pin_memory()
+    phi_host = torch.empty(zcount, G, dtype=torch.float64).pin_memory()
     e_steps = max(2, min(args.steps, 5))
 
     def e2e_step(i):
-        dev.cells_to_device(q_host, out=q[i & 1])                       # H2D + pack
+        dev.shard_to_device(q_host, q[i & 1])                           # H2D + pack (+ all-gather of the ranges)
         step(i)
-        dev.cells_to_host(dev.phi, out=phi_host)                        # unpack + D2H (+ sync)
+        dev.shard_to_host(dev.phi, phi_host)                            # unpack + D2H (+ sync)
 
     e2e_step(0)
     fence()
@@ -281,7 +284,8 @@ def main():
                              "flux_update_and_allgather": phase[2]},
             "e2e": {"value": updates_per_step / (e_ms * 1e-3), "unit": "updates/s", "ms_per_step": e_ms,
                     "h2d_bytes_per_step": Z * G * 8, "d2h_bytes_per_step": Z * G * 8,
-                    "what": "host q (pinned) -> device, sweep set + flux update on resident psi, phi -> host"},
+                    "what": "whole-job bytes; every rank copies the source of its own 1/N cell range from pinned host memory "
+                            "(all-gathered on the device), runs the step on resident psi, and reads its range of the flux back"},
             "gpu_launches": gpu_launches, "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -129,6 +129,12 @@ int ae_exchange_partials(const ae_slab *s, ae_work *w, void *stream);
 /* cells: logical [Z][G] (phi.new of group.py:18) <-> storage [G][Zp] */
 int ae_pack_cells(const double *logical, int64_t Z, int64_t Zp, int32_t G, double *storage, void *stream);
 int ae_unpack_cells(const double *storage, int64_t Z, int64_t Zp, int32_t G, double *logical, void *stream);
+/* Cell-range variants (cell-sharded host I/O on several GPUs): `logical` holds `count` cells [count][G],
+ * `storage` points at the first cell of a range of `cells` storage cells (whole tiles) inside rows of stride ld. */
+int ae_pack_cells_range(const double *logical, int64_t count, int64_t cells, int64_t ld, int32_t G,
+                        double *storage, void *stream);
+int ae_unpack_cells_range(const double *storage, int64_t count, int64_t cells, int64_t ld, int32_t G,
+                          double *logical, void *stream);
 /* psi: logical [Z][A_total][G] (TimeUnit.psi[..., step], time_unit.py:14) <-> storage [G][A][Zp];
  * angle_index [A] (device) maps local angle a to the reference angle number. */
 int ae_pack_psi(const double *logical, int64_t Z, int64_t Zp, int32_t A_total, int32_t G, const int32_t *angle_index,

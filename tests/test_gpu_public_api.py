@@ -248,3 +248,22 @@ def test_multi_region_slab_generic_zone_path():
     ro = orc.power_iteration(s.mu, s.weight, s.hx, tab, phi0)
     assert ro["status"] == 0 and abs(k.new - ro["k_new"]) < 1e-9
     assert _rel(mg.phi.new, ro["phi_new"]) < 1e-10
+
+
+def test_cell_range_host_io_roundtrip():
+    """ae_pack_cells_range / ae_unpack_cells_range (single rank: the range is the whole row)."""
+    import torch
+    from alpha_eigen_b200.device import SlabDevice
+    Z, A, G = 700, 4, 5
+    mu, w = np.polynomial.legendre.leggauss(A)
+    one = np.ones((1, G))
+    dev = SlabDevice(Z, 1.0, mu, w, np.zeros(Z, dtype=np.int64), one, np.zeros((1, G, G)), one, one, one)
+    z0, count, s0, cells = dev.cell_range()
+    assert (z0, count, s0, cells) == (0, Z, 0, dev.Zp)
+    src = torch.rand(Z, G, dtype=torch.float64).pin_memory()
+    rows = torch.zeros(G * dev.Zp, dtype=torch.float64, device=dev.dev)
+    dev.shard_to_device(src, rows)
+    np.testing.assert_array_equal(dev.cells_to_host(rows), src.numpy())
+    back = torch.empty(Z, G, dtype=torch.float64).pin_memory()
+    dev.shard_to_host(rows, back)
+    np.testing.assert_array_equal(back.numpy(), src.numpy())
