@@ -49,6 +49,8 @@ SYMBOLS = {
     "ae_norm_blocks": (C.c_int64, [C.c_int64]),
     "ae_sweep_set": (C.c_int, [C.POINTER(AeSlab), _P, _P, _P, _P, _P, _P]),
     "ae_sweep_sync_bytes": (C.c_int64, []),
+    "ae_sweep_plan": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, c_ip, c_ip, c_ip, c_ip,
+                                  C.c_int64]),
     "ae_reduce_partials": (C.c_int, [C.POINTER(AeSlab), _P, C.c_int32, _P, _P]),
     "ae_flux_update": (C.c_int, [C.POINTER(AeSlab), C.POINTER(AeWork), _P, C.c_int32, _P, C.c_double, C.c_int32, _P]),
     "ae_exchange_partials": (C.c_int, [C.POINTER(AeSlab), C.POINTER(AeWork), _P]),

@@ -44,8 +44,10 @@ struct SweepArgs {
     double *psi_out, *partial;
     SweepSync *sync;
     int64_t Z, Zp;
-    int64_t total_tiles;                // G * NBg * nt
+    int64_t total_tiles;                // units * nt (units = G * nbg / gs row-block gangs)
     int A, n_neg, G, nb_neg, nbg;       // nbg = angle blocks per group
+    int gs, subs;                       // gang size (CTAs that walk the same cells together), nb_dir / gs
+    int l2_hints;                       // keep hs/q/cdt tiles in L2 (evict_last), stream psi through it (evict_first)
 };
 
 // ---- PTX helpers: mbarrier + 1-D bulk async copy (TMA engine) -----------------------------------
@@ -76,16 +78,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+// L2 eviction policies: tiles several CTAs read (hs, q, cdt) are kept, psi is used exactly once.
+__device__ __forceinline__ uint64_t l2_policy(int kind)      // 0 normal, 1 evict_first, 2 evict_last
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
+    uint64_t pol;
+    if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
 }
-__device__ __forceinline__ void st_stream(double *p, double2 v)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol)
 {
-    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void st_stream(double *p, double2 v, uint64_t pol)
+{
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol)
+                 : "memory");
 }
 // Walks the tiles a CTA processes.  Its range [t0, t1) of the flattened (row block, tile) sequence
 // is visited as: last (head) piece, whole row blocks, first (tail) piece -- see the file header.
@@ -93,7 +106,7 @@ struct Cursor {
     int nt, rb, ti;                      // tiles per row; current row block and tile (sweep order)
     int b0, b1, first_ti;                // first / last row block of the range, tile where the range starts
     int64_t j, len_last;                 // tiles done so far; length of the head piece
-    __device__ void init(int64_t t0, int64_t t1, int nt_)
+    __host__ __device__ void init(int64_t t0, int64_t t1, int nt_)
     {
         nt = nt_;
         b0 = (int)(t0 / nt); b1 = (int)((t1 - 1) / nt);
@@ -102,7 +115,7 @@ struct Cursor {
         if (b0 == b1) { len_last = t1 - t0; rb = b0; ti = first_ti; }
         else { len_last = t1 - (int64_t)b1 * nt; rb = b1; ti = 0; }
     }
-    __device__ void advance()
+    __host__ __device__ void advance()
     {
         ++j; ++ti;
         if (b0 == b1) return;
@@ -140,6 +153,18 @@ __device__ __forceinline__ void row_setup(const SweepArgs &p, int rb, int warp, 
     c.poff = ((int64_t)blk * p.G + c.g) * p.Zp;
 }
 
+// Work unit u of gang member mb -> row block.  Without gangs (gs == 1) a unit IS a row block.  With gangs a unit is
+// gs angle blocks of one group and direction: its members walk the same cells at the same time, so hs/q/cdt
+// come from HBM once per unit and from L2 for the other gs - 1 members.
+__host__ __device__ __forceinline__ int unit_row(const SweepArgs &p, int u, int mb)
+{
+    if (p.gs == 1) return u;
+    const int upg = 2 * p.subs;                     // units per group (both directions have nb_neg blocks)
+    const int g = u / upg, r = u - g * upg;
+    const int dir = r / p.subs, sub = r - dir * p.subs;
+    return g * p.nbg + dir * p.nb_neg + sub * p.gs + mb;
+}
+
 template <int AC> struct StageCfg { static constexpr int stages = AC == kACbig ? 4 : 3; };
 
 // Warp-specialised persistent kernel: AC compute warps + reducer warp + producer warp.
@@ -175,10 +200,11 @@ __global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_k
     }
     __syncthreads();
     const int cta = s_cta;
+    const int gang = cta / p.gs, mb = cta - gang * p.gs;                    // members of a gang start back to back
     const unsigned stamp = sy->epoch + 1;                                   // epoch only advances after every CTA has left
     const int64_t nt = p.Zp / kTile;
-    const int64_t T = p.total_tiles, NC = gridDim.x;
-    const int64_t t0 = cta * T / NC, t1 = (cta + 1) * T / NC, W = t1 - t0;
+    const int64_t T = p.total_tiles, NC = gridDim.x / p.gs;
+    const int64_t t0 = gang * T / NC, t1 = (gang + 1) * T / NC, W = t1 - t0;
     const bool publishes = (t1 % nt) != 0;                                  // range ends inside a row block
     Cursor cur;
     cur.init(t0, t1, (int)nt);
@@ -187,8 +213,9 @@ __global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_k
 
     if (warp == AC + 1) {
         // ================= producer warp: TMA ring =====================================================
+        const uint64_t pol = l2_policy(p.l2_hints ? (lane < 3 ? 2 : 1) : 0);   // lanes 0-2 fetch hs/q/cdt, the rest psi
         for (int64_t j = 0; j < W; ++j, cur.advance()) {
-            if (cur.rb != c_rb) { row_setup<AC>(p, cur.rb, 0, c); c_rb = cur.rb; }
+            if (cur.rb != c_rb) { row_setup<AC>(p, unit_row(p, cur.rb, mb), 0, c); c_rb = cur.rb; }
             const int64_t off = (int64_t)(c.neg ? nt - 1 - cur.ti : cur.ti) * kTile;
             const int st = (int)(j % kStages);
             double *dst = ring + (size_t)st * kSlots * kTile;
@@ -200,7 +227,7 @@ __global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_k
             if (lane < nslots) {
                 const double *src = lane == 0 ? p.hs + goff : lane == 1 ? p.q + goff : lane == 2 ? p.cdt + goff
                                                                                    : p.psi_in + c.row + (int64_t)(lane - 3) * p.Zp + off;
-                bulk_g2s(dst + lane * kTile, src, kTileBytes, full + st);
+                bulk_g2s(dst + lane * kTile, src, kTileBytes, full + st, pol);
             }
         }
     } else if (warp == AC) {
@@ -208,9 +235,10 @@ __global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_k
         double hwv[AC];                                                     // half quadrature weights of the block's angles
         for (int64_t j = 0; j < W; ++j, cur.advance()) {
             if (cur.rb != c_rb) {
-                row_setup<AC>(p, cur.rb, 0, c);
+                const int row = unit_row(p, cur.rb, mb);
+                row_setup<AC>(p, row, 0, c);
                 c_rb = cur.rb;
-                const int a0 = c.neg ? (cur.rb % p.nbg) * AC : p.n_neg + (cur.rb % p.nbg - p.nb_neg) * AC;
+                const int a0 = c.neg ? (row % p.nbg) * AC : p.n_neg + (row % p.nbg - p.nb_neg) * AC;
 #pragma unroll
                 for (int w = 0; w < AC; ++w) hwv[w] = w < c.nblk ? 0.5 * p.wgt[a0 + w] : 0.0;
             }
@@ -243,17 +271,18 @@ __global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_k
         // ================= compute warps ==============================================================
         double carry = 0.0;
         int64_t j = 0;
+        const uint64_t pol = l2_policy(p.l2_hints ? 1 : 0);
         for (int piece = 0; piece < 2; ++piece) {
             const int64_t jend = piece == 0 ? (cur.len_last < W ? cur.len_last : W) : W;
             for (; j < jend; ++j, cur.advance()) {
                 const int rb = cur.rb, ti = cur.ti;
                 if (rb != c_rb || ti == 0) {
-                    if (rb != c_rb) { row_setup<AC>(p, rb, warp, c); c_rb = rb; }
+                    if (rb != c_rb) { row_setup<AC>(p, unit_row(p, rb, mb), warp, c); c_rb = rb; }
                     carry = 0.0;                                            // vacuum boundary: group.py:48,54
                     if (ti != 0) {                                          // continue a row another CTA started
                         if (lane == 0 && warp < c.nblk) {
-                            while (ld_acquire(&sy->flag[cta - 1][warp]) != stamp) {}
-                            carry = sy->carry[cta - 1][warp];
+                            while (ld_acquire(&sy->flag[cta - p.gs][warp]) != stamp) {}    // same member of the previous gang
+                            carry = sy->carry[cta - p.gs][warp];
                         }
                         carry = __shfl_sync(0xffffffffu, carry, 0);
                     }
@@ -276,7 +305,7 @@ __global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_k
                 if (WRITE_PSI && warp < c.nblk) {
                     double *pout = p.psi_out + c.row + (int64_t)warp * p.Zp + off + lane * 2;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) st_stream(pout + k * 64, make_double2(0.5 * f[2 * k], 0.5 * f[2 * k + 1]));
+                    for (int k = 0; k < 4; ++k) st_stream(pout + k * 64, make_double2(0.5 * f[2 * k], 0.5 * f[2 * k + 1]), pol);
                 }
                 double *rw = red + b * (AC * kTile) + warp * kTile + lane * 2;
                 mbar_wait(red_empty + b, (uint32_t)(((j >> 1) & 1) ^ 1));
@@ -329,9 +358,57 @@ int block_angles(int A, int n_neg)
     return ac;
 }
 
-template <int AC, bool RD, bool WR>
-static int launch_variant(const SweepArgs &p, const ae_ctrl *ctrl, int gate, cudaStream_t st)
+// Gang size for a grid of `grid` persistent CTAs: the divisor gs of the angle blocks per direction that minimises
+// (bytes per update with hs/q/cdt fetched nbg/gs times per group) / (fraction of the grid a whole number of gangs
+// fills).  C4 on one GPU (8 + 8 blocks of 16 angles, 148 CTAs): gs = 4 -> 37 gangs, shared inputs read 4x instead
+// of 16x per group.  AE_SWEEP_GANG=<n> forces a size (1 = every CTA walks its own cells, the pre-gang order).
+static int gang_size(const SweepArgs &p, int64_t grid, int64_t full_grid)
 {
+    static const char *force = getenv("AE_SWEEP_GANG");
+    const int nbd = p.nb_neg;
+    if (p.nbg != 2 * nbd || nbd < 2 || grid < full_grid) return 1;     // ragged directions / small problems: no gangs
+    if (force && atoi(force) >= 1) {
+        const int f = atoi(force);
+        return (nbd % f == 0 && grid / f >= 1) ? f : 1;
+    }
+    int best = 1;
+    double best_cost = 1e300;
+    for (int gs = 1; gs <= nbd; ++gs) {
+        if (nbd % gs) continue;
+        const int64_t ng = grid / gs;
+        if (ng < 1 || (int64_t)p.G * p.nbg / gs < ng) continue;     // a gang owns at least one unit's worth of tiles, so
+                                                                     // the hand-off it waits for was produced long before
+        const double bytes = 16.0 + 8.0 * p.nbg / p.A + 24.0 * (p.nbg / gs) / p.A;
+        const double cost = bytes * (double)grid / (double)(ng * gs);
+        if (cost < best_cost - 1e-12) { best_cost = cost; best = gs; }
+    }
+    return best;
+}
+
+// Grid size and gang shape for `resident` co-resident CTAs; fills p.gs / p.subs / p.total_tiles.
+static int64_t plan_grid(SweepArgs &p, int64_t resident)
+{
+    int64_t grid = resident;
+    if (grid > kMaxCtas) grid = kMaxCtas;
+    const int64_t full_grid = grid;
+    // small problems: at least one CTA per row block (rows are the only parallelism), else >= 4 tiles per CTA
+    const int64_t rows = (int64_t)p.G * p.nbg, quarter = (p.total_tiles + 3) / 4;
+    const int64_t want = rows > quarter ? rows : quarter;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    p.gs = gang_size(p, grid, full_grid);
+    p.subs = p.nb_neg / p.gs;
+    if (p.gs > 1) {
+        grid = grid / p.gs * p.gs;                                  // whole gangs only
+        p.total_tiles = (int64_t)p.G * (p.nbg / p.gs) * (p.Zp / kTile);
+    }
+    return grid;
+}
+
+template <int AC, bool RD, bool WR>
+static int launch_variant(const SweepArgs &p_in, const ae_ctrl *ctrl, int gate, cudaStream_t st)
+{
+    SweepArgs p = p_in;
     constexpr int slots = RD ? 3 + AC : 2;
     constexpr int threads = (AC + 2) * 32;
     const size_t smem = (size_t)(StageCfg<AC>::stages * slots + 2 * AC) * kTileBytes + (2 * StageCfg<AC>::stages + 4) * sizeof(uint64_t);
@@ -346,13 +423,7 @@ static int launch_variant(const SweepArgs &p, const ae_ctrl *ctrl, int gate, cud
     int dev = 0, sms = 0;
     AE_CUDA(cudaGetDevice(&dev));
     AE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int64_t grid = (int64_t)sms * ctas_per_sm;
-    if (grid > kMaxCtas) grid = kMaxCtas;
-    // small problems: at least one CTA per row block (rows are the only parallelism), else >= 4 tiles per CTA
-    const int64_t rows = (int64_t)p.G * p.nbg, quarter = (p.total_tiles + 3) / 4;
-    const int64_t want = rows > quarter ? rows : quarter;
-    if (grid > want) grid = want;
-    if (grid < 1) grid = 1;
+    const int64_t grid = plan_grid(p, (int64_t)sms * ctas_per_sm);
     sweep_kernel<AC, RD, WR><<<(unsigned)grid, threads, smem, st>>>(p, ctrl, gate);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
@@ -368,6 +439,18 @@ static int launch_shape(const SweepArgs &p, const ae_ctrl *ctrl, int gate, cudaS
     return launch_variant<AC, false, false>(p, ctrl, gate, st);
 }
 
+// Row-block shape of a problem: fills the integer fields of SweepArgs, returns the angles per CTA.
+static int shape_args(int A, int n_neg, int G, int64_t Zp, SweepArgs &p)
+{
+    const int blk = block_angles(A, n_neg);
+    p.Zp = Zp; p.A = A; p.n_neg = n_neg; p.G = G;
+    p.nb_neg = (n_neg + blk - 1) / blk;
+    p.nbg = p.nb_neg + (A - n_neg + blk - 1) / blk;
+    p.total_tiles = (int64_t)G * p.nbg * (Zp / kTile);
+    p.gs = 1; p.subs = p.nb_neg;                        // gangs are chosen per launch (grid size)
+    return blk;
+}
+
 // internal launcher shared with the solver loops (gate: skip when ctrl->inner_done is set)
 int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double *psi_out, double *partial,
                  void *sync, const ae_ctrl *ctrl, int gate, cudaStream_t st)
@@ -377,15 +460,13 @@ int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double
         return AE_BAD_ARG;
     }
     if (psi_in && !s->cdt) { set_error("ae_sweep_set: psi_in given but slab has no cdt"); return AE_BAD_ARG; }
-    const int ac = block_angles(s->A, s->n_neg);
-    const int blk = ac;
     SweepArgs p;
+    const int ac = shape_args(s->A, s->n_neg, s->G, s->Zp, p);
     p.hs = s->hs; p.cdt = s->cdt; p.q = q; p.mu_ihx = s->mu_ihx; p.wgt = s->wgt;
     p.psi_in = psi_in; p.psi_out = psi_out; p.partial = partial; p.sync = (SweepSync *)sync;
-    p.Z = s->Z; p.Zp = s->Zp; p.A = s->A; p.n_neg = s->n_neg; p.G = s->G;
-    p.nb_neg = (s->n_neg + blk - 1) / blk;
-    p.nbg = p.nb_neg + (s->A - s->n_neg + blk - 1) / blk;
-    p.total_tiles = (int64_t)s->G * p.nbg * (s->Zp / kTile);
+    p.Z = s->Z;
+    static const char *hints = getenv("AE_SWEEP_L2_HINTS");
+    p.l2_hints = !(hints && hints[0] == '0');
     return ac == kACbig ? launch_shape<kACbig>(p, ctrl, gate, st) : launch_shape<kACsmall>(p, ctrl, gate, st);
 }
 
@@ -395,6 +476,32 @@ extern "C" int32_t ae_partial_count(int32_t A, int32_t n_neg)
 {
     const int blk = ae::block_angles(A, n_neg);
     return (n_neg + blk - 1) / blk + (A - n_neg + blk - 1) / blk;
+}
+
+// Host-side replay of the kernel's work assignment (same Cursor / unit_row / plan_grid code): the (row block,
+// tile index in sweep order) pairs logical CTA `cta` visits, in order.  Test hook: no GPU needed.
+extern "C" int64_t ae_sweep_plan(int32_t A, int32_t n_neg, int32_t G, int64_t Zp, int32_t resident_ctas, int32_t cta,
+                                 int32_t *grid_out, int32_t *gang_out, int32_t *row_blocks, int32_t *tiles, int64_t cap)
+{
+    if (A <= 0 || n_neg < 0 || n_neg > A || G <= 0 || Zp <= 0 || Zp % ae::kTile || resident_ctas < 1) return -1;
+    ae::SweepArgs p;
+    ae::shape_args(A, n_neg, G, Zp, p);
+    const int64_t grid = ae::plan_grid(p, resident_ctas);
+    if (grid_out) *grid_out = (int32_t)grid;
+    if (gang_out) *gang_out = p.gs;
+    if (cta < 0 || cta >= grid) return 0;
+    const int64_t nt = Zp / ae::kTile, NC = grid / p.gs;
+    const int gang = cta / p.gs, mb = cta - gang * p.gs;
+    const int64_t t0 = gang * p.total_tiles / NC, t1 = (gang + 1) * p.total_tiles / NC, W = t1 - t0;
+    ae::Cursor cur;
+    cur.init(t0, t1, (int)nt);
+    for (int64_t j = 0; j < W; ++j, cur.advance()) {
+        if (j < cap) {
+            if (row_blocks) row_blocks[j] = ae::unit_row(p, cur.rb, mb);
+            if (tiles) tiles[j] = cur.ti;
+        }
+    }
+    return W;
 }
 
 extern "C" int64_t ae_sweep_sync_bytes(void) { return (int64_t)sizeof(ae::SweepSync); }

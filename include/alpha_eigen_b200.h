@@ -108,6 +108,12 @@ int ae_sweep_set(const ae_slab *s, const double *q, const double *psi_in, double
  * mailbox through which persistent CTAs hand running boundary fluxes to each other.  One buffer
  * per stream of sweeps (ae_work carries its own). */
 int64_t ae_sweep_sync_bytes(void);
+/* Host-only replay of the sweep kernel's work assignment for `resident_ctas` co-resident CTAs: writes the (row block,
+ * tile index in sweep order) pairs logical CTA `cta` visits, in order, into row_blocks / tiles (capacity cap) and
+ * returns how many there are (-1: bad argument); *grid_out = CTAs launched, *gang_out = gang size (CTAs that walk
+ * the same cells together so that hs/q/cdt are fetched from HBM once per gang).  No GPU needed (test hook). */
+int64_t ae_sweep_plan(int32_t A, int32_t n_neg, int32_t G, int64_t Zp, int32_t resident_ctas, int32_t cta,
+                      int32_t *grid_out, int32_t *gang_out, int32_t *row_blocks, int32_t *tiles, int64_t cap);
 /* phi[G][Zp] = sum_p partial[p] in block order; padding cells are zeroed. */
 int ae_reduce_partials(const ae_slab *s, const double *partial, int32_t P, double *phi, void *stream);
 

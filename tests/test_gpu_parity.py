@@ -113,6 +113,45 @@ def test_time_dependent_sweep_set_matches_oracle():
     assert _rel(dev.psi_to_host(psi), psi_o[:, dev.angles, :]) < 1e-13
 
 
+@pytest.mark.parametrize("Z,A,G", [(70_000, 64, 3), (41_000, 96, 2)])
+def test_ganged_sweep_matches_oracle(Z, A, G):
+    """Shapes with several angle blocks per direction and enough tiles to fill the persistent grid: the kernel
+    runs its CTAs in gangs (ae_sweep_plan says so) with row hand-offs between gangs.  Steady and time-dependent
+    (in place) sweep sets against the oracle, bit-for-bit against a second launch (determinism)."""
+    import ctypes as C
+    from oracle import ae_oracle as orc
+    p = _mg_problem(Z, A, G, seed=Z % 97)
+    t = p["tables"]
+    dev = _device(p, dt=0.1)
+    gang = C.c_int32(0)
+    dev.lib.ae_sweep_plan(dev.A, dev.n_neg, dev.G, dev.Zp, 148, -1, None, C.byref(gang), None, None, 0)
+    assert gang.value > 1, "shape was meant to exercise gangs"
+    q = p["rs"].rand(Z, G) + 0.05
+    inv_cell = t.invspeed[t.mat]
+    sigT = t.total[t.mat] + 10.0 * inv_cell
+    # steady form (no psi_in), psi written
+    phi_o, psi_o = orc.sweep_set(p["mu"], p["weight"], p["hx"], q, sigT, want_psi=True)
+    psi = dev.new_psi()
+    qd = dev.cells_to_device(q)
+    phi = dev.sweep_set(qd, psi_out=psi)
+    assert _rel(dev.cells_to_host(phi), phi_o) < 1e-13
+    assert _rel(dev.psi_to_host(psi), psi_o[:, dev.angles, :]) < 1e-13
+    # time-dependent form, in place, twice from the same start
+    psi_prev = p["rs"].rand(Z, A, G)
+    psi1 = dev.psi_to_device(psi_prev)
+    phi1 = dev.sweep_set(qd, psi_in=psi1, psi_out=psi1)
+    psi2 = dev.psi_to_device(psi_prev)
+    phi2 = dev.sweep_set(qd, psi_in=psi2, psi_out=psi2)
+    assert bool((phi1 == phi2).all()) and bool((psi1 == psi2).all())
+    got = dev.psi_to_host(psi1)                     # angle-by-angle oracle on a sample of rows from every block
+    for g in range(G):
+        for n in (0, 15, 16, A // 2 - 1, A // 2, A // 2 + 17, A - 1):
+            src = q[:, g] + psi_prev[:, n, g] * inv_cell[:, g] / 0.1
+            ref = orc.sweep(p["mu"][n], p["hx"], src, sigT[:, g])
+            a_dev = int(np.flatnonzero(dev.angles == n)[0])
+            assert _rel(got[:, a_dev, g], ref) < 1e-13
+
+
 def test_sweep1D_fixture(golden_dir):
     """OneGroup.sweep1D through the public class against psi vectors of the unmodified reference."""
     from alpha_eigen_modules.group import OneGroup
