@@ -37,6 +37,11 @@ class AeWork(C.Structure):
                 ("ctrl_host", C.c_void_p), ("sweep_sync", C.c_void_p), ("comm", C.c_void_p), ("P", C.c_int32), ("batch", C.c_int32)]
 
 
+class AeMember(C.Structure):
+    _fields_ = [("slab", C.POINTER(AeSlab)), ("work", C.POINTER(AeWork)), ("psi", C.c_void_p), ("psi_snap", C.c_void_p),
+                ("phi_snap", C.c_void_p), ("hist", C.c_void_p)]
+
+
 # every symbol include/alpha_eigen_b200.h declares: (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -67,6 +72,7 @@ SYMBOLS = {
     "ae_time_step": (C.c_int, [C.POINTER(AeSlab), C.POINTER(AeWork), _P, _P, C.c_double, c_ip, c_ip, _P]),
     "ae_time_march": (C.c_int, [C.POINTER(AeSlab), C.POINTER(AeWork), _P, _P, _P, C.c_int32, C.c_double, c_ip, c_ip,
                                 _P]),
+    "ae_ensemble_time_march": (C.c_int, [C.POINTER(AeMember), C.c_int32, C.c_int32, C.c_double, c_ip, c_ip, _P]),
     "ae_gram": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, _P]),
     "ae_dmd_from_gram": (C.c_int, [_P, C.c_int32, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_ip, _P]),
     "ae_tsqr": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, _P]),

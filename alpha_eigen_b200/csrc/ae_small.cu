@@ -16,6 +16,12 @@
 // fixed order.  The host reads the control block once, at the end.  Inputs stay in L2 (a few MB), so plain
 // loads suffice; results are bit-compatible with the streaming path (same maps, same angle order in the flux
 // sum), which the parity tests exercise through both.
+//
+// Ensembles (BASELINE configs[4]: 1024 parameter-varied 12-group slabs).  One member is a couple of dozen CTAs,
+// so ensemble_time_march_kernel runs MANY members in one cooperative launch: the grid is cut into teams of
+// `rows` CTAs, a team marches one member at a time exactly as small_time_march_kernel would (same code, the
+// grid barrier replaced by a barrier over the team's CTAs only), and pulls the next member from a device-side
+// queue when it is done.  Members keep their own convergence histories, so results equal stand-alone runs.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include "ae_common.cuh"
@@ -42,10 +48,43 @@ struct SmallArgs {
     int num_steps;
 };
 
+// Barrier over the CTAs of one team (all co-resident: cooperative launch).  `gen` counts the barriers passed.
+struct alignas(128) TeamBar {
+    unsigned count, gen;
+    int member;                                         // member the team is working on (written by its first CTA)
+};
+struct alignas(128) EnsQueue {
+    unsigned next;                                      // next member to hand out
+};
+struct EnsResult {
+    int32_t fail, steps_done, inner_iters, pad;         // fail: 0 ok, 1 inner / 2 outer loop did not converge
+    double change, outer_change;
+};
+
+__device__ __forceinline__ void team_barrier(TeamBar *bar, unsigned &gen, int nblocks)
+{
+    ++gen;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&bar->count, 1u) == (unsigned)nblocks - 1) {
+            bar->count = 0;                             // everybody has arrived; nobody re-arrives before gen moves
+            st_release(&bar->gen, gen);
+        } else {
+            while (ld_acquire(&bar->gen) != gen) __nanosleep(20);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 template <int AC>
 struct Small {
     const SmallArgs &p;
     cg::grid_group grid;
+    TeamBar *bar;                                       // NULL: the team is the whole grid (grid.sync())
+    unsigned bar_gen;
+    int bid, nblocks;                                   // this CTA's row block, CTAs working on the problem
     double *red, *sm;
     int tid, warp, lane;
     int64_t nt, n, gthreads, gtid;
@@ -56,12 +95,14 @@ struct Small {
     int64_t goff, prow;
     double *part;
 
-    __device__ Small(const SmallArgs &p_, double *red_, double *sm_) : p(p_), grid(cg::this_grid()), red(red_), sm(sm_)
+    __device__ Small(const SmallArgs &p_, double *red_, double *sm_, int bid_, int nblocks_, TeamBar *bar_ = nullptr,
+                     unsigned gen_ = 0)
+        : p(p_), grid(cg::this_grid()), bar(bar_), bar_gen(gen_), bid(bid_), nblocks(nblocks_), red(red_), sm(sm_)
     {
         tid = threadIdx.x; warp = tid >> 5; lane = tid & 31;
         nt = p.Zp / kTile; n = (int64_t)p.G * p.Zp;
-        gthreads = (int64_t)gridDim.x * blockDim.x; gtid = (int64_t)blockIdx.x * blockDim.x + tid;
-        const int rb = blockIdx.x;
+        gthreads = (int64_t)nblocks * blockDim.x; gtid = (int64_t)bid * blockDim.x + tid;
+        const int rb = bid;
         g = rb / p.nbg; blk = rb % p.nbg;
         neg = blk < p.nb_neg;
         const int a0 = neg ? blk * AC : p.n_neg + (blk - p.nb_neg) * AC;
@@ -72,6 +113,12 @@ struct Small {
         goff = (int64_t)g * p.Zp + lane * 2;
         prow = ((int64_t)g * p.A + a) * p.Zp + lane * 2;
         part = p.partial + ((int64_t)blk * p.G + g) * p.Zp;
+    }
+
+    __device__ void sync()
+    {
+        if (bar) team_barrier(bar, bar_gen, nblocks);
+        else grid.sync();
     }
 
     // One sweep of this CTA's row block over the whole slab (group.py:41-60 for each of its angles).
@@ -159,12 +206,12 @@ struct Small {
     int ratio_calls = 0;
     __device__ double grid_ratio(double num, double den)
     {
-        double *scr = p.scratch + (ratio_calls++ & 1) * 2 * gridDim.x;
+        double *scr = p.scratch + (ratio_calls++ & 1) * 2 * nblocks;
         block_sum2(num, den, sm);
-        if (tid == 0) { scr[2 * blockIdx.x] = num; scr[2 * blockIdx.x + 1] = den; }
-        grid.sync();
+        if (tid == 0) { scr[2 * bid] = num; scr[2 * bid + 1] = den; }
+        sync();
         double a = 0.0, b = 0.0;
-        for (int i = tid; i < (int)gridDim.x; i += blockDim.x) {
+        for (int i = tid; i < nblocks; i += blockDim.x) {
             a += __ldcg(scr + 2 * i);
             b += __ldcg(scr + 2 * i + 1);
         }
@@ -184,12 +231,12 @@ struct Small {
     {
         double num, den;
         flux_update(0, cold, q, phi, num, den);
-        grid.sync();
+        sync();
         it = 0; change = 0.0;
         while (it < max_iterations - 1) {               // `assert iteration < max_iterations`, group.py:72
             ++it;
             sweep<RD, false>(q[(it - 1) & 1], psi_in, nullptr);
-            grid.sync();
+            sync();
             flux_update(it, cold, q, phi, num, den);
             change = grid_ratio(num, den);              // group.py:78
             if (change < tol) return true;              // group.py:79
@@ -203,7 +250,7 @@ __global__ void __launch_bounds__(AC * 32, AC == 8 ? 2 : 1) small_source_iterati
 {
     extern __shared__ double red[];                     // [2][AC][kTile]
     __shared__ double sm[64];
-    Small<AC> S(p, red, sm);
+    Small<AC> S(p, red, sm, blockIdx.x, gridDim.x);
     double *const q[2] = {p.q0, p.q1};
     double *const phi[2] = {p.phi0, p.phi1};
     int it;
@@ -217,13 +264,11 @@ __global__ void __launch_bounds__(AC * 32, AC == 8 ? 2 : 1) small_source_iterati
     }
 }
 
+// TimeUnit.calculate_time_dependent_flux for the problem S works on (all CTAs of its team call this together).
 // ctrl->reserved on exit: 0 ok, 1 inner loop did not converge, 2 outer loop did not converge; power_iters = steps done.
 template <int AC>
-__global__ void __launch_bounds__(AC * 32, AC == 8 ? 2 : 1) small_time_march_kernel(const SmallArgs p)
+__device__ void time_march(Small<AC> &S, const SmallArgs &p, EnsResult *res)
 {
-    extern __shared__ double red[];
-    __shared__ double sm[64];
-    Small<AC> S(p, red, sm);
     double *const q[2] = {p.q0, p.q1};
     double *const phi[2] = {p.phi0, p.phi1};
     const int64_t n_psi = S.n * p.A;
@@ -263,7 +308,7 @@ __global__ void __launch_bounds__(AC * 32, AC == 8 ? 2 : 1) small_time_march_ker
             outer_change = S.grid_ratio(num, den);
             if (outer_change < p.tol) break;                                    // time_unit.py:42
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0) { p.outer_hist[step] = outer; p.inner_hist[step] = inner_total; }
+        if (S.bid == 0 && threadIdx.x == 0) { p.outer_hist[step] = outer; p.inner_hist[step] = inner_total; }
         if (fail) break;
         // commit: replay the last sweep with its own source, now writing psi (time_unit.py:26-27)
         S.template sweep<true, true>(q[(it - 1) & 1], psi_prev, psi_next);
@@ -274,9 +319,9 @@ __global__ void __launch_bounds__(AC * 32, AC == 8 ? 2 : 1) small_time_march_ker
                 for (int gg = 0; gg < p.G; ++gg) dst[(int64_t)gg * p.Zp + s] = cur[(int64_t)gg * p.Zp + s];
         }
         steps_done = step + 1;
-        S.grid.sync();                                  // q / phi / partial are rewritten by the next step
+        S.sync();                                       // q / phi / partial are rewritten by the next step
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (S.bid == 0 && threadIdx.x == 0) {
         p.ctrl->change = change;
         p.ctrl->outer_change = outer_change;
         p.ctrl->inner_iters = it;                       // the flux of the last step is in phi[it & 1]
@@ -284,6 +329,46 @@ __global__ void __launch_bounds__(AC * 32, AC == 8 ? 2 : 1) small_time_march_ker
         p.ctrl->power_iters = steps_done;
         p.ctrl->reserved = fail;
         p.ctrl->ticket = 0;
+        if (res) {
+            res->fail = fail; res->steps_done = steps_done; res->inner_iters = it; res->pad = 0;
+            res->change = change; res->outer_change = outer_change;
+        }
+    }
+}
+
+template <int AC>
+__global__ void __launch_bounds__(AC * 32, AC == 8 ? 2 : 1) small_time_march_kernel(const SmallArgs p)
+{
+    extern __shared__ double red[];
+    __shared__ double sm[64];
+    Small<AC> S(p, red, sm, blockIdx.x, gridDim.x);
+    time_march<AC>(S, p, nullptr);
+}
+
+// Many members in one launch: teams of `rows` CTAs pull members from a queue (see the file header).
+template <int AC>
+__global__ void __launch_bounds__(AC * 32, AC == 8 ? 2 : 1)
+    ensemble_time_march_kernel(const SmallArgs *members, int count, int rows, EnsQueue *queue, TeamBar *bars, EnsResult *results)
+{
+    extern __shared__ double red[];
+    __shared__ double sm[64];
+    __shared__ SmallArgs sp;
+    const int team = blockIdx.x / rows, bid = blockIdx.x - team * rows;
+    TeamBar *bar = bars + team;
+    unsigned gen = 0;
+    for (;;) {
+        if (bid == 0 && threadIdx.x == 0) bar->member = (int)atomicAdd(&queue->next, 1u);
+        team_barrier(bar, gen, rows);
+        const int m = *(volatile int *)&bar->member;
+        if (m >= count) break;
+        if (threadIdx.x == 0) sp = members[m];
+        __syncthreads();
+        {
+            Small<AC> S(sp, red, sm, bid, rows, bar, gen);
+            time_march<AC>(S, sp, results + m);
+            gen = S.bar_gen;
+        }
+        team_barrier(bar, gen, rows);                   // everybody has read bar->member and sp, and left the member's buffers
     }
 }
 
@@ -366,4 +451,87 @@ int launch_small_time_march(const ae_slab *s, ae_work *w, double *psi, double *p
     return AE_OK;
 }
 
+int check_work(const ae_slab *s, const ae_work *w, const char *who);
+
 }  // namespace ae
+
+// Time march of `count` same-shape small slabs in ONE cooperative launch (teams of CTAs, member queue).
+extern "C" int ae_ensemble_time_march(const ae_member *members, int32_t count, int32_t num_steps, double tol,
+                                      int32_t *status, int32_t *teams_out, void *stream)
+{
+    using namespace ae;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!members || count < 1 || num_steps < 1) { set_error("ae_ensemble_time_march: bad argument"); return AE_BAD_ARG; }
+    SmallArgs *h_args = (SmallArgs *)malloc(sizeof(SmallArgs) * (size_t)count);
+    EnsResult *h_res = (EnsResult *)malloc(sizeof(EnsResult) * (size_t)count);
+    if (!h_args || !h_res) { free(h_args); free(h_res); set_error("ae_ensemble_time_march: out of host memory"); return AE_CUDA_ERROR; }
+    struct Guard {
+        SmallArgs *a; EnsResult *r; void *d; cudaStream_t st;
+        ~Guard() { free(a); free(r); if (d) cudaFreeAsync(d, st); }
+    } guard{h_args, h_res, nullptr, st};
+    int ac0 = 0, rows0 = 0;
+    const ae_slab *s0 = members[0].slab;
+    for (int m = 0; m < count; ++m) {
+        const ae_member &mem = members[m];
+        AE_TRY(check_work(mem.slab, mem.work, "ae_ensemble_time_march"));
+        int ac = 0, rows = 0;
+        if (!mem.psi || !mem.hist || !mem.slab->cdt || mem.work->comm || !small_problem(mem.slab, mem.work, h_args[m], ac, rows)) {
+            set_error("ae_ensemble_time_march: member %d is not a single-GPU small time-dependent slab", m);
+            return AE_BAD_ARG;
+        }
+        if (m == 0) { ac0 = ac; rows0 = rows; }
+        if (mem.slab->Z != s0->Z || mem.slab->Zp != s0->Zp || mem.slab->A != s0->A || mem.slab->n_neg != s0->n_neg ||
+            mem.slab->G != s0->G) {
+            set_error("ae_ensemble_time_march: member %d has a different shape (Z, A, n_neg, G must match)", m);
+            return AE_BAD_ARG;
+        }
+        SmallArgs &p = h_args[m];
+        p.tol = tol; p.psi = mem.psi; p.psi_snap = mem.psi_snap; p.phi_snap = mem.phi_snap;
+        p.outer_hist = mem.hist; p.inner_hist = mem.hist + num_steps; p.num_steps = num_steps;
+        AE_CUDA(cudaMemsetAsync(mem.hist, 0, sizeof(int32_t) * 2 * (size_t)num_steps, st));
+    }
+    const void *kernel = ac0 == 16 ? (const void *)ensemble_time_march_kernel<16> : (const void *)ensemble_time_march_kernel<8>;
+    const size_t smem = 2 * (size_t)ac0 * kTile * sizeof(double);
+    if (smem > 48 * 1024) AE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, dev = 0, sms = 0;
+    AE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ac0 * 32, smem));
+    AE_CUDA(cudaGetDevice(&dev));
+    AE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int teams = per_sm * sms / rows0;
+    if (teams > count) teams = count;
+    if (teams < 1) { set_error("ae_ensemble_time_march: a member needs %d co-resident CTAs, the device holds %d", rows0, per_sm * sms); return AE_BAD_ARG; }
+    if (teams_out) *teams_out = teams;
+    // one device block: [SmallArgs x count][EnsResult x count][EnsQueue][TeamBar x teams]
+    const size_t off_res = (sizeof(SmallArgs) * (size_t)count + 127) / 128 * 128;
+    const size_t off_q = off_res + (sizeof(EnsResult) * (size_t)count + 127) / 128 * 128;
+    const size_t off_bar = off_q + sizeof(EnsQueue);
+    const size_t bytes = off_bar + sizeof(TeamBar) * (size_t)teams;
+    char *d = nullptr;
+    AE_CUDA(cudaMallocAsync((void **)&d, bytes, st));
+    guard.d = d;
+    AE_CUDA(cudaMemsetAsync(d + off_res, 0, bytes - off_res, st));
+    AE_CUDA(cudaMemcpyAsync(d, h_args, sizeof(SmallArgs) * (size_t)count, cudaMemcpyHostToDevice, st));
+    const SmallArgs *d_args = (const SmallArgs *)d;
+    EnsResult *d_res = (EnsResult *)(d + off_res);
+    EnsQueue *d_q = (EnsQueue *)(d + off_q);
+    TeamBar *d_bar = (TeamBar *)(d + off_bar);
+    int cnt = count, rows = rows0;
+    void *args[] = {(void *)&d_args, (void *)&cnt, (void *)&rows, (void *)&d_q, (void *)&d_bar, (void *)&d_res};
+    AE_CUDA(cudaLaunchCooperativeKernel(kernel, dim3((unsigned)(teams * rows0)), dim3(ac0 * 32), args, smem, st));
+    AE_CUDA(cudaMemcpyAsync(h_res, d_res, sizeof(EnsResult) * (size_t)count, cudaMemcpyDeviceToHost, st));
+    AE_CUDA(cudaStreamSynchronize(st));
+    int any_fail = 0;
+    const size_t n_psi = (size_t)s0->G * s0->Zp * s0->A;
+    for (int m = 0; m < count; ++m) {
+        ae_work *w = members[m].work;
+        if (h_res[m].inner_iters & 1) { double *t = w->phi; w->phi = w->phi_alt; w->phi_alt = t; }   // newest flux -> w->phi
+        const int failed = h_res[m].fail != 0 || h_res[m].steps_done != num_steps;
+        any_fail |= failed;
+        if (status) status[m] = failed ? AE_NOT_CONVERGED : AE_OK;
+        if (!failed && members[m].psi_snap)
+            AE_CUDA(cudaMemcpyAsync(members[m].psi, members[m].psi_snap + (size_t)(num_steps - 1) * n_psi, n_psi * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, st));
+    }
+    AE_CUDA(cudaStreamSynchronize(st));
+    return (any_fail && !status) ? AE_NOT_CONVERGED : AE_OK;
+}

@@ -38,7 +38,7 @@ static int poll_ctrl(ae_work *w, cudaStream_t st)
     return AE_OK;
 }
 
-static int check_work(const ae_slab *s, const ae_work *w, const char *who)
+int check_work(const ae_slab *s, const ae_work *w, const char *who)
 {
     if (!s || !w || !w->phi || !w->phi_alt || !w->phi_outer || !w->base || !w->q0 || !w->q1 || !w->partial || !w->norm_scratch ||
         !w->ctrl || !w->ctrl_host || !w->sweep_sync || w->P != ae_partial_count(s->A, s->n_neg)) {

@@ -137,14 +137,34 @@ def case_c5_sample(out, E=32, Z=2048, A=16, G=12, steps=200, concurrent=12):
     flight on one GPU (member-parallel mode; every member is an independent solve)."""
     from alpha_eigen_b200.ensemble import Ensemble, synthetic_ensemble
     members = synthetic_ensemble(1024, Z, A, G)[:: 1024 // E][:E]
-    Ensemble(members[:2], dt=0.1, num_steps=20, concurrent=2).run()          # warm-up
+    Ensemble(members[:2], dt=0.1, num_steps=20, concurrent=2, mode="streams").run()          # warm-up
     sync(); t0 = time.perf_counter()
-    res = Ensemble(members, dt=0.1, num_steps=steps, concurrent=concurrent).run()
+    res = Ensemble(members, dt=0.1, num_steps=steps, concurrent=concurrent, mode="streams").run()
     sync(); t1 = time.perf_counter()
     sweeps = sum(int(np.sum(r["inner"])) + steps for r in res)
-    out({"case": "c5_ensemble_sample", "members": E, "of": 1024, "Z": Z, "A": A, "G": G, "steps": steps,
+    out({"case": "c5_ensemble_streams", "members": E, "of": 1024, "Z": Z, "A": A, "G": G, "steps": steps,
          "concurrent_members": concurrent, "wall_s": t1 - t0, "members_per_s": E / (t1 - t0),
          "sweep_sets": sweeps, "updates_per_s": float(sweeps) * Z * A * G / (t1 - t0),
+         "all_converged": all(r["status"] == 0 for r in res),
+         "alpha0_first_last": [float(res[0]["alphas"][0].real), float(res[-1]["alphas"][0].real)],
+         "ranks": [int(res[0]["rank"]), int(res[-1]["rank"])]})
+
+
+def case_c5_batched(out, E=128, Z=2048, A=16, G=12, steps=200, snapshots="psi"):
+    """BASELINE configs[4], one GPU's share (128 of 1024 members at 8 GPUs): all marches in one cooperative kernel
+    (ae_ensemble_time_march: teams of CTAs pulling members from a device-side queue), then the members' DMDs."""
+    from alpha_eigen_b200.ensemble import solve_members_batched, synthetic_ensemble
+    members = synthetic_ensemble(1024, Z, A, G)[:: 1024 // E][:E]
+    solve_members_batched(members[:2], 0.1, 10, snapshots=snapshots)             # warm-up
+    tm = {}
+    sync(); t0 = time.perf_counter()
+    res = solve_members_batched(members, 0.1, steps, snapshots=snapshots, timings=tm)
+    sync(); t1 = time.perf_counter()
+    sweeps = sum(int(np.sum(r["inner"])) + steps for r in res)
+    out({"case": "c5_ensemble_batched", "members": E, "of": 1024, "Z": Z, "A": A, "G": G, "steps": steps,
+         "snapshots": snapshots, "members_in_flight": int(res[0]["in_flight"]), "wall_s": t1 - t0, "setup_s": tm["setup"],
+         "march_s": tm["march"], "dmd_s": tm["dmd"], "members_per_s": E / (t1 - t0), "sweep_sets": sweeps,
+         "march_updates_per_s": float(sweeps) * Z * A * G / tm["march"],
          "all_converged": all(r["status"] == 0 for r in res),
          "alpha0_first_last": [float(res[0]["alphas"][0].real), float(res[-1]["alphas"][0].real)],
          "ranks": [int(res[0]["rank"]), int(res[-1]["rank"])]})
@@ -157,6 +177,7 @@ def main():
     ap.add_argument("--skip-long", action="store_true")
     ap.add_argument("--skip-c5", action="store_true")
     ap.add_argument("--only-c5", action="store_true")
+    ap.add_argument("--c5-members", type=int, default=128, help="members of the 1024-member ensemble to run (one GPU's share)")
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     f = open(args.out, "w")
@@ -168,7 +189,9 @@ def main():
         f.flush()
 
     if args.only_c5:
-        case_c5_sample(out)
+        case_c5_batched(out, E=args.c5_members)
+        case_c5_batched(out, E=args.c5_members, snapshots="phi")
+        case_c5_sample(out, E=min(32, args.c5_members))
         f.close()
         return
     case_kp_k(out)
@@ -179,6 +202,7 @@ def main():
     if not args.skip_c3:
         case_c3_alpha(out)
     if not args.skip_c5:
+        case_c5_batched(out, E=args.c5_members)
         case_c5_sample(out)
     f.close()
 

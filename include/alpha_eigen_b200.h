@@ -177,6 +177,24 @@ int ae_time_step(const ae_slab *s, ae_work *w, const double *psi_prev, double *p
 int ae_time_march(const ae_slab *s, ae_work *w, double *psi, double *psi_snap, double *phi_snap,
                   int32_t num_steps, double tol, int32_t *outer_hist, int32_t *inner_hist, void *stream);
 
+/* ---- ensembles of small slabs (BASELINE configs[4]) ----------------------------------------------------
+ * One member = one TimeUnit.calculate_time_dependent_flux (time_unit.py:17-27) on its own slab and buffers. */
+typedef struct ae_member {
+    const ae_slab *slab;     /* host pointers to the member's problem and work buffers (all members: same Z, A, */
+    ae_work *work;           /* n_neg, G; single GPU; small enough for the fused kernels)                       */
+    double *psi;             /* [G][A][Zp] psi0 on entry, the last step's psi on exit */
+    double *psi_snap;        /* [num_steps][G][A][Zp] or NULL, as in ae_time_march */
+    double *phi_snap;        /* [num_steps][G][Zp] or NULL */
+    int32_t *hist;           /* DEVICE [2][num_steps]: outer, then inner iterations per step */
+} ae_member;
+/* Marches all members in ONE cooperative launch: the grid is cut into teams of CTAs (one team = the row blocks
+ * of one member) that pull members from a device-side queue and synchronise only among themselves; every member
+ * keeps its own convergence history, so results equal `count` separate ae_time_march calls.  status [count]
+ * (host, may be NULL) receives AE_OK / AE_NOT_CONVERGED per member; *teams_out (may be NULL) the number of
+ * members in flight.  On return each member's work->phi is the flux of its last step. */
+int ae_ensemble_time_march(const ae_member *members, int32_t count, int32_t num_steps, double tol,
+                           int32_t *status, int32_t *teams_out, void *stream);
+
 /* ---- DMD: TimeUnit.compute_alpha_eigenvalues (time_unit.py:61-92) ---------------------- */
 /* gram[n][n] (device, row-major) = S S^T for snapshot rows S [n][ld] restricted to len columns. */
 int ae_gram(const double *snap, int64_t ld, int64_t len, int32_t n, double *gram, void *stream);

@@ -200,14 +200,16 @@ def test_flux_update_entry_point_matches_numpy():
     assert abs(ctrl.change - change) < 1e-12 * change and ctrl.inner_iters == 7 and ctrl.inner_done == 0
 
 
-def test_ensemble_members_match_standalone_oracle():
+@pytest.mark.parametrize("mode", ["batched", "streams"])
+def test_ensemble_members_match_standalone_oracle(mode):
     """BASELINE configs[4] in miniature: every member of a concurrently solved ensemble equals its own
-    stand-alone oracle solve (iteration counts, psi) and carries its own alpha spectrum."""
+    stand-alone oracle solve (iteration counts, psi) and carries its own alpha spectrum.  batched = all members
+    in one cooperative kernel (ae_ensemble_time_march), streams = one fused kernel per member."""
     from alpha_eigen_b200.ensemble import Ensemble, synthetic_ensemble
     from oracle import ae_oracle as orc
     E, Z, A, G, steps = 5, 300, 4, 3, 12
     members = synthetic_ensemble(E, Z, A, G)
-    res = Ensemble(members, dt=0.1, num_steps=steps, concurrent=3).run(keep_snapshots=True)
+    res = Ensemble(members, dt=0.1, num_steps=steps, concurrent=3, mode=mode).run(keep_snapshots=True)
     dom = []
     for p, r in zip(members, res):
         tab = orc.Tables(p["mat"], p["total"], p["scat"], p["chi"], p["nusf"], p["invspeed"])
@@ -222,6 +224,58 @@ def test_ensemble_members_match_standalone_oracle():
         assert abs(r["alphas"][0] - ref[0]) < 1e-6 * abs(ref[0])
         dom.append(r["alphas"][0].real)
     assert len(set(np.round(dom, 8))) == E          # parameter variation shows up in the spectrum
+
+
+def test_batched_ensemble_queue_and_failed_member():
+    """More members than teams fit on the chip (the device-side queue hands them out), members of a shape with two
+    angle blocks per direction, and one member that cannot converge: it must be reported alone, the others must
+    equal the one-kernel-per-member path bit for bit (same arithmetic, same order)."""
+    import torch
+    from alpha_eigen_b200 import _lib
+    from alpha_eigen_b200.device import SlabDevice
+    from alpha_eigen_b200.ensemble import march_batched, synthetic_ensemble
+    E, Z, A, G, steps = 70, 520, 20, 4, 4          # S20: 10 angles per direction = 2 blocks of 8 -> 16 CTAs per member
+    members = synthetic_ensemble(E, Z, A, G)
+    bad = 37
+    members[bad]["nusf"] = members[bad]["nusf"] * 400.0        # wildly supercritical: the fission loop diverges
+    devs, psis, snaps, phis = [], [], [], []
+    for p in members:
+        dev = SlabDevice(p["Z"], p["hx"], p["mu"], p["weight"], p["mat"], p["total"], p["scat"], p["chi"], p["nusf"],
+                         p["invspeed"], dt=0.1)
+        devs.append(dev)
+        psis.append(dev.psi_to_device(np.repeat(0.5 * p["phi0"][:, None, :], A, axis=1)))
+        snaps.append(torch.zeros(steps * dev.G * dev.A * dev.Zp, dtype=torch.float64, device=dev.dev))
+        phis.append(torch.zeros(steps * dev.G * dev.Zp, dtype=torch.float64, device=dev.dev))
+    status, outer, inner, teams = march_batched(devs, psis, snaps, phis, steps)
+    assert 1 <= teams < E, teams
+    assert status[bad] == _lib.AE_NOT_CONVERGED and np.count_nonzero(status) == 1
+    for j in (0, 1, bad - 1, bad + 1, E - 1):
+        p = members[j]
+        solo = SlabDevice(p["Z"], p["hx"], p["mu"], p["weight"], p["mat"], p["total"], p["scat"], p["chi"], p["nusf"],
+                          p["invspeed"], dt=0.1)
+        psi = solo.psi_to_device(np.repeat(0.5 * p["phi0"][:, None, :], A, axis=1))
+        snap = torch.zeros_like(snaps[j])
+        phi_snap = torch.zeros_like(phis[j])
+        st, o, i = solo.time_march(psi, steps, 1e-10, snap, phi_snap)
+        assert st == 0 and list(o) == list(outer[j]) and list(i) == list(inner[j])
+        assert bool((snap == snaps[j]).all()) and bool((phi_snap == phis[j]).all()) and bool((psi == psis[j]).all())
+        assert bool((solo.phi == devs[j].phi).all())
+
+
+def test_ensemble_rejects_mixed_shapes():
+    import torch
+    from alpha_eigen_b200.device import SlabDevice
+    from alpha_eigen_b200.ensemble import march_batched, synthetic_ensemble
+    a = synthetic_ensemble(1, 300, 4, 3)[0]
+    b = synthetic_ensemble(1, 600, 4, 3)[0]
+    devs, psis = [], []
+    for p in (a, b):
+        dev = SlabDevice(p["Z"], p["hx"], p["mu"], p["weight"], p["mat"], p["total"], p["scat"], p["chi"], p["nusf"],
+                         p["invspeed"], dt=0.1)
+        devs.append(dev)
+        psis.append(dev.new_psi())
+    with pytest.raises(ValueError, match="different shape"):
+        march_batched(devs, psis, None, None, 2)
 
 
 def test_multi_region_slab_generic_zone_path():

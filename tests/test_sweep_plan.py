@@ -95,6 +95,8 @@ def test_plan_c3_pairs_the_two_blocks_of_a_direction():
     (7, 2, 3, 70_000, 296),         # unequal directions: no gangs
     (64, 32, 12, 300_000, 148),     # gangs, ranges cutting rows
     (128, 64, 9, 40_000, 148),      # four blocks per direction
+    (64, 32, 37, 8000, 148),        # shapes of test_ganged_sweep_matches_oracle
+    (96, 48, 26, 5000, 148),
     (32, 16, 70, 125_000, 148),     # C4 rows of one rank at 8 GPUs: one block per direction
 ])
 def test_plan_covers_every_tile_once(A, n_neg, G, cells, resident):
