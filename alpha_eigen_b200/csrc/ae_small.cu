@@ -346,8 +346,10 @@ __global__ void __launch_bounds__(AC * 32, AC == 8 ? 2 : 1) small_time_march_ker
 }
 
 // Many members in one launch: teams of `rows` CTAs pull members from a queue (see the file header).
-template <int AC>
-__global__ void __launch_bounds__(AC * 32, AC == 8 ? 2 : 1)
+// MINB = CTAs per SM the register allocation aims at: members in flight = MINB * SMs / rows.  The march of a small
+// member is latency bound (serial tile chains, team barriers), so more teams in flight win until spills bite.
+template <int AC, int MINB>
+__global__ void __launch_bounds__(AC * 32, MINB)
     ensemble_time_march_kernel(const SmallArgs *members, int count, int rows, EnsQueue *queue, TeamBar *bars, EnsResult *results)
 {
     extern __shared__ double red[];
@@ -490,7 +492,13 @@ extern "C" int ae_ensemble_time_march(const ae_member *members, int32_t count, i
         p.outer_hist = mem.hist; p.inner_hist = mem.hist + num_steps; p.num_steps = num_steps;
         AE_CUDA(cudaMemsetAsync(mem.hist, 0, sizeof(int32_t) * 2 * (size_t)num_steps, st));
     }
-    const void *kernel = ac0 == 16 ? (const void *)ensemble_time_march_kernel<16> : (const void *)ensemble_time_march_kernel<8>;
+    // 8-warp CTAs: 2 (128 registers), 3 (80) or 4 (64, some spills) CTAs per SM; AE_ENSEMBLE_CTAS_PER_SM overrides
+    static const char *force = getenv("AE_ENSEMBLE_CTAS_PER_SM");
+    const int minb = force && atoi(force) >= 2 && atoi(force) <= 4 ? atoi(force) : 3;
+    const void *kernel = ac0 == 16 ? (const void *)ensemble_time_march_kernel<16, 1>
+                         : minb == 2 ? (const void *)ensemble_time_march_kernel<8, 2>
+                         : minb == 3 ? (const void *)ensemble_time_march_kernel<8, 3>
+                                     : (const void *)ensemble_time_march_kernel<8, 4>;
     const size_t smem = 2 * (size_t)ac0 * kTile * sizeof(double);
     if (smem > 48 * 1024) AE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0, dev = 0, sms = 0;

@@ -1,10 +1,13 @@
 """Materials (mirror of reference material.py) plus an explicit multigroup table material.
 
 SimpleMaterial reproduces the hard-coded one-group Kornreich-Parsons data (material.py:9-20).
-Material reads the reference's HDF5 layout (material.py:36-46) when h5py is available.
+Material reads the reference's HDF5 cross-section files (material.py:36-46) with h5py or, when that is not
+installed, the built-in reader hdf5_lite; the reference's own data set is packaged as .npz.
 TableMaterial carries explicit multigroup arrays; it is what the synthetic 12- and 70-group
 benchmark slabs use (the reference has no runnable multigroup path).
 """
+import os
+
 import numpy as np
 
 _KP = {  # name -> (scatter_xs, nu_sigmaf)      material.py:12-20
@@ -39,33 +42,67 @@ class TableMaterial(SimpleMaterial):
         self.inv_speed = np.asarray(inv_speed, dtype=np.float64).reshape(G)
 
 
-class Material(SimpleMaterial):
-    """HDF5-backed multigroup material, file layout of material.py:30,36-46."""
+_PACKAGED_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
-    def __init__(self, material_type, num_groups, data_dir="./data"):
+
+def _open_hdf5(path):
+    """h5py when it is installed, else the built-in reader (same calls: hf[name][:])."""
+    try:
+        import h5py
+        return h5py.File(path, "r")
+    except ImportError:
+        from .hdf5_lite import File
+        return File(path, "r")
+
+
+class Material(SimpleMaterial):
+    """Multigroup material read from the reference's cross-section files (material.py:26-46).
+
+    File lookup: `<data_dir>/<G>_group/<name>.hdf5` relative to the working directory, exactly as
+    material.py:30 does; when that file does not exist, the copy of the reference's data set packaged with this
+    module (alpha_eigen_b200/data/<G>_group/<name>.npz, written by tools/convert_xs_data.py: same datasets, same
+    names) is used, so `Material('metal', 70)` works from any directory.
+
+    material.py:43 discards the file's fission spectrum (chi = zeros), which makes every fission source vanish;
+    that behaviour is kept by default and `use_file_chi=True` wires the `chi` dataset in.
+    """
+
+    def __init__(self, material_type, num_groups, data_dir="./data", use_file_chi=False):
         super().__init__(material_type, num_groups)
         self.name = material_type
         self.filename = f"{data_dir}/{num_groups}_group/{material_type}.hdf5"
+        self.use_file_chi = use_file_chi
         self.group_edges = None
         self.group_centers = None
         self.num_energy_groups = num_groups
         self.parse_file()
 
+    def _datasets(self):
+        if os.path.exists(self.filename):
+            with _open_hdf5(self.filename) as hf:
+                return {k: np.asarray(hf[k][:]) for k in hf.keys()}
+        packaged = os.path.join(_PACKAGED_DATA, f"{self.num_groups}_group", f"{self.name}.npz")
+        if not os.path.exists(packaged):
+            raise FileNotFoundError(f"{self.filename} not found and no packaged copy at {packaged}")
+        with np.load(packaged) as z:
+            return {k: z[k] for k in z.files}
+
     def parse_file(self):
-        try:
-            import h5py
-        except ImportError as e:  # the reference imports h5py at module scope (material.py:2)
-            raise ImportError("Material needs h5py to read " + self.filename) from e
-        with h5py.File(self.filename, "r") as hf:
-            self.scatter_xs = hf["scat_xs"][:].transpose()
-            self.total_xs = hf["total_xs"][:]
-            self.nu_sigmaf = hf["nusigma_f"][:]
-            self.inv_speed = hf["inverse_speed"][:]
-            self.group_edges = hf["group_edges"][:]
-            self.chi = np.zeros(self.num_energy_groups)         # material.py:43 (file's chi is ignored)
-            self.nusigma_f = self.chi.copy()
-        self.group_centers = 0.5 * (self.group_edges[:-1] + self.group_edges[1:])
+        hf = self._datasets()
+        as_f64 = lambda a: np.atleast_1d(np.asarray(a, dtype=np.float64))
+        self.scatter_xs = as_f64(hf["scat_xs"]).transpose()         # material.py:38: [g_from, g_to] after the transpose
+        self.total_xs = as_f64(hf["total_xs"])
+        self.nu_sigmaf = as_f64(hf["nusigma_f"])
+        self.inv_speed = as_f64(hf["inverse_speed"])
+        self.group_edges = as_f64(hf["group_edges"])
+        self.chi = np.zeros(self.num_energy_groups)                 # material.py:43 (the file's chi is ignored)
+        if self.use_file_chi and "chi" in hf:
+            self.chi = as_f64(hf["chi"])
+        self.nusigma_f = np.zeros(self.num_energy_groups)           # material.py:44
+        self.group_centers = (self.group_edges[0:-1] + self.group_edges[1:]) * 0.5
         self.num_energy_groups = np.size(self.group_centers)
+        if self.scatter_xs.ndim == 1 and self.num_energy_groups == 1:
+            self.scatter_xs = self.scatter_xs.reshape(1, 1)
 
 
 def material_row(mat, G):

@@ -304,6 +304,45 @@ def test_multi_region_slab_generic_zone_path():
     assert _rel(mg.phi.new, ro["phi_new"]) < 1e-10
 
 
+def test_real_70_group_data_through_the_public_classes():
+    """the reference's own 70-group metal / polyethylene cross-sections
+    (material.py:26-46; packaged copy, read through Material) on a reflected metal slab: k power iteration and
+    a short time march through MultiGroup / TimeUnit against the oracle on the same tables."""
+    from alpha_eigen_b200.group import MultiGroup
+    from alpha_eigen_b200.material import Material
+    from alpha_eigen_b200.slab import MultiRegionSlab
+    from alpha_eigen_b200.time_unit import TimeUnit
+    from oracle import ae_oracle as orc
+    G = 70
+    metal = Material("metal", G, use_file_chi=True)         # material.py:43 zeroes chi: no fission source at all
+    poly = Material("polyethylene", G, use_file_chi=True)
+    np.random.seed(2021)
+    s = MultiRegionSlab(length=10, cells_per_mfp=1, num_angles=8, reflector_thick=2, inner_thick=1, num_zones=200,
+                        num_groups=G, material1=metal, material2=poly)
+    mg = MultiGroup(s)
+    mg.create_zones()
+    tab = orc.Tables(mg._mat_index, *[np.array([getattr(m, n) for m in mg._materials]) for n in
+                                      ("total_xs", "scatter_xs", "chi", "nu_sigmaf", "inv_speed")])
+    phi0 = mg.phi.old.copy()
+    k = mg.perform_power_iteration(quiet=True)
+    ro = orc.power_iteration(s.mu, s.weight, s.hx, tab, phi0)
+    assert ro["status"] == 0 and k.converged
+    assert abs(k.new - ro["k_new"]) < 1e-9 * ro["k_new"], (k.new, ro["k_new"])
+    assert _rel(mg.phi.new, ro["phi_new"]) < 1e-10
+    # two backward-Euler steps from the converged flux shape (metal inv_speed spans 1.8e-2 .. 4.3e3); the fixed
+    # source of the march is group.source (time_unit.py:19), which the power iteration left as the fission source
+    steps = 2
+    tu = TimeUnit(s, mg, steps, 0.1)
+    psi0 = np.repeat(0.5 * mg.phi.new[:, None, :], s.num_angles, axis=1)
+    tu.psi0 = psi0
+    s_ext = np.asarray(mg.source, dtype=np.float64).reshape(s.num_zones, G).copy()
+    tu.calculate_time_dependent_flux()
+    rt = orc.time_march(s.mu, s.weight, s.hx, tab, s_ext, psi0, 0.1, steps)
+    assert rt["status"] == 0
+    assert list(tu.outer_iterations) == list(rt["outer"]) and list(tu.inner_iterations) == list(rt["inner"])
+    assert _rel(tu.psi[..., steps - 1], rt["psi_last"]) < 1e-10
+
+
 def test_cell_range_host_io_roundtrip():
     """ae_pack_cells_range / ae_unpack_cells_range (single rank: the range is the whole row)."""
     import torch
