@@ -161,41 +161,67 @@ struct Small {
     }
 
     // Flux update over the cells owned by this thread; it == 0 is the cold start (group.py:66 / time_unit.py:45).
+    // Groups are handled four at a time: the loads of a chunk are issued together and only then consumed (every
+    // operand sits in L2, ~1 us away, and one group after the other would expose that latency G times); sums
+    // keep the reference's order (partials in block order, norms in group order, scatter over g' ascending).
     __device__ void flux_update(int it, double cold, double *const (&q)[2], double *const (&phi)[2], double &num, double &den)
     {
         const double *phi_in = phi[(it + 1) & 1];
         double *phi_out = phi[it & 1], *q_next = q[it & 1];
         num = 0.0; den = 0.0;
         constexpr int kLocalG = 16;                     // a cell's fluxes stay in registers / L1-resident local memory
+        constexpr int kU = 4;
+        const int G = p.G;
         for (int64_t s = gtid; s < p.Zp; s += gthreads) {
             const bool valid = logical_cell(s) < p.Z;
             double xv[kLocalG];
-            for (int gg = 0; gg < p.G; ++gg) {
-                const int64_t i = (int64_t)gg * p.Zp + s;
-                double x;
-                if (it == 0) {
-                    x = valid ? cold : 0.0;
-                } else {
-                    x = p.partial[i];
-                    for (int pp = 1; pp < p.nbg; ++pp) x += p.partial[(int64_t)pp * n + i];    // block order (group.py:77)
-                    const double d = x - phi_in[i];                                         // group.py:78
-                    num = fma(d, d, num);
-                    den = fma(x, x, den);
+            for (int g0 = 0; g0 < G; g0 += kU) {
+                double x[kU], old[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    x[u] = 0.0; old[u] = 0.0;
+                    if (g0 + u < G && it != 0) {
+                        const int64_t i = (int64_t)(g0 + u) * p.Zp + s;
+                        x[u] = p.partial[i];
+                        old[u] = phi_in[i];
+                    }
                 }
-                phi_out[i] = x;                                                             // group.py:80
-                if (gg < kLocalG) xv[gg] = x;
+                for (int pp = 1; pp < p.nbg; ++pp) {                                        // block order (group.py:77)
+#pragma unroll
+                    for (int u = 0; u < kU; ++u)
+                        if (g0 + u < G && it != 0) x[u] += p.partial[(int64_t)pp * n + (int64_t)(g0 + u) * p.Zp + s];
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    if (g0 + u >= G) continue;
+                    if (it == 0) {
+                        x[u] = valid ? cold : 0.0;
+                    } else {
+                        const double d = x[u] - old[u];                                     // group.py:78
+                        num = fma(d, d, num);
+                        den = fma(x[u], x[u], den);
+                    }
+                    phi_out[(int64_t)(g0 + u) * p.Zp + s] = x[u];                           // group.py:80
+                    if (g0 + u < kLocalG) xv[g0 + u] = x[u];
+                }
             }
-            const double *sc = p.scat + (size_t)p.mat[s] * p.G * p.G;
-            for (int gg = 0; gg < p.G; ++gg) {
-                double acc = 0.0;
-                if (p.G <= kLocalG) {
-                    for (int gp = 0; gp < p.G; ++gp) acc = fma(xv[gp], __ldg(sc + gp * p.G + gg), acc);
-                } else {
-                    for (int gp = 0; gp < p.G; ++gp)
-                        acc = fma(phi_out[(int64_t)gp * p.Zp + s], __ldg(sc + gp * p.G + gg), acc);
+            const double *sc = p.scat + (size_t)p.mat[s] * G * G;
+            for (int g0 = 0; g0 < G; g0 += kU) {
+                double acc[kU], b[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    acc[u] = 0.0;
+                    b[u] = g0 + u < G ? p.base[(int64_t)(g0 + u) * p.Zp + s] : 0.0;         // in flight during the sums
                 }
-                const int64_t i = (int64_t)gg * p.Zp + s;
-                q_next[i] = p.base[i] + 0.5 * acc;                                          // group.py:73 / time_unit.py:53
+                for (int gp = 0; gp < G; ++gp) {
+                    const double xg = G <= kLocalG ? xv[gp] : phi_out[(int64_t)gp * p.Zp + s];
+#pragma unroll
+                    for (int u = 0; u < kU; ++u)
+                        if (g0 + u < G) acc[u] = fma(xg, __ldg(sc + gp * G + g0 + u), acc[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u)
+                    if (g0 + u < G) q_next[(int64_t)(g0 + u) * p.Zp + s] = b[u] + 0.5 * acc[u];   // group.py:73 / time_unit.py:53
             }
         }
     }

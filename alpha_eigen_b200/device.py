@@ -60,6 +60,82 @@ class Comm:
             self.handle = C.c_void_p()
 
 
+class HostPipe:
+    """Double-buffered, cell-sharded host I/O for a stream of steps whose sources come from (and whose fluxes go
+    to) pinned host memory: the upload of step i+1's source and the download of step i-1's flux run on their own
+    CUDA streams (the copy engines) while step i's kernels run, so in steady state a step costs
+    max(kernels, copies) instead of their sum.  Usage per step i:
+
+        pipe.feed(i, rows)              # main stream: wait for upload i, pack it into rows [G][Zp] (+ all-gather)
+        pipe.upload(i + 1, next_host)   # copy stream: H2D of the next source, overlaps the kernels below
+        ... kernels of step i ...
+        pipe.drain(i, flux_rows, out_host)   # main: unpack this rank's cells; copy stream: D2H into out_host
+
+    and pipe.wait() before the host touches the last results.  upload(0, ...) primes the pipe."""
+
+    def __init__(self, dev: "SlabDevice"):
+        torch = dev.torch
+        self.dev = dev
+        _, count, _, _ = dev.cell_range()
+        n = max(count, 1) * dev.G
+        f64 = dict(dtype=torch.float64, device=dev.dev)
+        self.stage_in = [torch.empty(n, **f64) for _ in range(2)]
+        self.stage_out = [torch.empty(n, **f64) for _ in range(2)]
+        self.copy_in, self.copy_out = torch.cuda.Stream(device=dev.dev), torch.cuda.Stream(device=dev.dev)
+        ev = lambda: [torch.cuda.Event(), torch.cuda.Event()]
+        self.in_ready, self.in_free, self.out_ready, self.out_free = ev(), ev(), ev(), ev()
+        self.in_used, self.out_used = [False, False], [False, False]
+
+    def upload(self, i, shard_host):
+        """Start the H2D copy of step i's source: pinned (count, G) tensor with this rank's cells."""
+        torch, k = self.dev.torch, i & 1
+        with torch.cuda.stream(self.copy_in):
+            if self.in_used[k]:
+                self.copy_in.wait_event(self.in_free[k])            # step i-2 has packed this slot
+            self.stage_in[k][:shard_host.numel()].copy_(shard_host.view(-1), non_blocking=True)
+            self.in_ready[k].record(self.copy_in)
+        self.in_used[k] = True
+
+    def feed(self, i, rows):
+        """On the current stream: pack the uploaded source of step i into `rows` [G][Zp] (all ranks gather)."""
+        dev, k = self.dev, i & 1
+        main = dev.torch.cuda.current_stream(dev.dev)
+        _, count, s0, cells = dev.cell_range()
+        main.wait_event(self.in_ready[k])
+        _lib.check(dev.lib.ae_pack_cells_range(self.stage_in[k].data_ptr(), count, cells, dev.Zp, dev.G,
+                                               rows.data_ptr() + 8 * s0, dev.stream))
+        self.in_free[k].record(main)
+        if dev.comm is not None:
+            _lib.check(dev.lib.ae_comm_gather_rows(dev.comm.handle, rows.data_ptr(), dev.G, dev.Zp, dev.stream))
+
+    def drain(self, i, rows, shard_host):
+        """Unpack this rank's cell range of `rows` [G][Zp] (current stream) and start its D2H copy."""
+        dev, k = self.dev, i & 1
+        torch = dev.torch
+        main = torch.cuda.current_stream(dev.dev)
+        _, count, s0, cells = dev.cell_range()
+        if self.out_used[k]:
+            main.wait_event(self.out_free[k])                       # the download of step i-2 has left this slot
+        _lib.check(dev.lib.ae_unpack_cells_range(rows.data_ptr() + 8 * s0, count, cells, dev.Zp, dev.G,
+                                                 self.stage_out[k].data_ptr(), dev.stream))
+        self.out_ready[k].record(main)
+        with torch.cuda.stream(self.copy_out):
+            self.copy_out.wait_event(self.out_ready[k])
+            shard_host.view(-1).copy_(self.stage_out[k][:shard_host.numel()], non_blocking=True)
+            self.out_free[k].record(self.copy_out)
+        self.out_used[k] = True
+
+    def join(self):
+        """Make the current stream wait for every copy issued so far (for device-side timing)."""
+        main = self.dev.torch.cuda.current_stream(self.dev.dev)
+        main.wait_stream(self.copy_in)
+        main.wait_stream(self.copy_out)
+
+    def wait(self):
+        self.copy_in.synchronize()
+        self.copy_out.synchronize()
+
+
 class SlabDevice:
     """One (slab, cross-sections, dt) problem resident in HBM.
 

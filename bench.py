@@ -150,7 +150,7 @@ def main():
     import torch
     import torch.distributed as dist
     from alpha_eigen_b200 import _lib, distributed
-    from alpha_eigen_b200.device import SlabDevice, shard_angles
+    from alpha_eigen_b200.device import HostPipe, SlabDevice, shard_angles
     from alpha_eigen_b200.synthetic import synthetic_problem
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -239,20 +239,38 @@ def main():
     z0, zcount, _, _ = dev.cell_range()
     q_host = torch.rand(max(zcount, 1), G, dtype=torch.float64)[:zcount].pin_memory()
     phi_host = torch.empty(zcount, G, dtype=torch.float64).pin_memory()
-    e_steps = max(2, min(args.steps, 5))
+    e_steps = max(3, min(args.steps, 8))
 
-    def e2e_step(i):
-        dev.shard_to_device(q_host, q[i & 1])                           # H2D + pack (+ all-gather of the ranges)
-        step(i)
-        dev.shard_to_host(dev.phi, phi_host)                            # unpack + D2H (+ sync)
+    # Every step still uploads its own source and downloads its own flux; the copies run on the copy engines
+    # (HostPipe: two staging slots, own streams) so that the upload of step i+1 and the download of step i-1
+    # overlap the kernels of step i.  AE_BENCH_E2E_SERIAL=1 times the unpipelined sequence instead.
+    serial = os.environ.get("AE_BENCH_E2E_SERIAL") == "1"
+    pipe = HostPipe(dev)
 
-    e2e_step(0)
+    def e2e_run(n):
+        if serial:
+            for i in range(n):
+                dev.shard_to_device(q_host, q[i & 1])                   # H2D + pack (+ all-gather of the ranges)
+                step(i)
+                dev.shard_to_host(dev.phi, phi_host)                    # unpack + D2H (+ sync)
+            return
+        pipe.upload(0, q_host)
+        for i in range(n):
+            pipe.feed(i, q[i & 1])                                      # pack (+ all-gather of the ranges)
+            if i + 1 < n:
+                pipe.upload(i + 1, q_host)                              # H2D of the next source, behind the sweep
+            step(i)
+            pipe.drain(i, dev.phi, phi_host)                            # unpack, D2H behind the next sweep
+        pipe.join()                                                     # the last flux has reached the host
+
+    e2e_run(2)
     fence()
+    pipe.wait()
     t_beg.record()
-    for i in range(e_steps):
-        e2e_step(i)
+    e2e_run(e_steps)
     t_end.record()
     fence()
+    pipe.wait()
     e_ms = t_beg.elapsed_time(t_end) / e_steps
     if world > 1:
         t = torch.tensor([e_ms], dtype=torch.float64, device=dev.dev)
@@ -284,8 +302,11 @@ def main():
                              "flux_update_and_allgather": phase[2]},
             "e2e": {"value": updates_per_step / (e_ms * 1e-3), "unit": "updates/s", "ms_per_step": e_ms,
                     "h2d_bytes_per_step": Z * G * 8, "d2h_bytes_per_step": Z * G * 8,
-                    "what": "whole-job bytes; every rank copies the source of its own 1/N cell range from pinned host memory "
-                            "(all-gathered on the device), runs the step on resident psi, and reads its range of the flux back"},
+                    "steps": e_steps, "pipelined": not serial,
+                    "what": "whole-job bytes; every step every rank copies the source of its own 1/N cell range from pinned "
+                            "host memory (all-gathered on the device), runs the step on resident psi, and reads its range of "
+                            "the flux back to pinned host memory; copies run on their own streams, double-buffered, so the "
+                            "upload of step i+1 and the download of step i-1 overlap the kernels of step i"},
             "gpu_launches": gpu_launches, "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -63,6 +63,29 @@ def test_cli_matches_reference_flags():
     assert "alphas =" in out.stdout
 
 
+def test_cli_extras_subcritical_variant_and_output(tmp_path):
+    """--nu_sigmaf / --dt / --output: the sub-critical K-P slab of the report's Table 1
+    (nu*Sigma_f = 0.3, k = 0.4243 on a fine mesh) through the CLI, against the oracle on the same mesh."""
+    from oracle import ae_oracle as orc
+    from tests.kp import kp_problem
+    out_file = str(tmp_path / "flux.npz")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), "--problem", "kornreich-parsons-symmetric",
+                          "--cells_per_mfp", "50", "--num_angles", "16", "--nu_sigmaf", "0.3", "--output", out_file],
+                         capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert out.returncode == 0, out.stderr
+    p = kp_problem(9, 50, 16, nusf_fuel=0.3)
+    ro = orc.power_iteration(p["mu"], p["weight"], p["hx"], p["tables"], p["phi0"])
+    got = np.load(out_file)
+    assert abs(float(got["k"]) - ro["k_new"]) < 1e-9 and abs(float(got["k"]) - 0.4243178) < 1e-3     # report: fine mesh
+    assert _rel(got["phi"], ro["phi_new"]) < 1e-10 and got["midpoints"].shape == (450,)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), "--problem", "kornreich-parsons-symmetric",
+                          "--cells_per_mfp", "10", "--num_angles", "4", "--steps", "20", "--dt", "0.05", "--nu_sigmaf", "0.3",
+                          "--output", out_file], capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert out.returncode == 0, out.stderr
+    got = np.load(out_file)
+    assert float(got["dt"]) == 0.05 and got["phi_steps"].shape == (90, 1, 20) and np.all(np.real(got["alphas"]) < 0)
+
+
 def test_sweep1D_honours_explicit_sigT_in_both_directions():
     """Repair R5: the reference ignores sigT for mu < 0 (group.py:56); the oracle and the device do not."""
     from oracle import ae_oracle as orc
@@ -302,6 +325,34 @@ def test_multi_region_slab_generic_zone_path():
     ro = orc.power_iteration(s.mu, s.weight, s.hx, tab, phi0)
     assert ro["status"] == 0 and abs(k.new - ro["k_new"]) < 1e-9
     assert _rel(mg.phi.new, ro["phi_new"]) < 1e-10
+
+
+def test_host_pipe_overlapped_io_roundtrip():
+    """HostPipe: double-buffered upload / pack and unpack / download on side streams; five steps with distinct
+    sources, each result must be the source of its own step (slot reuse is ordered by events)."""
+    import torch
+    from alpha_eigen_b200.device import HostPipe, SlabDevice
+    Z, A, G = 3000, 4, 6
+    mu, w = np.polynomial.legendre.leggauss(A)
+    one = np.ones((1, G))
+    dev = SlabDevice(Z, 1.0, mu, w, np.zeros(Z, dtype=np.int64), one, np.zeros((1, G, G)), one, one, one)
+    pipe = HostPipe(dev)
+    n = 5
+    src = [torch.rand(Z, G, dtype=torch.float64).pin_memory() for _ in range(n)]
+    out = [torch.zeros(Z, G, dtype=torch.float64).pin_memory() for _ in range(n)]
+    rows = [torch.zeros(G * dev.Zp, dtype=torch.float64, device=dev.dev) for _ in range(2)]
+    pipe.upload(0, src[0])
+    for i in range(n):
+        pipe.feed(i, rows[i & 1])
+        if i + 1 < n:
+            pipe.upload(i + 1, src[i + 1])
+        rows[i & 1].mul_(2.0)                                       # the "step"
+        pipe.drain(i, rows[i & 1], out[i])
+    pipe.join()
+    torch.cuda.current_stream().synchronize()
+    pipe.wait()
+    for i in range(n):
+        np.testing.assert_array_equal(out[i].numpy(), 2.0 * src[i].numpy())
 
 
 def test_real_70_group_data_through_the_public_classes():
