@@ -118,85 +118,114 @@ __global__ void atilde_kernel(const double *__restrict__ gram, int n /*K+1*/, co
 // Householder QR of the tall matrix T = S^T (len x n) is backward stable, and only its n x n
 // triangular factor is needed (Q is never formed).
 //
-// Each CTA keeps a working matrix W[(n + B)][ldw] in shared memory: rows 0..n-1 hold the running
-// R, rows n.. hold the next block of B rows of T.  One "append" runs n Householder steps; step k
-// only touches row k of R and the B block rows (the rest of column k is already zero).  Thread j
-// owns column j: the reflector entries are warp-uniform smem broadcasts, the column entries are
-// stride-1 across threads, ldw is odd so column walks are conflict-free.
-__global__ void __launch_bounds__(128) tsqr_kernel(const double *__restrict__ in, int64_t ld, int64_t len, int n,
-                                                   int row_major, int64_t rows_per_cta, int B, double *__restrict__ r_out)
+// Each CTA keeps the running triangle R[n][ldw] in shared memory and the current block of kTsqrB rows of T in
+// REGISTERS: 512 threads = 128 column slots x 4 row parts, thread (j, part) holds rows 4b + part (b = 0..23) of
+// column j.  One "append" runs n Householder steps; step k only touches row k of R and the block rows (the rest
+// of column k is already zero):
+//   the four threads of column k publish the reflector x (their 96 block entries) in a small shared buffer, sum
+//   its square and derive (tau, 1/(alpha - beta), beta) exactly as LAPACK's dlarfg does;   -- one barrier --
+//   every thread of a column j > k forms its part of x.A[:,j] from registers, the four parts meet with two
+//   shuffles, row k of R and the 24 register rows are updated.
+// The reflector buffer is double buffered by the parity of k, so one barrier per step suffices.  (The first
+// version kept the block in shared memory with one thread per column: every step streamed the whole trailing block
+// through shared memory twice, 4.3 us per step at 4 warps per SM; this one takes ~0.5 us.)
+constexpr int kTsqrParts = 4, kTsqrRegRows = 24, kTsqrB = kTsqrParts * kTsqrRegRows;    // 96 rows per block
+constexpr int kTsqrThreads = kGN * kTsqrParts;                                          // 512
+static_assert(kGN == 128 && kTsqrThreads == 512, "thread layout assumes 128 column slots");
+
+template <bool ROW_MAJOR>
+__global__ void __launch_bounds__(kTsqrThreads, 1) tsqr_kernel(const double *__restrict__ in, int64_t ld, int64_t len, int n,
+                                                               int64_t rows_per_cta, double *__restrict__ r_out)
 {
-    extern __shared__ double W[];
-    __shared__ double hh[4];                        // tau, 1/(alpha-beta), beta
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ double R[];                   // [n][ldw], then x[2][kTsqrB], then hh[2][4]
     const int ldw = n | 1;
+    double *xbuf = R + n * ldw;
+    double *hbuf = xbuf + 2 * kTsqrB;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int part = lane & 3, j = (tid >> 5) * 8 + (lane >> 2);       // the 4 parts of a column are adjacent lanes
+    const unsigned quad = 0xFu << (lane & ~3);
     const int64_t m_begin = (int64_t)blockIdx.x * rows_per_cta;
     const int64_t m_end = min(len, m_begin + rows_per_cta);
-    for (int i = tid; i < n * ldw; i += blockDim.x) W[i] = 0.0;
-    for (int64_t m0 = m_begin; m0 < m_end; m0 += B) {
-        __syncthreads();
-        // load block rows: T[m0+b][i]
-        if (row_major) {
-            for (int idx = tid; idx < B * n; idx += blockDim.x) {
-                const int b = idx / n, i = idx % n;
-                const int64_t m = m0 + b;
-                W[(n + b) * ldw + i] = m < m_end ? in[m * ld + i] : 0.0;
-            }
-        } else {
-            for (int idx = tid; idx < B * n; idx += blockDim.x) {
-                const int i = idx / B, b = idx % B;
-                const int64_t m = m0 + b;
-                W[(n + b) * ldw + i] = m < m_end ? in[(int64_t)i * ld + m] : 0.0;
-            }
+    for (int i = tid; i < n * ldw; i += blockDim.x) R[i] = 0.0;
+    for (int64_t m0 = m_begin; m0 < m_end; m0 += kTsqrB) {
+        double a[kTsqrRegRows];
+#pragma unroll
+        for (int b = 0; b < kTsqrRegRows; ++b) {
+            const int64_t m = m0 + 4 * b + part;
+            a[b] = (j < n && m < m_end) ? __ldg(ROW_MAJOR ? in + m * ld + j : in + (int64_t)j * ld + m) : 0.0;
         }
-        __syncthreads();
+        __syncthreads();                            // R zeroed / the previous block's last step is complete
         for (int k = 0; k < n; ++k) {
-            if (warp == 0) {                        // dlarfg on x = (W[k][k], W[n..n+B)[k])
-                double ss = 0.0;
-                for (int b = lane; b < B; b += 32) { const double x = W[(n + b) * ldw + k]; ss = fma(x, x, ss); }
-                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                if (lane == 0) {
-                    const double alpha = W[k * ldw + k];
+            double *x = xbuf + (k & 1) * kTsqrB, *hh = hbuf + (k & 1) * 4;
+            if (j == k) {                           // dlarfg on (R[k][k], block entries of column k)
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                for (int b = 0; b < kTsqrRegRows; b += 4) {
+                    s0 = fma(a[b], a[b], s0); s1 = fma(a[b + 1], a[b + 1], s1);
+                    s2 = fma(a[b + 2], a[b + 2], s2); s3 = fma(a[b + 3], a[b + 3], s3);
+                }
+#pragma unroll
+                for (int b = 0; b < kTsqrRegRows; ++b) x[4 * b + part] = a[b];
+                double ss = (s0 + s1) + (s2 + s3);
+                ss += __shfl_xor_sync(quad, ss, 1);
+                ss += __shfl_xor_sync(quad, ss, 2);
+                if (part == 0) {
+                    const double alpha = R[k * ldw + k];
                     if (ss == 0.0) {
-                        hh[0] = 0.0; hh[1] = 0.0; hh[2] = alpha;
+                        hh[0] = 0.0; hh[1] = 0.0;
                     } else {
                         const double beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
                         hh[0] = (beta - alpha) / beta;
                         hh[1] = 1.0 / (alpha - beta);
-                        hh[2] = beta;
+                        R[k * ldw + k] = beta;
                     }
                 }
             }
             __syncthreads();
             const double tau = hh[0], inv = hh[1];
-            const int j = tid;
-            if (j == k) W[k * ldw + k] = hh[2];
             if (j > k && j < n && tau != 0.0) {
-                double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;             // four chains: the FMA latency, not the LDS
-                int b = 0;                                                  // rate, bounds this loop
-                for (; b + 4 <= B; b += 4) {
-                    d0 = fma(W[(n + b) * ldw + k], W[(n + b) * ldw + j], d0);
-                    d1 = fma(W[(n + b + 1) * ldw + k], W[(n + b + 1) * ldw + j], d1);
-                    d2 = fma(W[(n + b + 2) * ldw + k], W[(n + b + 2) * ldw + j], d2);
-                    d3 = fma(W[(n + b + 3) * ldw + k], W[(n + b + 3) * ldw + j], d3);
+                double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll
+                for (int b = 0; b < kTsqrRegRows; b += 4) {
+                    d0 = fma(x[4 * b + part], a[b], d0); d1 = fma(x[4 * b + 4 + part], a[b + 1], d1);
+                    d2 = fma(x[4 * b + 8 + part], a[b + 2], d2); d3 = fma(x[4 * b + 12 + part], a[b + 3], d3);
                 }
-                for (; b < B; ++b) d0 = fma(W[(n + b) * ldw + k], W[(n + b) * ldw + j], d0);
-                const double dot = (d0 + d1) + (d2 + d3);
-                const double w = tau * fma(inv, dot, W[k * ldw + j]);
-                W[k * ldw + j] -= w;
+                double dot = (d0 + d1) + (d2 + d3);
+                dot += __shfl_xor_sync(quad, dot, 1);
+                dot += __shfl_xor_sync(quad, dot, 2);
+                const double rkj = R[k * ldw + j];
+                const double w = tau * fma(inv, dot, rkj);
                 const double wi = w * inv;
-#pragma unroll 4
-                for (int b2 = 0; b2 < B; ++b2) W[(n + b2) * ldw + j] = fma(-wi, W[(n + b2) * ldw + k], W[(n + b2) * ldw + j]);
+                __syncwarp(quad);                   // all four parts have read R[k][j]
+                if (part == 0) R[k * ldw + j] = rkj - w;
+#pragma unroll
+                for (int b = 0; b < kTsqrRegRows; ++b) a[b] = fma(-wi, x[4 * b + part], a[b]);
             }
-            __syncthreads();
         }
     }
     __syncthreads();
     double *out = r_out + (size_t)blockIdx.x * n * n;
     for (int idx = tid; idx < n * n; idx += blockDim.x) {
-        const int i = idx / n, j = idx % n;
-        out[idx] = j >= i ? W[i * ldw + j] : 0.0;
+        const int i = idx / n, jj = idx % n;
+        out[idx] = jj >= i ? R[i * ldw + jj] : 0.0;
     }
+}
+
+static size_t tsqr_smem(int n) { return ((size_t)n * (n | 1) + 2 * kTsqrB + 8) * sizeof(double); }
+
+static int tsqr_launch(const double *in, int64_t ld, int64_t len, int n, bool row_major, int64_t rows_per_cta, int ctas,
+                       double *r_out, cudaStream_t st)
+{
+    const size_t smem = tsqr_smem(n);
+    if (row_major) {
+        AE_CUDA(cudaFuncSetAttribute((const void *)tsqr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tsqr_kernel<true><<<ctas, kTsqrThreads, smem, st>>>(in, ld, len, n, rows_per_cta, r_out);
+    } else {
+        AE_CUDA(cudaFuncSetAttribute((const void *)tsqr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tsqr_kernel<false><<<ctas, kTsqrThreads, smem, st>>>(in, ld, len, n, rows_per_cta, r_out);
+    }
+    AE_CUDA(cudaGetLastError());
+    return AE_OK;
 }
 
 // column-major copies for cuSOLVER: Ax = R[:, 0:K]  ((K+1) x K), Ry = R[:, 1:K+1]
@@ -387,62 +416,47 @@ done:
     return status;
 }
 
-static int tsqr_block_rows(int n)
+// Triangles are merged by a tree of further QRs (stacked triangles are just another tall matrix, row-major);
+// fan-in 6 keeps every CTA of a level at ~7 blocks of rows.
+constexpr int kTsqrFanIn = 6;
+
+static int tsqr_merge_tree(double *in, double *scratch, int count, int n, double *r_out, cudaStream_t st)
 {
-    const int ldw = n | 1;
-    int B = (int)((200 * 1024) / (sizeof(double) * ldw)) - n;
-    if (B > 96) B = 96;
-    return B;
+    while (count > 1) {
+        const int next = count <= kTsqrFanIn + 2 ? 1 : (count + kTsqrFanIn - 1) / kTsqrFanIn;
+        const int per = (count + next - 1) / next;
+        double *dst = next == 1 ? r_out : scratch;
+        AE_TRY(tsqr_launch(in, n, (int64_t)count * n, n, true, (int64_t)per * n, next, dst, st));
+        count = next;
+        double *t = in; in = scratch; scratch = t;
+    }
+    return AE_OK;
 }
 
 extern "C" int ae_tsqr(const double *snap, int64_t ld, int64_t len, int32_t n, double *r_out, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (!snap || !r_out || n < 1 || n > kGN || len < 1) { set_error("ae_tsqr: bad argument (n=%d)", n); return AE_BAD_ARG; }
-    const int B = tsqr_block_rows(n);
-    if (B < 8) { set_error("ae_tsqr: n=%d too large for shared memory", n); return AE_BAD_ARG; }
-    const int ldw = n | 1;
-    const size_t smem = (size_t)(n + B) * ldw * sizeof(double);
-    AE_CUDA(cudaFuncSetAttribute((const void *)tsqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int ncta = 148;
+    int dev = 0, ncta = 148;
+    AE_CUDA(cudaGetDevice(&dev));
+    AE_CUDA(cudaDeviceGetAttribute(&ncta, cudaDevAttrMultiProcessorCount, dev));
     int64_t rows = (len + ncta - 1) / ncta;
-    rows = (rows + B - 1) / B * B;
+    rows = (rows + kTsqrB - 1) / kTsqrB * kTsqrB;
     ncta = (int)((len + rows - 1) / rows);
-    double *parts = nullptr, *parts2 = nullptr;
-    AE_CUDA(cudaMallocAsync((void **)&parts, (size_t)ncta * n * n * sizeof(double), st));
-    AE_CUDA(cudaMallocAsync((void **)&parts2, (size_t)((ncta + 11) / 12) * n * n * sizeof(double), st));
-    tsqr_kernel<<<ncta, 128, smem, st>>>(snap, ld, len, n, 0, rows, B, parts);
-    // merge tree: QR of stacked triangles (row-major), 12 per CTA and level, so no CTA ever chews on more
-    // than ~15 blocks (one CTA merging all 148 triangles was 60 % of the run time on small problems)
-    int count = ncta;
-    double *in = parts, *out = parts2;
-    while (count > 1) {
-        const int next = count <= 16 ? 1 : (count + 11) / 12;
-        const int per = (count + next - 1) / next;
-        double *dst = next == 1 ? r_out : out;
-        tsqr_kernel<<<next, 128, smem, st>>>(in, n, (int64_t)count * n, n, 1, (int64_t)per * n, B, dst);
-        count = next;
-        double *t = in; in = out; out = t;
-    }
-    if (ncta == 1) AE_CUDA(cudaMemcpyAsync(r_out, parts, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    cudaError_t e = cudaGetLastError();
+    double *parts = nullptr;
+    const size_t tri = (size_t)n * n;
+    AE_CUDA(cudaMallocAsync((void **)&parts, ((size_t)ncta + (ncta + kTsqrFanIn - 1) / kTsqrFanIn) * tri * sizeof(double), st));
+    int status = tsqr_launch(snap, ld, len, n, false, rows, ncta, ncta == 1 ? r_out : parts, st);
+    if (status == AE_OK) status = tsqr_merge_tree(parts, parts + (size_t)ncta * tri, ncta, n, r_out, st);
     cudaFreeAsync(parts, st);
-    cudaFreeAsync(parts2, st);
-    AE_CUDA(e);
-    return AE_OK;
+    return status;
 }
 
 extern "C" int ae_tsqr_merge(const double *r_stack, int32_t count, int32_t n, double *r_out, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (!r_stack || !r_out || count < 1 || n < 1 || n > kGN) { set_error("ae_tsqr_merge: bad argument"); return AE_BAD_ARG; }
-    const int B = tsqr_block_rows(n);
-    const int ldw = n | 1;
-    const size_t smem = (size_t)(n + B) * ldw * sizeof(double);
-    AE_CUDA(cudaFuncSetAttribute((const void *)tsqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tsqr_kernel<<<1, 128, smem, st>>>(r_stack, n, (int64_t)count * n, n, 1, (int64_t)count * n, B, r_out);
-    AE_CUDA(cudaGetLastError());
-    return AE_OK;
+    return tsqr_launch(r_stack, n, (int64_t)count * n, n, true, (int64_t)count * n, 1, r_out, st);
 }
 
 extern "C" int ae_dmd_from_r(const double *r_dev, int32_t K, double dt, double rank_tol, double *alpha_re,

@@ -61,19 +61,35 @@ struct EnsResult {
     double change, outer_change;
 };
 
+__device__ __forceinline__ unsigned atom_add_acq_rel(unsigned *p, unsigned v)
+{
+    unsigned old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Arrival is ONE acq_rel atomic (it publishes this CTA's writes -- bar.sync made them thread 0's -- and, for the last
+// arriver, acquires everybody else's); waiters poll with RELAXED loads and fence once when the generation has
+// moved.  Polling with ld.acquire costs an L1 invalidation (CCTL.IVALL) per poll -- 570 per wait in the first
+// version, which also emptied the L1 of the other teams' CTAs on the SM -- and made a barrier 4-5 us.
 __device__ __forceinline__ void team_barrier(TeamBar *bar, unsigned &gen, int nblocks)
 {
     ++gen;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(&bar->count, 1u) == (unsigned)nblocks - 1) {
+        if (atom_add_acq_rel(&bar->count, 1u) == (unsigned)nblocks - 1) {
             bar->count = 0;                             // everybody has arrived; nobody re-arrives before gen moves
             st_release(&bar->gen, gen);
         } else {
-            while (ld_acquire(&bar->gen) != gen) __nanosleep(20);
+            while (ld_relaxed(&bar->gen) != gen) __nanosleep(32);
+            __threadfence();                            // acquire side of the release store above
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -130,6 +146,10 @@ struct Small {
         for (int64_t ti = 0; ti < nt; ++ti) {
             const int64_t off = (neg ? nt - 1 - ti : ti) * kTile;
             double ca[kL], cb[kL], f[kL];
+            if (ti + 1 < nt) {                          // next tile of the row: L2 -> L1 while this one is solved
+                const int64_t nxt = (neg ? nt - 2 - ti : ti + 1) * kTile;
+                tile_prefetch<RD>(p.hs + goff + nxt, qc + nxt, RD ? p.cdt + goff + nxt : nullptr, RD ? psi_in + prow + nxt : nullptr);
+            }
             tile_maps<RD>(p.hs + goff + off, qc + off, RD ? p.cdt + goff + off : nullptr, RD ? psi_in + prow + off : nullptr, m,
                           two_m, ca, cb);
             if (neg) tile_solve<true>(ca, cb, carry, f, lane);
@@ -161,7 +181,7 @@ struct Small {
     }
 
     // Flux update over the cells owned by this thread; it == 0 is the cold start (group.py:66 / time_unit.py:45).
-    // Groups are handled four at a time: the loads of a chunk are issued together and only then consumed (every
+    // Groups are handled kU at a time: the loads of a chunk are issued together and only then consumed (every
     // operand sits in L2, ~1 us away, and one group after the other would expose that latency G times); sums
     // keep the reference's order (partials in block order, norms in group order, scatter over g' ascending).
     __device__ void flux_update(int it, double cold, double *const (&q)[2], double *const (&phi)[2], double &num, double &den)
@@ -170,7 +190,7 @@ struct Small {
         double *phi_out = phi[it & 1], *q_next = q[it & 1];
         num = 0.0; den = 0.0;
         constexpr int kLocalG = 16;                     // a cell's fluxes stay in registers / L1-resident local memory
-        constexpr int kU = 4;
+        constexpr int kU = 16;                          // groups in flight together (all of them up to G = 16)
         const int G = p.G;
         for (int64_t s = gtid; s < p.Zp; s += gthreads) {
             const bool valid = logical_cell(s) < p.Z;
@@ -518,9 +538,11 @@ extern "C" int ae_ensemble_time_march(const ae_member *members, int32_t count, i
         p.outer_hist = mem.hist; p.inner_hist = mem.hist + num_steps; p.num_steps = num_steps;
         AE_CUDA(cudaMemsetAsync(mem.hist, 0, sizeof(int32_t) * 2 * (size_t)num_steps, st));
     }
-    // 8-warp CTAs: 2 (128 registers), 3 (80) or 4 (64, some spills) CTAs per SM; AE_ENSEMBLE_CTAS_PER_SM overrides
+    // 8-warp CTAs: 2 (128 registers), 3 (80, spills) or 4 (64, more spills) CTAs per SM; measured equal within 5 % on
+    // the 12-group ensemble (profiles/r01_c5_ensemble.jsonl), so the spill-free build is the default;
+    // AE_ENSEMBLE_CTAS_PER_SM overrides
     static const char *force = getenv("AE_ENSEMBLE_CTAS_PER_SM");
-    const int minb = force && atoi(force) >= 2 && atoi(force) <= 4 ? atoi(force) : 3;
+    const int minb = force && atoi(force) >= 2 && atoi(force) <= 4 ? atoi(force) : 2;
     const void *kernel = ac0 == 16 ? (const void *)ensemble_time_march_kernel<16, 1>
                          : minb == 2 ? (const void *)ensemble_time_march_kernel<8, 2>
                          : minb == 3 ? (const void *)ensemble_time_march_kernel<8, 3>

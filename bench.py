@@ -282,8 +282,9 @@ def main():
         bytes_per_update = 16.0 + 24.0 / dev.A + 8.0 * dev.P / dev.A    # psi r+w, hs/q/cdt over angles, partial
         alg_bytes = bytes_per_update * local_updates
         achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch (profiles/r01_c4_kernel_dram_bytes_v5.csv)
-        traffic = 322.4e9 if (args.workload == "c4" and world == 1 and not args.cells) else None
+        # dram__bytes_read.sum + dram__bytes_write.sum of one sweep launch (profiles/r01_c4_sweep_dram_bytes_v6_gangs.csv:
+        # 152.7 + 152.3 GB; 170.1 + 152.3 GB before the gang order, profiles/r01_c4_kernel_dram_bytes_v5.csv)
+        traffic = 305.0e9 if (args.workload == "c4" and world == 1 and not args.cells) else None
         line = {
             "metric": "sweep cell*angle*group updates/s", "value": value, "unit": "updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
