@@ -29,6 +29,13 @@
 
 namespace cg = cooperative_groups;
 
+// Groups of a cell whose loads are in flight together in the flux update.  Measured on the 12-group ensemble march
+// (72 members, one B200): 4 -> 1.31 s, 8 -> 2.73 s, 16 -> 1.73 s (wider chunks spill and waste predicated work); an
+// L1 prefetch of the next tile during the sweeps cost another 9 %, so the tiles are simply loaded when needed.
+#ifndef AE_SMALL_KU
+#define AE_SMALL_KU 4
+#endif
+
 namespace ae {
 
 struct SmallArgs {
@@ -77,7 +84,7 @@ __device__ __forceinline__ unsigned ld_relaxed(const unsigned *p)
 // Arrival is ONE acq_rel atomic (it publishes this CTA's writes -- bar.sync made them thread 0's -- and, for the last
 // arriver, acquires everybody else's); waiters poll with RELAXED loads and fence once when the generation has
 // moved.  Polling with ld.acquire costs an L1 invalidation (CCTL.IVALL) per poll -- 570 per wait in the first
-// version, which also emptied the L1 of the other teams' CTAs on the SM -- and made a barrier 4-5 us.
+// version, which also emptied the L1 of the other teams' CTAs on the SM (march 7 % slower).
 __device__ __forceinline__ void team_barrier(TeamBar *bar, unsigned &gen, int nblocks)
 {
     ++gen;
@@ -146,10 +153,6 @@ struct Small {
         for (int64_t ti = 0; ti < nt; ++ti) {
             const int64_t off = (neg ? nt - 1 - ti : ti) * kTile;
             double ca[kL], cb[kL], f[kL];
-            if (ti + 1 < nt) {                          // next tile of the row: L2 -> L1 while this one is solved
-                const int64_t nxt = (neg ? nt - 2 - ti : ti + 1) * kTile;
-                tile_prefetch<RD>(p.hs + goff + nxt, qc + nxt, RD ? p.cdt + goff + nxt : nullptr, RD ? psi_in + prow + nxt : nullptr);
-            }
             tile_maps<RD>(p.hs + goff + off, qc + off, RD ? p.cdt + goff + off : nullptr, RD ? psi_in + prow + off : nullptr, m,
                           two_m, ca, cb);
             if (neg) tile_solve<true>(ca, cb, carry, f, lane);
@@ -190,7 +193,7 @@ struct Small {
         double *phi_out = phi[it & 1], *q_next = q[it & 1];
         num = 0.0; den = 0.0;
         constexpr int kLocalG = 16;                     // a cell's fluxes stay in registers / L1-resident local memory
-        constexpr int kU = 16;                          // groups in flight together (all of them up to G = 16)
+        constexpr int kU = AE_SMALL_KU;                 // groups in flight together
         const int G = p.G;
         for (int64_t s = gtid; s < p.Zp; s += gthreads) {
             const bool valid = logical_cell(s) < p.Z;
