@@ -34,6 +34,10 @@
 #include "ae_common.cuh"
 #include "ae_tile.cuh"
 
+#ifndef AE_SWEEP_REDUCERS
+#define AE_SWEEP_REDUCERS 2      // reducer warps of the 16-angle CTA (1, 2 or 4)
+#endif
+
 namespace ae {
 
 constexpr int kACsmall = 8, kACbig = 16; // compute warps (angles) per CTA: small / many-angle problems
@@ -165,9 +169,19 @@ __host__ __device__ __forceinline__ int unit_row(const SweepArgs &p, int u, int 
     return g * p.nbg + dir * p.nb_neg + sub * p.gs + mb;
 }
 
-template <int AC> struct StageCfg { static constexpr int stages = AC == kACbig ? 4 : 3; };
+template <int AC> struct StageCfg {
+    static constexpr int stages = AC == kACbig ? 4 : 3;
+    // Reducer warps, each summing its share of a tile's cells.  With one reducer the compute warps of the 16-angle
+    // CTA spent 21 % of their samples waiting for the reduction array to be recycled (ncu, C3); a second one
+    // halves that latency and still fits the register file (19 warps x 96 registers).  Measured (sweep kernel, ms,
+    // profiles/r01_sweep_reducer_warps_ab.log): C3 1.414 / 1.284 / 1.228 and C4 62.0 / 54.3 / 56.8 with 1 / 2 / 4
+    // reducers -- C4 runs at the board's power cap, where the extra warps of the 4-reducer build cost more than
+    // they hide.  Two 8-angle CTAs per SM have no room for another warp.
+    static constexpr int reducers = AC == kACbig ? AE_SWEEP_REDUCERS : 1;
+    static constexpr int threads = (AC + reducers + 1) * 32;
+};
 
-// Warp-specialised persistent kernel: AC compute warps + reducer warp + producer warp.
+// Warp-specialised persistent kernel: AC compute warps + reducer warp(s) + producer warp.
 // Compute warp w owns one angle of the current row block and meets no CTA-wide barrier inside the tile
 // loop; the producer warp feeds the TMA ring; the reducer warp folds the per-warp weighted fluxes into
 // the partial scalar flux.  Hand-shakes are mbarriers:
@@ -176,9 +190,10 @@ template <int AC> struct StageCfg { static constexpr int stages = AC == kACbig ?
 //   red_full[b]  compute -> reducer    all AC warps have written their flux contribution into red[b]
 //   red_empty[b] reducer -> compute    red[b] has been summed and may be overwritten
 template <int AC, bool READ_PSI, bool WRITE_PSI>
-__global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_kernel(const SweepArgs p, const ae_ctrl *ctrl, int gate)
+__global__ void __launch_bounds__(StageCfg<AC>::threads, AC == kACsmall ? 2 : 1) sweep_kernel(const SweepArgs p, const ae_ctrl *ctrl, int gate)
 {
     constexpr int kStages = StageCfg<AC>::stages;
+    constexpr int kRed = StageCfg<AC>::reducers, kPerRed = 4 / kRed;   // a reducer sums kPerRed of the 4 double2 columns
     constexpr int kSlots = (READ_PSI ? 3 + AC : 2);             // 2 KB slots per stage
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *ring = reinterpret_cast<double *>(smem_raw);                    // [kStages][kSlots][kTile]
@@ -195,7 +210,7 @@ __global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_k
     if (tid == 0) {
         s_cta = (int)atomicInc(&sy->ticket, gridDim.x - 1);                // logical id in START order; self-resetting
         for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, AC); }
-        for (int b = 0; b < 2; ++b) { mbar_init(red_full + b, AC); mbar_init(red_empty + b, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(red_full + b, AC); mbar_init(red_empty + b, kRed); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -211,7 +226,7 @@ __global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_k
     RowCtx c;
     int c_rb = -1;
 
-    if (warp == AC + 1) {
+    if (warp == AC + kRed) {
         // ================= producer warp: TMA ring =====================================================
         const uint64_t pol = l2_policy(p.l2_hints ? (lane < 3 ? 2 : 1) : 0);   // lanes 0-2 fetch hs/q/cdt, the rest psi
         for (int64_t j = 0; j < W; ++j, cur.advance()) {
@@ -230,8 +245,9 @@ __global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_k
                 bulk_g2s(dst + lane * kTile, src, kTileBytes, full + st, pol);
             }
         }
-    } else if (warp == AC) {
-        // ================= reducer warp: partial scalar flux of the block ==============================
+    } else if (warp >= AC) {
+        // ================= reducer warp(s): partial scalar flux of the block ===========================
+        const int k0 = (warp - AC) * kPerRed;                               // this warp's double2 columns of a tile
         double hwv[AC];                                                     // half quadrature weights of the block's angles
         for (int64_t j = 0; j < W; ++j, cur.advance()) {
             if (cur.rb != c_rb) {
@@ -246,18 +262,18 @@ __global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_k
             const int b = (int)(j & 1);
             const double *rb_ = red + b * (AC * kTile) + lane * 2;
             mbar_wait(red_full + b, (uint32_t)((j >> 1) & 1));
-            double2 acc[4];
+            double2 acc[kPerRed];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const double2 v = *reinterpret_cast<const double2 *>(rb_ + k * 64);
+            for (int k = 0; k < kPerRed; ++k) {
+                const double2 v = *reinterpret_cast<const double2 *>(rb_ + (k0 + k) * 64);
                 acc[k] = make_double2(hwv[0] * v.x, hwv[0] * v.y);
             }
 #pragma unroll
             for (int w = 1; w < AC; ++w)                                    // warps = angles in order (group.py:77)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < kPerRed; ++k) {
                     if (w >= c.nblk) continue;          // idle warps of a ragged block worked on stale data (may be NaN)
-                    const double2 v = *reinterpret_cast<const double2 *>(rb_ + w * kTile + k * 64);
+                    const double2 v = *reinterpret_cast<const double2 *>(rb_ + w * kTile + (k0 + k) * 64);
                     acc[k].x = fma(hwv[w], v.x, acc[k].x);                  // 0.5*w_a*(in+out) = w_a*psi_mid
                     acc[k].y = fma(hwv[w], v.y, acc[k].y);
                 }
@@ -265,7 +281,7 @@ __global__ void __launch_bounds__((AC + 2) * 32, AC == kACsmall ? 2 : 1) sweep_k
             if (lane == 0) mbar_arrive(red_empty + b);
             double *dst = p.partial + c.poff + off + lane * 2;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) *reinterpret_cast<double2 *>(dst + k * 64) = acc[k];
+            for (int k = 0; k < kPerRed; ++k) *reinterpret_cast<double2 *>(dst + (k0 + k) * 64) = acc[k];
         }
     } else {
         // ================= compute warps ==============================================================
@@ -410,7 +426,7 @@ static int launch_variant(const SweepArgs &p_in, const ae_ctrl *ctrl, int gate, 
 {
     SweepArgs p = p_in;
     constexpr int slots = RD ? 3 + AC : 2;
-    constexpr int threads = (AC + 2) * 32;
+    constexpr int threads = StageCfg<AC>::threads;
     const size_t smem = (size_t)(StageCfg<AC>::stages * slots + 2 * AC) * kTileBytes + (2 * StageCfg<AC>::stages + 4) * sizeof(uint64_t);
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
