@@ -31,7 +31,10 @@ namespace cg = cooperative_groups;
 
 // Groups of a cell whose loads are in flight together in the flux update.  Measured on the 12-group ensemble march
 // (72 members, one B200): 4 -> 1.31 s, 8 -> 2.73 s, 16 -> 1.73 s (wider chunks spill and waste predicated work); an
-// L1 prefetch of the next tile during the sweeps cost another 9 %, so the tiles are simply loaded when needed.
+// L1 prefetch of the next tile during the sweeps cost another 9 %, and a cp.async double-buffered shared-memory ring
+// for the tiles changed nothing on the one-group problems and cost 6 % on the ensemble
+// (profiles/r01_small_kernel_cp_async_staging_ab.log): tile-load latency is not what limits these sweeps, so the
+// tiles are simply loaded when needed.  (One-group problems would prefer a width of 1 by 5-10 %.)
 #ifndef AE_SMALL_KU
 #define AE_SMALL_KU 4
 #endif
