@@ -1,4 +1,6 @@
-"""Generate golden vectors by running the UNMODIFIED reference (/root/reference) in this container.
+"""Generate golden vectors by running the UNMODIFIED reference (/root/reference) in this container
+(the `march` mode drives the reference's own sweep and inner iteration under the documented minimal repairs of
+its broken time loop, applied from outside -- see the comment there).
 
 The reference cannot travel to the GPU box, so its outputs are committed as small .npz fixtures
 next to this script.  Run from the repo root:
@@ -73,6 +75,66 @@ elif mode == "sweep":
     np.savez_compressed(out, length=length, cells_per_mfp=cpm, num_angles=A, source=src, psi=psis,
              phi_si=g.phi.new, psi_si=psi_after, total_xs=g.total_xs, scatter_xs=g.scatter_xs,
              mu=slab.mu, weight=slab.weight, hx=slab.hx)
+elif mode == "march":
+    # Time march with the reference's OWN sweep1D (group.py:41-60) and time_dependent_source_iteration
+    # (time_unit.py:44-59), both unmodified, under the minimal repairs of SURVEY section 3.3 applied from outside:
+    #   R3  tu.phi becomes an ndarray SUBCLASS, so `self.phi.new = phi_old` (time_unit.py:59) sticks instead of raising;
+    #   R5  every zone gets a material shim whose total_xs is the time-augmented sigT of that zone, which is what the
+    #       negative-mu branch reads (group.py:56);
+    #   R2 / R4  the two outer loops that cannot work as written (time_unit.py:17-27 reads the psi slot it is about to
+    #       fill, :30-42 never updates phi) are driven here, line by line as the reference spells them, with the
+    #       previous step's psi and the inner solve's flux.
+    # psi0 = phi0 / 2 for every angle (DESIGN.md section 2), phi0 the seeded symmetric guess of phi.py:10-11.
+    length, cpm, A, steps = map(int, sys.argv[3:7])
+    dt = 0.1                                                            # inputs.py:39
+    slab, g = build(length, cpm, A)
+    Z = slab.num_zones
+    tu = TimeUnit(slab, g, steps, dt)
+    class PhiArray(np.ndarray): pass
+    tu.phi = tu.phi.view(PhiArray)                                      # R3
+    sigT = g.total_xs + 1 / dt * g.inv_speed                            # time_unit.py:24
+    class Shim: pass
+    for i in range(Z):                                                  # R5
+        m = Shim(); m.__dict__.update(g.zone[i].material.__dict__); m.total_xs = float(sigT[i, 0])
+        g.zone[i].material = m
+    phi0 = g.phi.new.copy()
+    psi_prev = np.repeat(0.5 * phi0[:, None, :], A, axis=1)             # (Z, A, 1)
+    for n in range(A):
+        tu.source[:, n] = g.source[:]                                   # time_unit.py:18-19 (zero: no power iteration ran)
+    outer_hist, inner_hist = [], []
+    calls = {"n": 0}
+    orig = OneGroup.sweep1D
+    def counted(self, angle, source, sigT=None):
+        calls["n"] += 1
+        return orig(self, angle, source, sigT)
+    OneGroup.sweep1D = counted
+    for step in range(steps):
+        source = tu.source.copy()
+        for n in range(A):
+            source[:, n, 0] = tu.source[:, n, 0] + psi_prev[:, n, 0] * g.inv_speed[:, 0] / dt     # :23 with R2
+        phi = np.zeros((Z, 1))                                          # :30
+        iteration, before = 0, calls["n"]
+        while True:
+            iteration += 1
+            assert iteration < 100
+            phi_old = phi.copy()                                        # :36
+            Q = source.copy()
+            for n in range(A):
+                Q[:, n, 0] += 0.5 * (g.chi[:, 0] * phi[:, 0] * g.nu_sigmaf[:, 0])                 # :38-39
+            tu.time_dependent_source_iteration(sigT, Q)                 # :40, unmodified reference code
+            phi = np.asarray(tu.phi.new).copy()                         # R4
+            change = np.linalg.norm(np.reshape(phi - phi_old, (Z, 1))) / np.linalg.norm(np.reshape(phi, (Z, 1)))   # :41
+            if change < 1e-10:
+                break
+        outer_hist.append(iteration)
+        inner_hist.append((calls["n"] - before) // A)
+        tu.phi[:, 0, step] = np.reshape(phi, Z)                         # :25
+        for n in range(A):
+            tu.psi[:, n, :, step] = g.angle[n].psi_midpoint             # :26-27
+        psi_prev = tu.psi[:, :, :, step].copy()
+    np.savez_compressed(out, length=length, cells_per_mfp=cpm, num_angles=A, steps=steps, dt=dt, phi0=phi0,
+             psi=np.asarray(tu.psi), phi=np.asarray(tu.phi), outer=np.array(outer_hist, dtype=np.int32),
+             inner=np.array(inner_hist, dtype=np.int32))
 elif mode == "dmd":
     # unmodified TimeUnit.compute_alpha_eigenvalues on seeded snapshot arrays (SURVEY appendix A)
     kind, Z, A, steps = sys.argv[3], int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
@@ -115,6 +177,10 @@ def main():
         out = os.path.join(HERE, f"kp_sweep_{length}_{cpm}_{A}.npz")
         print("sweep golden", length, cpm, A, flush=True)
         run(["sweep", out, length, cpm, A])
+    for length, cpm, A, steps in [(9, 5, 2, 6), (9, 10, 4, 4)]:
+        out = os.path.join(HERE, f"kp_march_repaired_{length}_{cpm}_{A}_{steps}.npz")
+        print("march golden (reference sweep + inner iteration, repaired outer loops)", length, cpm, A, steps, flush=True)
+        run(["march", out, length, cpm, A, steps])
     print("dmd golden (modes)", flush=True)
     run(["dmd", os.path.join(HERE, "dmd_modes_64_4_50.npz"), "modes", 64, 4, 50])
     run(["dmd", os.path.join(HERE, "dmd_modes_40_2_200.npz"), "modes", 40, 2, 200])

@@ -270,6 +270,29 @@ def test_time_march_matches_oracle_one_group(cpm, A, steps):
     assert _rel(dev.psi_to_host(psi), res["psi_last"][:, dev.angles, :]) < 1e-10
 
 
+@pytest.mark.parametrize("name", ["kp_march_repaired_9_5_2_6", "kp_march_repaired_9_10_4_4"])
+def test_time_march_against_repaired_reference_fixture(golden_dir, name):
+    """Device march against snapshots produced by the reference's own sweep1D / time_dependent_source_iteration under
+    the minimal repairs of its time loop (tests/golden/make_golden.py, mode `march`): identical iteration counts,
+    angular and scalar flux of every step within 1e-10."""
+    from tests.kp import kp_problem, kp_psi0
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cpm, A, steps = int(g["cells_per_mfp"]), int(g["num_angles"]), int(g["steps"])
+    p = kp_problem(9, cpm, A)
+    dev = _device(p, dt=float(g["dt"]))
+    torch = dev.torch
+    psi = dev.psi_to_device(kp_psi0(p))
+    n_psi, n_phi = dev.G * dev.A * dev.Zp, dev.G * dev.Zp
+    psi_snap = torch.zeros(steps * n_psi, dtype=torch.float64, device=dev.dev)
+    phi_snap = torch.zeros(steps * n_phi, dtype=torch.float64, device=dev.dev)
+    st, outer, inner = dev.time_march(psi, steps, 1e-10, psi_snap, phi_snap)
+    assert st == 0 and list(outer) == list(g["outer"]) and list(inner) == list(g["inner"])
+    for s_ in range(steps):
+        got = dev.psi_to_host(psi_snap[s_ * n_psi:(s_ + 1) * n_psi])
+        assert _rel(got, g["psi"][:, :, :, s_][:, dev.angles, :]) < 1e-10
+        assert _rel(dev.cells_to_host(phi_snap[s_ * n_phi:(s_ + 1) * n_phi]), g["phi"][:, :, s_]) < 1e-10
+
+
 def test_time_march_multigroup_in_place_matches_oracle():
     from oracle import ae_oracle as orc
     Z, A, G, steps, dt = 400, 6, 4, 4, 0.1

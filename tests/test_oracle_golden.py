@@ -84,6 +84,22 @@ def test_dmd_march_matches_oracle_march(golden_dir):
     assert abs(dom - _sorted_c(g["alphas"])[0]) < 1e-10 * abs(dom)
 
 
+@pytest.mark.parametrize("name", ["kp_march_repaired_9_5_2_6", "kp_march_repaired_9_10_4_4"])
+def test_time_march_equals_repaired_reference(golden_dir, name):
+    """The fixtures come from the reference's own sweep1D and time_dependent_source_iteration (unmodified) driven
+    through the minimal repairs R2-R5 of its broken time loop (tests/golden/make_golden.py, mode `march`).  The
+    oracle's march must reproduce them: same iteration counts, psi and phi snapshots to the last bit."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cpm, A, steps = int(g["cells_per_mfp"]), int(g["num_angles"]), int(g["steps"])
+    p = kp_problem(9, cpm, A)
+    np.testing.assert_array_equal(p["phi0"], g["phi0"])
+    r = orc.time_march(p["mu"], p["weight"], p["hx"], p["tables"], np.zeros((p["Z"], 1)), kp_psi0(p), float(g["dt"]), steps)
+    assert r["status"] == 0
+    assert list(r["outer"]) == list(g["outer"]) and list(r["inner"]) == list(g["inner"])
+    np.testing.assert_array_equal(r["psi_snap"].reshape(g["psi"].shape), g["psi"])
+    np.testing.assert_array_equal(r["phi_snap"].reshape(g["phi"].shape), g["phi"])
+
+
 def test_multigroup_reduces_to_one_group():
     """G=2 with two uncoupled identical groups must reproduce the one-group answer group by group."""
     p = kp_problem(9, 10, 4)
