@@ -9,7 +9,10 @@ Parity status (details in ae_oracle.c's header and DESIGN.md):
     (tests/golden/make_golden.py).
   * compute_alpha_eigenvalues (time_unit.py:61-92): pinned by outputs of the unmodified
     reference routine on seeded snapshot arrays (tests/golden/dmd_*.npz).
-  * time march and G > 1: PARITY UNPINNED (the reference has no runnable path).
+  * time march (one group): the reference's loop crashes as shipped; pinned against snapshots produced by the
+    reference's unmodified sweep1D and time_dependent_source_iteration under the minimal repairs R2-R5 applied from
+    outside (tests/golden/kp_march_repaired_*.npz, make_golden.py mode `march`): bit-exact.
+  * G > 1: PARITY UNPINNED (the reference has no runnable multigroup path).
 """
 from __future__ import annotations
 
