@@ -12,7 +12,9 @@ Parity status (details in ae_oracle.c's header and DESIGN.md):
   * time march (one group): the reference's loop crashes as shipped; pinned against snapshots produced by the
     reference's unmodified sweep1D and time_dependent_source_iteration under the minimal repairs R2-R5 applied from
     outside (tests/golden/kp_march_repaired_*.npz, make_golden.py mode `march`): bit-exact.
-  * G > 1: PARITY UNPINNED (the reference has no runnable multigroup path).
+  * G > 1: the fission and scatter source terms are pinned against the reference's Zone.compute_fission_source /
+    compute_scattering_source (zone.py:38-51; tests/golden/mg_zone_sources_7_40.npz); the iteration around them is
+    PARITY UNPINNED (the reference has no runnable multigroup driver).
 """
 from __future__ import annotations
 
@@ -106,6 +108,16 @@ def sweep_set(mu, w, hx, q, sigT, want_psi=False):
     lib().aeo_sweep_set(ctypes.c_int64(Z), A, G, _d(mu), _d(w), ctypes.c_double(hx), _d(q), _d(sigT),
                         _d(psi), _d(phi), _d(scratch))
     return (phi, psi) if want_psi else phi
+
+
+def mg_sources(tab: Tables, phi):
+    """(0.5 chi_g sum_g' nusf_g' phi_g', 0.5 sum_g' sigma_s(g'->g) phi_g') per cell, both (Z,G): the fission and
+    scatter terms of the multigroup solvers (zone.py:38-51)."""
+    phi = _f64(phi)
+    Z, G = phi.shape
+    fis, sca = np.empty((Z, G)), np.empty((Z, G))
+    lib().aeo_mg_sources(ctypes.c_int64(Z), G, _i(tab.mat), _d(tab.scat), _d(tab.chi), _d(tab.nusf), _d(phi), _d(fis), _d(sca))
+    return fis, sca
 
 
 def source_iteration(mu, w, hx, tab: Tables, source, tol=1e-8, max_iterations=100, want_psi=False):

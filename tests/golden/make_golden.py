@@ -75,6 +75,40 @@ elif mode == "sweep":
     np.savez_compressed(out, length=length, cells_per_mfp=cpm, num_angles=A, source=src, psi=psis,
              phi_si=g.phi.new, psi_si=psi_after, total_xs=g.total_xs, scatter_xs=g.scatter_xs,
              mu=slab.mu, weight=slab.weight, hx=slab.hx)
+elif mode == "zone":
+    # Multigroup source formulas of the reference, the only executable multigroup code it has: Zone.compute_fission_source
+    # and Zone.compute_scattering_source (zone.py:38-51) on seeded fluxes and cross-sections.
+    from alpha_eigen_modules.zone import Zone
+    G, Z = int(sys.argv[3]), int(sys.argv[4])
+    rs = np.random.RandomState(5)
+    class S: pass
+    slab = S(); slab.num_groups = G
+    class M: pass
+    mats = []
+    for _ in range(3):
+        m = M()
+        m.scatter_xs = rs.rand(G, G)            # [g_from, g_to] (material.py:38)
+        m.nu_sigmaf = rs.rand(G)
+        m.chi = rs.rand(G); m.chi /= m.chi.sum()
+        mats.append(m)
+    mat_idx = rs.randint(0, 3, Z)
+    phi = rs.rand(Z, G) + 0.1
+    fission = np.zeros((Z, G)); source = np.zeros((Z, G))
+    for i in range(Z):
+        z = Zone(slab, float(i))
+        z.material = mats[mat_idx[i]]
+        z.out_group_scatter_xs = z.material.scatter_xs.copy()          # zone.py:33-36
+        for g in range(G):
+            z.out_group_scatter_xs[g, g] = 0
+        z.phi.old = phi[i].copy(); z.phi.new = phi[i].copy()
+        z.compute_fission_source()                                      # zone.py:38-42
+        fission[i] = z.fission_source
+        z.source = np.zeros(G)
+        z.compute_scattering_source()                                   # zone.py:48-51 (out-group scatter + fission)
+        source[i] = z.source
+    np.savez_compressed(out, G=G, Z=Z, mat=mat_idx, phi=phi, scat=np.array([m.scatter_xs for m in mats]),
+             nusf=np.array([m.nu_sigmaf for m in mats]), chi=np.array([m.chi for m in mats]),
+             fission_source=fission, scatter_plus_fission_source=source)
 elif mode == "march":
     # Time march with the reference's OWN sweep1D (group.py:41-60) and time_dependent_source_iteration
     # (time_unit.py:44-59), both unmodified, under the minimal repairs of SURVEY section 3.3 applied from outside:
@@ -181,6 +215,8 @@ def main():
         out = os.path.join(HERE, f"kp_march_repaired_{length}_{cpm}_{A}_{steps}.npz")
         print("march golden (reference sweep + inner iteration, repaired outer loops)", length, cpm, A, steps, flush=True)
         run(["march", out, length, cpm, A, steps])
+    print("zone source formulas golden", flush=True)
+    run(["zone", os.path.join(HERE, "mg_zone_sources_7_40.npz"), 7, 40])
     print("dmd golden (modes)", flush=True)
     run(["dmd", os.path.join(HERE, "dmd_modes_64_4_50.npz"), "modes", 64, 4, 50])
     run(["dmd", os.path.join(HERE, "dmd_modes_40_2_200.npz"), "modes", 40, 2, 200])

@@ -100,6 +100,22 @@ def test_time_march_equals_repaired_reference(golden_dir, name):
     np.testing.assert_array_equal(r["phi_snap"].reshape(g["phi"].shape), g["phi"])
 
 
+def test_multigroup_source_terms_equal_reference_zone_formulas(golden_dir):
+    """The only executable multigroup code of the reference, Zone.compute_fission_source / compute_scattering_source
+    (zone.py:38-51), evaluated on seeded data (make_golden.py, mode `zone`).  The oracle's fission term must equal
+    zone.py:38-42 exactly; zone.py:48-51 adds, per source group, the OUT-of-group scatter and the fission
+    contribution, i.e. the oracle's full scatter term minus its in-group part plus its fission term."""
+    g = np.load(os.path.join(golden_dir, "mg_zone_sources_7_40.npz"))
+    G = int(g["G"])
+    one = np.ones((3, G))
+    tab = orc.Tables(g["mat"], one, g["scat"], g["chi"], g["nusf"], one)
+    fis, sca = orc.mg_sources(tab, g["phi"])
+    np.testing.assert_array_equal(fis, g["fission_source"])
+    in_group = 0.5 * g["phi"] * np.array([np.diag(g["scat"][m]) for m in g["mat"]])
+    ref = g["scatter_plus_fission_source"]
+    assert np.max(np.abs((sca - in_group + fis) - ref) / np.abs(ref)) < 5e-15     # same terms, different summation order
+
+
 def test_multigroup_reduces_to_one_group():
     """G=2 with two uncoupled identical groups must reproduce the one-group answer group by group."""
     p = kp_problem(9, 10, 4)
