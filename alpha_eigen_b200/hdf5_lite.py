@@ -3,10 +3,10 @@ cross-sections -- material.py:36-46 -- live in HDF5 files).
 
 Covers what classic h5py-written files of plain numeric arrays use: superblock version 0 or 1, groups stored
 as symbol tables (v1 B-tree + local heap + SNOD nodes), version-1 object headers with continuation blocks,
-simple dataspaces, little- or big-endian fixed-point and IEEE floating-point datatypes, and compact,
-contiguous or unfiltered chunked (v1 chunk B-tree) layouts.  Anything else (filters / compression, new-style
-groups, variable-length or compound types) raises Hdf5Error naming the feature, so a file this reader cannot
-handle never yields silently wrong numbers.
+simple dataspaces, little- or big-endian fixed-point and IEEE floating-point datatypes, and compact or
+contiguous layouts (what the reference's files use).  Anything else (chunked storage, filters / compression,
+new-style groups, variable-length or compound types) raises Hdf5Error naming the feature, so a file this reader
+cannot handle never yields silently wrong numbers.
 
     with File(path) as hf:          # same spelling as h5py for the calls material.py makes
         a = hf["scat_xs"][:]
@@ -204,10 +204,7 @@ class File:
                 addr += self._base
                 return b[addr:addr + n * itemsize]
             if cls == 2:
-                rank1 = m[2]
-                btree = int.from_bytes(m[3:11], "little")
-                dims = [int.from_bytes(m[11 + 4 * i:15 + 4 * i], "little") for i in range(rank1)]
-                return self._chunked(btree, shape, dims[:-1], itemsize, n)
+                raise Hdf5Error("chunked datasets are not supported (no fixture to validate them against)")
             raise Hdf5Error(f"layout class {cls}")
         if ver in (1, 2):
             rank, cls = m[1], m[2]
@@ -216,8 +213,7 @@ class File:
             if cls != 0:
                 addr = int.from_bytes(m[p:p + 8], "little")
                 p += 8
-            dims = [int.from_bytes(m[p + 4 * i:p + 4 * i + 4], "little") for i in range(rank)]
-            p += 4 * rank
+            p += 4 * rank                               # dimension sizes (the dataspace message has them too)
             if cls == 0:
                 size = int.from_bytes(m[p:p + 4], "little")
                 return bytes(m[p + 4:p + 4 + size])
@@ -226,34 +222,5 @@ class File:
                     return bytes(n * itemsize)
                 addr += self._base
                 return b[addr:addr + n * itemsize]
-            return self._chunked(addr, shape, dims[:-1], itemsize, n)
+            raise Hdf5Error("chunked datasets are not supported (no fixture to validate them against)")
         raise Hdf5Error(f"data layout version {ver}")
-
-    def _chunked(self, btree, shape, chunk, itemsize, n):
-        out = np.zeros(tuple(shape) + (itemsize,), dtype=np.uint8)     # bytes of every element; unwritten chunks stay 0
-        if btree == _UNDEF:
-            return out.tobytes()
-        rank = len(shape)
-        stack = [btree + self._base]
-        b = self._b
-        while stack:
-            a = stack.pop()
-            if b[a:a + 4] != b"TREE" or b[a + 4] != 1:
-                raise Hdf5Error("chunk B-tree node expected")
-            level, used = b[a + 5], self._u(a + 6, 2)
-            key = 8 + 8 * (rank + 1)
-            p = a + 24
-            for _ in range(used):
-                nbytes, mask = self._u(p, 4), self._u(p + 4, 4)
-                offs = [self._u(p + 8 + 8 * i, 8) for i in range(rank)]
-                child = self._u(p + key, 8) + self._base
-                p += key + 8
-                if level > 0:
-                    stack.append(child)
-                    continue
-                if mask:
-                    raise Hdf5Error("filtered chunks are not supported")
-                blk = np.frombuffer(b, dtype=np.uint8, count=nbytes, offset=child).reshape(tuple(chunk) + (itemsize,))
-                sl = tuple(slice(o, min(o + c, s)) for o, c, s in zip(offs, chunk, shape))
-                out[sl] = blk[tuple(slice(0, s.stop - s.start) for s in sl)]
-        return out.tobytes()
