@@ -3,8 +3,8 @@ cross-sections -- material.py:36-46 -- live in HDF5 files).
 
 Covers what classic h5py-written files of plain numeric arrays use: superblock version 0 or 1, groups stored
 as symbol tables (v1 B-tree + local heap + SNOD nodes), version-1 object headers with continuation blocks,
-simple dataspaces, little- or big-endian fixed-point and IEEE floating-point datatypes, and compact or
-contiguous layouts (what the reference's files use).  Anything else (chunked storage, filters / compression,
+simple dataspaces, little- or big-endian fixed-point and IEEE floating-point datatypes, and contiguous storage
+(what the reference's files use).  Anything else (compact or chunked storage, filters / compression,
 new-style groups, variable-length or compound types) raises Hdf5Error naming the feature, so a file this reader
 cannot handle never yields silently wrong numbers.
 
@@ -190,37 +190,16 @@ class File:
         raise Hdf5Error(f"datatype class {cls} (version {ver}) is not supported")
 
     def _layout_bytes(self, m, shape, itemsize, n):
-        b = self._b
+        """Bytes of a version-3 contiguous layout message -- the only storage the reference's files use and therefore
+        the only one this reader has fixtures for; everything else is refused rather than guessed at."""
         ver = m[0]
-        if ver == 3:
-            cls = m[1]
-            if cls == 0:
-                size = int.from_bytes(m[2:4], "little")
-                return bytes(m[4:4 + size])
-            if cls == 1:
-                addr = int.from_bytes(m[2:10], "little")
-                if addr == _UNDEF:
-                    return bytes(n * itemsize)          # never written: fill value 0
-                addr += self._base
-                return b[addr:addr + n * itemsize]
-            if cls == 2:
-                raise Hdf5Error("chunked datasets are not supported (no fixture to validate them against)")
-            raise Hdf5Error(f"layout class {cls}")
-        if ver in (1, 2):
-            rank, cls = m[1], m[2]
-            p = 8
-            addr = None
-            if cls != 0:
-                addr = int.from_bytes(m[p:p + 8], "little")
-                p += 8
-            p += 4 * rank                               # dimension sizes (the dataspace message has them too)
-            if cls == 0:
-                size = int.from_bytes(m[p:p + 4], "little")
-                return bytes(m[p + 4:p + 4 + size])
-            if cls == 1:
-                if addr == _UNDEF:
-                    return bytes(n * itemsize)
-                addr += self._base
-                return b[addr:addr + n * itemsize]
-            raise Hdf5Error("chunked datasets are not supported (no fixture to validate them against)")
-        raise Hdf5Error(f"data layout version {ver}")
+        if ver != 3:
+            raise Hdf5Error(f"data layout message version {ver} is not supported")
+        cls = m[1]
+        if cls != 1:
+            raise Hdf5Error({0: "compact", 2: "chunked"}.get(cls, f"class-{cls}") + " dataset storage is not supported")
+        addr = int.from_bytes(m[2:10], "little")
+        if addr == _UNDEF:
+            return bytes(n * itemsize)                  # allocated but never written: fill value 0
+        addr += self._base
+        return self._b[addr:addr + n * itemsize]
