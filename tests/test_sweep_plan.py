@@ -108,3 +108,21 @@ def test_plan_rejects_bad_arguments():
     lib = _lib.load()
     assert lib.ae_sweep_plan(0, 0, 1, 256, 148, 0, None, None, None, None, 0) == -1
     assert lib.ae_sweep_plan(4, 2, 1, 255, 148, 0, None, None, None, None, 0) == -1
+
+
+@pytest.mark.parametrize("force,expect", [("1", 1), ("2", 2), ("8", 8), ("3", 1)])
+def test_forced_gang_size(force, expect):
+    """AE_SWEEP_GANG overrides the automatic choice (read once per process, hence the subprocess); a size that does not
+    divide the angle blocks per direction falls back to 1.  Coverage must hold for every forced size."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from tests.test_sweep_plan import check_plan\n"
+            "from alpha_eigen_b200 import _lib\n"
+            "print(check_plan(256, 128, 70, _lib.load().ae_padded_cells(200_000), 148)[1])\n") % root
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, AE_SWEEP_GANG=force))
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert int(out.stdout.strip().splitlines()[-1]) == expect
