@@ -8,10 +8,12 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libalpha_eigen_b200.so")
+# AE_LIB selects another build of the same sources (kernel A/B experiments, tools/); the product is the in-tree default
+LIB_PATH = os.environ.get("AE_LIB") or os.path.join(_HERE, "libalpha_eigen_b200.so")
 
 AE_OK, AE_NOT_CONVERGED, AE_BAD_ARG, AE_CUDA_ERROR = 0, 1, 2, 3
 AE_TILE, AE_LANE_CELLS = 256, 8
+AE_WORK_NO_FUSED, AE_WORK_REREAD_PSI = 1, 2
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
@@ -27,14 +29,15 @@ class AeSlab(C.Structure):
     _fields_ = [("Z", C.c_int64), ("Zp", C.c_int64), ("A", C.c_int32), ("n_neg", C.c_int32), ("G", C.c_int32),
                 ("M", C.c_int32), ("mu_ihx", C.c_void_p), ("wgt", C.c_void_p), ("mat", C.c_void_p),
                 ("scat", C.c_void_p), ("chi", C.c_void_p), ("nusf", C.c_void_p), ("hs", C.c_void_p),
-                ("cdt", C.c_void_p), ("s_ext", C.c_void_p)]
+                ("cdt", C.c_void_p), ("s_ext", C.c_void_p), ("tile_info", C.c_void_p)]
 
 
 class AeWork(C.Structure):
     _fields_ = [("phi", C.c_void_p), ("phi_alt", C.c_void_p), ("phi_outer", C.c_void_p), ("base", C.c_void_p),
                 ("q0", C.c_void_p), ("q1", C.c_void_p), ("partial", C.c_void_p), ("reduced", C.c_void_p),
-                ("norm_scratch", C.c_void_p), ("ctrl", C.c_void_p),
-                ("ctrl_host", C.c_void_p), ("sweep_sync", C.c_void_p), ("comm", C.c_void_p), ("P", C.c_int32), ("batch", C.c_int32)]
+                ("phi_fixed", C.c_void_p), ("norm_scratch", C.c_void_p), ("ctrl", C.c_void_p),
+                ("ctrl_host", C.c_void_p), ("sweep_sync", C.c_void_p), ("comm", C.c_void_p), ("P", C.c_int32), ("batch", C.c_int32),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 class AeMember(C.Structure):
@@ -53,6 +56,7 @@ SYMBOLS = {
     "ae_partial_count": (C.c_int32, [C.c_int32, C.c_int32]),
     "ae_norm_blocks": (C.c_int64, [C.c_int64]),
     "ae_sweep_set": (C.c_int, [C.POINTER(AeSlab), _P, _P, _P, _P, _P, _P]),
+    "ae_tile_info": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, _P, _P]),
     "ae_sweep_sync_bytes": (C.c_int64, []),
     "ae_sweep_plan": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, c_ip, c_ip, c_ip, c_ip,
                                   C.c_int64]),
@@ -105,7 +109,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.ae_abi_version() != 1:
+        if lib.ae_abi_version() != 2:
             raise AlphaEigenError("ABI version mismatch")
         _lib = lib
     return _lib

@@ -450,7 +450,7 @@ int block_angles(int A, int n_neg);
 static bool small_problem(const ae_slab *s, ae_work *w, SmallArgs &p, int &ac, int &rows)
 {
     static const char *off = getenv("AE_NO_FUSED_SMALL");
-    if (off && off[0] == '1') return false;
+    if ((off && off[0] == '1') || (w->flags & AE_WORK_NO_FUSED)) return false;
     if (w->comm) return false;                                          // multi-GPU goes through the exchange path
     const int64_t updates = s->Zp * (int64_t)s->A * s->G;
     if (updates > (1 << 23) || s->Zp / kTile > 256) return false;       // big enough for the streaming kernels

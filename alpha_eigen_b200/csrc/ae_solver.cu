@@ -5,13 +5,14 @@
 // kernels with the reference's formulas and tolerances; the host only polls a small control block
 // (one pinned-memory read per `batch` source iterations) so that iteration counts -- and therefore
 // results -- are identical to the reference's, which stops on the first iterate that passes.
+#include <stdlib.h>
 #include "ae_common.cuh"
 
 namespace ae {
 int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double *psi_out, double *partial,
                  void *sync, const ae_ctrl *ctrl, int gate, cudaStream_t st);
-int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, const double *phi_in, double *phi_out,
-                    double *q_next, int init, double cold, double tol, int iteration, int gate, cudaStream_t st);
+int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, const double *fixed, const double *phi_in,
+                    double *phi_out, double *q_next, int init, double cold, double tol, int iteration, int gate, cudaStream_t st);
 int launch_fission_base(const ae_slab *s, ae_work *w, const double *phi, double *base, int with_ext, cudaStream_t st);
 int launch_small_source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, double cold, double tol,
                                   int max_iterations, int *launched, cudaStream_t st);
@@ -49,9 +50,30 @@ int check_work(const ae_slab *s, const ae_work *w, const char *who)
     return AE_OK;
 }
 
+// Time-dependent solves.  The angular source of a step is q + cdt*psi^n (time_unit.py:23,53) and only q changes
+// between the sweeps of the step, while the sweep is LINEAR in its source: phi = sum_a w_a L_a(q) + sum_a w_a L_a(cdt psi^n).
+// The second term is swept once (this function, the only pass that reads psi^n) into w->phi_fixed; the ~40 inner
+// iterations of the step then sweep q alone -- 24/A bytes per update instead of 8 + 24/A -- and the flux update adds
+// phi_fixed.  AE_WORK_REREAD_PSI (or AE_TD_REREAD_PSI=1) restores the literal scheme (psi^n re-read by every inner sweep) for A/B runs.
+static bool reread_psi(const ae_work *w)
+{
+    static const char *e = getenv("AE_TD_REREAD_PSI");
+    return (e && e[0] == '1') || (w->flags & AE_WORK_REREAD_PSI);
+}
+static int compute_fixed(const ae_slab *s, ae_work *w, const double *psi_in, cudaStream_t st)
+{
+    if (!w->phi_fixed) { set_error("time-dependent solve: ae_work.phi_fixed is missing"); return AE_BAD_ARG; }
+    AE_CUDA(cudaMemsetAsync(w->q1, 0, (size_t)s->G * s->Zp * sizeof(double), st));        // q1 is free until the first update
+    AE_TRY(launch_sweep(s, w->q1, psi_in, nullptr, w->partial, w->sweep_sync, w->ctrl, 0, st));
+    AE_TRY(ae_reduce_partials(s, w->partial, w->P, w->phi_fixed, st));
+    if (w->comm) AE_TRY(comm_reduce_scatter_rows(w->comm, w->phi_fixed, s->G, s->Zp, st)); // valid on this rank's cell range
+    return AE_OK;
+}
+
 // group.py:62-81 / time_unit.py:44-59.  The flux iterate ping-pongs between w->phi and w->phi_alt (the
 // update kernel must not read and write the same buffer); on return w->phi is the converged flux.
-static int source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, double cold, double tol,
+// *fixed_ready (time-dependent callers): w->phi_fixed already holds the contribution of psi_in.
+static int source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, int *fixed_ready, double cold, double tol,
                             int max_iterations, int *iters, int *last_q, cudaStream_t st)
 {
     double *q[2] = {w->q0, w->q1};
@@ -68,8 +90,15 @@ static int source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, 
         if (n & 1) { w->phi = phi[1]; w->phi_alt = phi[0]; }
         return w->ctrl_host->inner_done ? AE_OK : AE_NOT_CONVERGED;
     }
+    const double *fixed = nullptr, *sweep_psi = psi_in;
+    if (psi_in && !reread_psi(w)) {
+        if (!fixed_ready || !*fixed_ready) AE_TRY(compute_fixed(s, w, psi_in, st));
+        if (fixed_ready) *fixed_ready = 1;
+        fixed = w->phi_fixed;
+        sweep_psi = nullptr;
+    }
     // phi_old = cold (group.py:66 / time_unit.py:45); q0 = base + 0.5*sigma_s*phi_old (group.py:73)
-    AE_TRY(launch_finalize(s, w, nullptr, 0, nullptr, phi[0], q[0], 1, cold, tol, 0, 0, st));
+    AE_TRY(launch_finalize(s, w, nullptr, 0, nullptr, nullptr, phi[0], q[0], 1, cold, tol, 0, 0, st));
     int it = 0;         // iterations launched so far
     int status = AE_OK, n_done = 0;
     for (;;) {
@@ -80,15 +109,15 @@ static int source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, 
         for (int b = 0; b < nb; ++b) {
             const int i = it + b;                       // 0-based; reference iteration number is i+1
             const int gate = b > 0;                     // first of a batch always runs
-            AE_TRY(launch_sweep(s, q[i & 1], psi_in, nullptr, w->partial, w->sweep_sync, w->ctrl, gate, st));
+            AE_TRY(launch_sweep(s, q[i & 1], sweep_psi, nullptr, w->partial, w->sweep_sync, w->ctrl, gate, st));
             if (w->comm) {
                 // angle-sharded sweeps, cell-sharded update: reduce-scatter the flux, update 1/N of the cells,
                 // all-gather the new source (inside launch_finalize)
                 AE_TRY(exchange_partials(s, w, st));
-                AE_TRY(launch_finalize(s, w, w->reduced, 1, phi[i & 1], phi[(i + 1) & 1], q[(i + 1) & 1], 0, cold, tol,
+                AE_TRY(launch_finalize(s, w, w->reduced, 1, fixed, phi[i & 1], phi[(i + 1) & 1], q[(i + 1) & 1], 0, cold, tol,
                                        i + 1, gate, st));
             } else {
-                AE_TRY(launch_finalize(s, w, w->partial, w->P, phi[i & 1], phi[(i + 1) & 1], q[(i + 1) & 1], 0, cold, tol,
+                AE_TRY(launch_finalize(s, w, w->partial, w->P, fixed, phi[i & 1], phi[(i + 1) & 1], q[(i + 1) & 1], 0, cold, tol,
                                        i + 1, gate, st));
             }
         }
@@ -119,7 +148,7 @@ extern "C" int ae_flux_update(const ae_slab *s, ae_work *w, const double *partia
 {
     AE_TRY(check_work(s, w, "ae_flux_update"));
     if (!partial || !q_next || P < 1) { set_error("ae_flux_update: bad argument"); return AE_BAD_ARG; }
-    AE_TRY(launch_finalize(s, w, partial, P, w->phi, w->phi_alt, q_next, 0, 0.0, tol, iteration, 0, (cudaStream_t)stream));
+    AE_TRY(launch_finalize(s, w, partial, P, nullptr, w->phi, w->phi_alt, q_next, 0, 0.0, tol, iteration, 0, (cudaStream_t)stream));
     double *t = w->phi; w->phi = w->phi_alt; w->phi_alt = t;      // w->phi is always the newest iterate
     return AE_OK;
 }
@@ -128,7 +157,7 @@ extern "C" int ae_source_iteration(const ae_slab *s, ae_work *w, const double *p
                                    int32_t max_iterations, int32_t *iters, int32_t *last_q_index, void *stream)
 {
     AE_TRY(check_work(s, w, "ae_source_iteration"));
-    return source_iteration(s, w, psi_in, cold_start, tol, max_iterations, iters, last_q_index, (cudaStream_t)stream);
+    return source_iteration(s, w, psi_in, nullptr, cold_start, tol, max_iterations, iters, last_q_index, (cudaStream_t)stream);
 }
 
 // group.py:97-116
@@ -147,7 +176,7 @@ extern "C" int ae_power_iteration(const ae_slab *s, ae_work *w, double tol, int3
         if (!(iteration < max_iterations)) { status = AE_NOT_CONVERGED; iteration -= 1; break; }   // group.py:102
         AE_TRY(launch_fission_base(s, w, w->phi_outer, w->base, 0, st));    // group.py:104: source = zeros + fission
         int si = 0;
-        status = source_iteration(s, w, nullptr, 1e-12, si_tol, si_max_iterations, &si, &last_q, st);
+        status = source_iteration(s, w, nullptr, nullptr, 1e-12, si_tol, si_max_iterations, &si, &last_q, st);
         if (si_hist) si_hist[iteration - 1] = si;
         if (status != AE_OK) { iteration -= 1; break; }     // *iters = completed power iterations
         AE_TRY(launch_k_update(s, w, tol, iteration, st));
@@ -180,12 +209,13 @@ extern "C" int ae_time_step(const ae_slab *s, ae_work *w, const double *psi_prev
     const size_t nbytes = (size_t)s->G * s->Zp * sizeof(double);
     AE_CUDA(cudaMemsetAsync(w->phi_outer, 0, nbytes, st));      // time_unit.py:30 phi = zeros
     int outer = 0, inner_total = 0, last_q = 0, status = AE_OK;
+    int fixed_ready = 0;                                        // phi_fixed is swept once per step, on first use
     for (;;) {
         outer += 1;
         if (!(outer < 100)) { status = AE_NOT_CONVERGED; break; }               // time_unit.py:35
         AE_TRY(launch_fission_base(s, w, w->phi_outer, w->base, 1, st));        // time_unit.py:37-39
         int si = 0;
-        status = source_iteration(s, w, psi_prev, 0.0, tol, 100, &si, &last_q, st);     // time_unit.py:40
+        status = source_iteration(s, w, psi_prev, &fixed_ready, 0.0, tol, 100, &si, &last_q, st);    // time_unit.py:40
         inner_total += si;
         if (status != AE_OK) break;
         AE_TRY(launch_outer_check(s, w, st));                                   // time_unit.py:41 (+R4)

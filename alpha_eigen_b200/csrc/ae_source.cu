@@ -98,6 +98,7 @@ __global__ void norm_finalize_kernel(const double *pairs, int nranks, int mode, 
 struct FinArgs {
     const double *partial;      // [P][G][Zp] (P may be 1 when phi was already reduced over angle blocks / ranks)
     const double *base;         // [G][Zp]
+    const double *fixed;        // [G][Zp] added to the sum of the partials (ae_work.phi_fixed) or NULL
     const int32_t *mat;         // [Zp]
     const double *scat;         // [M][G][G]
     const double *phi_in;       // [G][Zp] previous iterate
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(kCB) finalize_small_kernel(const FinArgs p)
                 } else {
                     x = p.partial[i];
                     for (int pp = 1; pp < p.P; ++pp) x += p.partial[(int64_t)pp * n + i];
+                    if (p.fixed) x += p.fixed[i];
                 }
                 if (!valid) x = 0.0;
                 if (!p.init) {
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(256, 6) flux_assemble_kernel(const FinArgs p)
     const int64_t n = (int64_t)p.G * p.Zp;
     const int64_t row = (int64_t)blockIdx.y * p.Zp + p.c0;
     const double *part = p.partial + row;
+    const double *fix = p.fixed ? p.fixed + row : nullptr;
     const double *old = p.phi_in + row;
     double *out = p.phi + row;
     double num = 0.0, den = 0.0;
@@ -191,6 +194,10 @@ __global__ void __launch_bounds__(256, 6) flux_assemble_kernel(const FinArgs p)
 #pragma unroll 4
         for (int pp = 1; pp < p.P; ++pp) {                       // block order (group.py:77 over angle blocks)
             const double2 y = *reinterpret_cast<const double2 *>(part + (int64_t)pp * n + i);
+            x.x += y.x; x.y += y.y;
+        }
+        if (fix) {                                               // the part of the flux psi^n drives (once per step)
+            const double2 y = *reinterpret_cast<const double2 *>(fix + i);
             x.x += y.x; x.y += y.y;
         }
         const double2 o = *reinterpret_cast<const double2 *>(old + i);
@@ -418,13 +425,13 @@ static int finish_sharded_norm(const ae_slab *s, ae_work *w, double *rows, int m
     return AE_OK;
 }
 
-int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, const double *phi_in, double *phi_out,
-                    double *q_next, int init, double cold, double tol, int iteration, int gate, cudaStream_t st)
+int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, const double *fixed, const double *phi_in,
+                    double *phi_out, double *q_next, int init, double cold, double tol, int iteration, int gate, cudaStream_t st)
 {
     const Shard sh = shard_of(s, w);
     if (s->Zp % (kTile * comm_size(w->comm))) { set_error("Zp must be a multiple of 256 * ranks"); return AE_BAD_ARG; }
     FinArgs p;
-    p.partial = partial; p.base = w->base; p.mat = s->mat; p.scat = s->scat; p.phi_in = phi_in; p.phi = phi_out;
+    p.partial = partial; p.base = w->base; p.fixed = fixed; p.mat = s->mat; p.scat = s->scat; p.phi_in = phi_in; p.phi = phi_out;
     p.q_next = q_next; p.norm = norm_out(w, kNormInner, tol, iteration);
     p.Z = s->Z; p.Zp = s->Zp; p.c0 = sh.c0; p.cn = sh.cn; p.P = P; p.G = s->G; p.M = s->M;
     p.init = init; p.gate = gate; p.cold = cold;

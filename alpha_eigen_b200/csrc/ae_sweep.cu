@@ -45,6 +45,7 @@ constexpr int kTileBytes = kTile * 8;   // 2 KB
 
 struct SweepArgs {
     const double *hs, *cdt, *q, *mu_ihx, *wgt, *psi_in;
+    const double *tinfo;                // [G][Zp/kTile][2] uniform-tile records (ae_tile_info) or NULL: general path only
     double *psi_out, *partial;
     SweepSync *sync;
     int64_t Z, Zp;
@@ -104,31 +105,26 @@ __device__ __forceinline__ void st_stream(double *p, double2 v, uint64_t pol)
     asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol)
                  : "memory");
 }
-// Walks the tiles a CTA processes.  Its range [t0, t1) of the flattened (row block, tile) sequence
-// is visited as: last (head) piece, whole row blocks, first (tail) piece -- see the file header.
-struct Cursor {
-    int nt, rb, ti;                      // tiles per row; current row block and tile (sweep order)
-    int b0, b1, first_ti;                // first / last row block of the range, tile where the range starts
-    int64_t j, len_last;                 // tiles done so far; length of the head piece
+// A CTA's range [t0, t1) of the flattened (row block, tile) sequence is visited as: last (head) piece, whole row
+// blocks, first (tail) piece -- see the file header -- as a short list of segments (row block, first tile in sweep
+// order, tiles): what the kernel's tile loops iterate over.  Segment 0 is the piece whose end hands carries on; the last one may consume a hand-off.
+struct Segments {
+    int nt, b0, b1, first_ti, len_last, count;
     __host__ __device__ void init(int64_t t0, int64_t t1, int nt_)
     {
         nt = nt_;
         b0 = (int)(t0 / nt); b1 = (int)((t1 - 1) / nt);
         first_ti = (int)(t0 - (int64_t)b0 * nt);
-        j = 0;
-        if (b0 == b1) { len_last = t1 - t0; rb = b0; ti = first_ti; }
-        else { len_last = t1 - (int64_t)b1 * nt; rb = b1; ti = 0; }
+        if (t1 <= t0) { count = 0; len_last = 0; }
+        else if (b0 == b1) { len_last = (int)(t1 - t0); count = 1; }
+        else { len_last = (int)(t1 - (int64_t)b1 * nt); count = b1 - b0 + 1; }
     }
-    __host__ __device__ void advance()
+    __host__ __device__ void get(int k, int &rb, int &ti0, int &n) const
     {
-        ++j; ++ti;
-        if (b0 == b1) return;
-        if (j == len_last) {                        // head piece done
-            if (b1 - b0 > 1) { rb = b0 + 1; ti = 0; } else { rb = b0; ti = first_ti; }
-        } else if (ti == nt && j > len_last) {      // a whole row block done
-            ++rb; ti = 0;
-            if (rb == b1) { rb = b0; ti = first_ti; }
-        }
+        if (count == 1) { rb = b0; ti0 = first_ti; n = len_last; }
+        else if (k == 0) { rb = b1; ti0 = 0; n = len_last; }
+        else if (k == count - 1) { rb = b0; ti0 = first_ti; n = nt - first_ti; }
+        else { rb = b0 + k; ti0 = 0; n = nt; }
     }
 };
 
@@ -169,8 +165,13 @@ __host__ __device__ __forceinline__ int unit_row(const SweepArgs &p, int u, int 
     return g * p.nbg + dir * p.nb_neg + sub * p.gs + mb;
 }
 
-template <int AC> struct StageCfg {
-    static constexpr int stages = AC == kACbig ? 4 : 3;
+#ifndef AE_SWEEP_PHI_STAGES
+#define AE_SWEEP_PHI_STAGES 12
+#endif
+template <int AC, bool READ_PSI = true> struct StageCfg {
+    // phi-only sweeps stage one 2 KB tile (q) per step, so a deep ring costs little and keeps enough tiles in flight
+    // to cover the TMA latency at their much higher tile rate
+    static constexpr int stages = READ_PSI ? (AC == kACbig ? 4 : 3) : AE_SWEEP_PHI_STAGES;
     // Reducer warps, each summing its share of a tile's cells.  With one reducer the compute warps of the 16-angle
     // CTA spent 21 % of their samples waiting for the reduction array to be recycled (ncu, C3); a second one
     // halves that latency and still fits the register file (19 warps x 96 registers).  Measured (sweep kernel, ms,
@@ -192,17 +193,19 @@ template <int AC> struct StageCfg {
 template <int AC, bool READ_PSI, bool WRITE_PSI>
 __global__ void __launch_bounds__(StageCfg<AC>::threads, AC == kACsmall ? 2 : 1) sweep_kernel(const SweepArgs p, const ae_ctrl *ctrl, int gate)
 {
-    constexpr int kStages = StageCfg<AC>::stages;
+    constexpr int kStages = StageCfg<AC, READ_PSI>::stages;
     constexpr int kRed = StageCfg<AC>::reducers, kPerRed = 4 / kRed;   // a reducer sums kPerRed of the 4 double2 columns
     constexpr int kSlots = (READ_PSI ? 3 + AC : 2);             // 2 KB slots per stage
+    constexpr int kStageLen = kSlots * kTile + 2;               // doubles per stage: the slots + the tile's record
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *ring = reinterpret_cast<double *>(smem_raw);                    // [kStages][kSlots][kTile]
-    double *red = ring + kStages * kSlots * kTile;                          // [2][AC][kTile]
+    double *ring = reinterpret_cast<double *>(smem_raw);                    // [kStages][kStageLen]
+    double *red = ring + kStages * kStageLen;                               // [2][AC][kTile]
     uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * AC * kTile);    // [kStages]
     uint64_t *empty = full + kStages;                                       // [kStages]
     uint64_t *red_full = empty + kStages;                                   // [2]
     uint64_t *red_empty = red_full + 2;                                     // [2]
     __shared__ int s_cta;
+    __shared__ __align__(16) double s_ap[AC][kL];                           // uniform-tile constants, per compute warp
     if (gate && ctrl->inner_done) return;                                   // batch launched past convergence
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -217,122 +220,179 @@ __global__ void __launch_bounds__(StageCfg<AC>::threads, AC == kACsmall ? 2 : 1)
     const int cta = s_cta;
     const int gang = cta / p.gs, mb = cta - gang * p.gs;                    // members of a gang start back to back
     const unsigned stamp = sy->epoch + 1;                                   // epoch only advances after every CTA has left
-    const int64_t nt = p.Zp / kTile;
+    const int nt = (int)(p.Zp / kTile);
     const int64_t T = p.total_tiles, NC = gridDim.x / p.gs;
-    const int64_t t0 = gang * T / NC, t1 = (gang + 1) * T / NC, W = t1 - t0;
+    const int64_t t0 = gang * T / NC, t1 = (gang + 1) * T / NC;
     const bool publishes = (t1 % nt) != 0;                                  // range ends inside a row block
-    Cursor cur;
-    cur.init(t0, t1, (int)nt);
+    Segments segs;
+    segs.init(t0, t1, nt);
+    const bool info = p.tinfo != nullptr;
     RowCtx c;
-    int c_rb = -1;
+    // Every role walks the same segments (pieces of rows) in the same order; inside a segment the tile loop is
+    // plain counting: ring stage `st` with phase `ph`, reduction buffer `b` with phase `bph`.
+    int st = 0, b = 0;
+    uint32_t ph = 0, bph = 0;
 
     if (warp == AC + kRed) {
         // ================= producer warp: TMA ring =====================================================
         const uint64_t pol = l2_policy(p.l2_hints ? (lane < 3 ? 2 : 1) : 0);   // lanes 0-2 fetch hs/q/cdt, the rest psi
-        for (int64_t j = 0; j < W; ++j, cur.advance()) {
-            if (cur.rb != c_rb) { row_setup<AC>(p, unit_row(p, cur.rb, mb), 0, c); c_rb = cur.rb; }
-            const int64_t off = (int64_t)(c.neg ? nt - 1 - cur.ti : cur.ti) * kTile;
-            const int st = (int)(j % kStages);
-            double *dst = ring + (size_t)st * kSlots * kTile;
-            const int64_t goff = (int64_t)c.g * p.Zp + off;
+        for (int k = 0; k < segs.count; ++k) {
+            int rb, ti0, n;
+            segs.get(k, rb, ti0, n);
+            row_setup<AC>(p, unit_row(p, rb, mb), 0, c);
+            const int dir = c.neg ? -1 : 1;
+            int tile = c.neg ? nt - 1 - ti0 : ti0;                          // storage tile index, walks along the sweep
+            // The record of a tile ({hs, cdt} when all its cells share them, NaN otherwise) tells which copies it
+            // needs.  The records of a segment are contiguous: each lane fetches one, 32 tiles per refill and one
+            // refill ahead, and they are handed round by shuffle (a load per tile in this loop would put its whole
+            // L2 latency on every tile whenever the ring is not full).
+            const double *recs = info ? p.tinfo + 2 * ((int64_t)c.g * nt + tile) : nullptr;
+            double rec_cur = 0.0, rec_nxt = 0.0;
+            if (info && lane < n) rec_nxt = __ldg(recs + 2 * dir * lane);
             const int nslots = READ_PSI ? 3 + c.nblk : 2;
-            mbar_wait(empty + st, (uint32_t)(((j / kStages) & 1) ^ 1));     // consumers released the stage
-            if (lane == 0) mbar_expect_tx(full + st, (uint32_t)(nslots * kTileBytes));
-            __syncwarp();
-            if (lane < nslots) {
-                const double *src = lane == 0 ? p.hs + goff : lane == 1 ? p.q + goff : lane == 2 ? p.cdt + goff
-                                                                                   : p.psi_in + c.row + (int64_t)(lane - 3) * p.Zp + off;
-                bulk_g2s(dst + lane * kTile, src, kTileBytes, full + st, pol);
+            for (int i = 0; i < n; ++i, tile += dir) {
+                if ((i & 31) == 0) {
+                    rec_cur = rec_nxt;
+                    if (info && i + 32 + lane < n) rec_nxt = __ldg(recs + 2 * dir * (i + 32 + lane));
+                }
+                const double rec_h = __shfl_sync(0xffffffffu, rec_cur, i & 31);
+                const bool uniform = info && rec_h == rec_h;
+                const int64_t off = (int64_t)tile * kTile;
+                double *dst = ring + (size_t)st * kStageLen;
+                const int64_t goff = (int64_t)c.g * p.Zp + off;
+                // a uniform tile needs neither the hs nor the cdt tile
+                const int ncopies = uniform ? nslots - (READ_PSI ? 2 : 1) : nslots;
+                mbar_wait(empty + st, ph ^ 1);                              // consumers released the stage
+                if (lane == 0) mbar_expect_tx(full + st, (uint32_t)(ncopies * kTileBytes + (info ? 16 : 0)));
+                __syncwarp();
+                if (lane < nslots && !(uniform && (lane == 0 || lane == 2))) {
+                    const double *src = lane == 0 ? p.hs + goff : lane == 1 ? p.q + goff : lane == 2 ? p.cdt + goff
+                                                                                       : p.psi_in + c.row + (int64_t)(lane - 3) * p.Zp + off;
+                    bulk_g2s(dst + lane * kTile, src, kTileBytes, full + st, pol);
+                }
+                if (info && lane == 31) bulk_g2s(dst + kSlots * kTile, recs + 2 * dir * i, 16, full + st, pol);
+                if (++st == kStages) { st = 0; ph ^= 1; }
             }
         }
     } else if (warp >= AC) {
         // ================= reducer warp(s): partial scalar flux of the block ===========================
         const int k0 = (warp - AC) * kPerRed;                               // this warp's double2 columns of a tile
         double hwv[AC];                                                     // half quadrature weights of the block's angles
-        for (int64_t j = 0; j < W; ++j, cur.advance()) {
-            if (cur.rb != c_rb) {
-                const int row = unit_row(p, cur.rb, mb);
-                row_setup<AC>(p, row, 0, c);
-                c_rb = cur.rb;
-                const int a0 = c.neg ? (row % p.nbg) * AC : p.n_neg + (row % p.nbg - p.nb_neg) * AC;
+        for (int k = 0; k < segs.count; ++k) {
+            int rb, ti0, n;
+            segs.get(k, rb, ti0, n);
+            const int row = unit_row(p, rb, mb);
+            row_setup<AC>(p, row, 0, c);
+            const int a0 = c.neg ? (row % p.nbg) * AC : p.n_neg + (row % p.nbg - p.nb_neg) * AC;
 #pragma unroll
-                for (int w = 0; w < AC; ++w) hwv[w] = w < c.nblk ? 0.5 * p.wgt[a0 + w] : 0.0;
-            }
-            const int64_t off = (int64_t)(c.neg ? nt - 1 - cur.ti : cur.ti) * kTile;
-            const int b = (int)(j & 1);
-            const double *rb_ = red + b * (AC * kTile) + lane * 2;
-            mbar_wait(red_full + b, (uint32_t)((j >> 1) & 1));
-            double2 acc[kPerRed];
+            for (int w = 0; w < AC; ++w) hwv[w] = w < c.nblk ? 0.5 * p.wgt[a0 + w] : 0.0;
+            const int step = c.neg ? -kTile : kTile;
+            double *dst = p.partial + c.poff + (int64_t)(c.neg ? nt - 1 - ti0 : ti0) * kTile + lane * 2 + k0 * 64;
+            for (int i = 0; i < n; ++i, dst += step) {
+                const double *rb_ = red + b * (AC * kTile) + lane * 2 + k0 * 64;
+                mbar_wait(red_full + b, bph);
+                // straight-line: every index is a compile-time constant.  Absent angles of a ragged block have
+                // weight 0 and their warps store zeros, so they are simply summed.
+                double2 acc[kPerRed];
 #pragma unroll
-            for (int k = 0; k < kPerRed; ++k) {
-                const double2 v = *reinterpret_cast<const double2 *>(rb_ + (k0 + k) * 64);
-                acc[k] = make_double2(hwv[0] * v.x, hwv[0] * v.y);
-            }
-#pragma unroll
-            for (int w = 1; w < AC; ++w)                                    // warps = angles in order (group.py:77)
-#pragma unroll
-                for (int k = 0; k < kPerRed; ++k) {
-                    if (w >= c.nblk) continue;          // idle warps of a ragged block worked on stale data (may be NaN)
-                    const double2 v = *reinterpret_cast<const double2 *>(rb_ + w * kTile + (k0 + k) * 64);
-                    acc[k].x = fma(hwv[w], v.x, acc[k].x);                  // 0.5*w_a*(in+out) = w_a*psi_mid
-                    acc[k].y = fma(hwv[w], v.y, acc[k].y);
+                for (int kk = 0; kk < kPerRed; ++kk) {
+                    const double2 v = *reinterpret_cast<const double2 *>(rb_ + kk * 64);
+                    acc[kk] = make_double2(hwv[0] * v.x, hwv[0] * v.y);
                 }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(red_empty + b);
-            double *dst = p.partial + c.poff + off + lane * 2;
 #pragma unroll
-            for (int k = 0; k < kPerRed; ++k) *reinterpret_cast<double2 *>(dst + (k0 + k) * 64) = acc[k];
+                for (int w = 1; w < AC; ++w)                                // warps = angles in order (group.py:77)
+#pragma unroll
+                    for (int kk = 0; kk < kPerRed; ++kk) {
+                        const double2 v = *reinterpret_cast<const double2 *>(rb_ + w * kTile + kk * 64);
+                        acc[kk].x = fma(hwv[w], v.x, acc[kk].x);            // 0.5*w_a*(in+out) = w_a*psi_mid
+                        acc[kk].y = fma(hwv[w], v.y, acc[kk].y);
+                    }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(red_empty + b);
+#pragma unroll
+                for (int kk = 0; kk < kPerRed; ++kk) *reinterpret_cast<double2 *>(dst + kk * 64) = acc[kk];
+                b ^= 1;
+                bph ^= (b == 0);
+            }
         }
     } else {
         // ================= compute warps ==============================================================
-        double carry = 0.0;
-        int64_t j = 0;
         const uint64_t pol = l2_policy(p.l2_hints ? 1 : 0);
-        for (int piece = 0; piece < 2; ++piece) {
-            const int64_t jend = piece == 0 ? (cur.len_last < W ? cur.len_last : W) : W;
-            for (; j < jend; ++j, cur.advance()) {
-                const int rb = cur.rb, ti = cur.ti;
-                if (rb != c_rb || ti == 0) {
-                    if (rb != c_rb) { row_setup<AC>(p, unit_row(p, rb, mb), warp, c); c_rb = rb; }
-                    carry = 0.0;                                            // vacuum boundary: group.py:48,54
-                    if (ti != 0) {                                          // continue a row another CTA started
-                        if (lane == 0 && warp < c.nblk) {
-                            while (ld_acquire(&sy->flag[cta - p.gs][warp]) != stamp) {}    // same member of the previous gang
-                            carry = sy->carry[cta - p.gs][warp];
-                        }
-                        carry = __shfl_sync(0xffffffffu, carry, 0);
+        const double nan_v = __longlong_as_double(0x7ff8000000000000LL);
+        UniCoef uc;                                                         // constants of the current (row, sigT) pair
+        for (int k = 0; k < segs.count; ++k) {
+            int rb, ti0, n;
+            segs.get(k, rb, ti0, n);
+            row_setup<AC>(p, unit_row(p, rb, mb), warp, c);
+            double u_h = nan_v;                                             // the hs value uc was built for (NaN: none)
+            double carry = 0.0;                                             // vacuum boundary: group.py:48,54
+            if (ti0 != 0) {                                                 // continue a row another CTA started
+                if (lane == 0 && warp < c.nblk) {
+                    while (ld_acquire(&sy->flag[cta - p.gs][warp]) != stamp) {}    // same member of the previous gang
+                    carry = sy->carry[cta - p.gs][warp];
+                }
+                carry = __shfl_sync(0xffffffffu, carry, 0);
+            }
+            const bool present = warp < c.nblk;
+            const int step = c.neg ? -kTile : kTile;
+            int64_t off = (int64_t)(c.neg ? nt - 1 - ti0 : ti0) * kTile;    // first cell of the tile
+            double *pout = WRITE_PSI ? p.psi_out + c.row + (int64_t)warp * p.Zp + off + lane * 2 : nullptr;
+            for (int i = 0; i < n; ++i, off += step) {
+                const double *stage = ring + (size_t)st * kStageLen + lane * 2;
+                double cb[kL], f[kL];
+                mbar_wait(full + st, ph);
+                double2 rec = make_double2(nan_v, 0.0);
+                if (info) rec = *reinterpret_cast<const double2 *>(ring + (size_t)st * kStageLen + kSlots * kTile);
+                if (rec.x == rec.x) {
+                    // uniform tile: constant coefficients (rebuilt when the row or the region changes)
+                    if (!(rec.x == u_h)) {
+                        if (c.neg) uni_setup<true>(c.m, c.two_m, rec.x, lane, s_ap[warp], uc);
+                        else uni_setup<false>(c.m, c.two_m, rec.x, lane, s_ap[warp], uc);
+                        u_h = rec.x;
+                    }
+                    uni_maps<READ_PSI>(stage + kTile, stage + (3 + warp) * kTile, rec.y, uc.r, cb);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty + st);                 // stage is in registers: release it
+                    if (c.neg) uni_solve<true>(cb, uc, carry, f, lane);
+                    else uni_solve<false>(cb, uc, carry, f, lane);
+                } else {
+                    double ca[kL];
+                    tile_maps<READ_PSI>(stage, stage + kTile, stage + 2 * kTile, stage + (3 + warp) * kTile, c.m, c.two_m, ca, cb);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty + st);                 // stage is in registers: release it
+                    if (c.neg) tile_solve<true>(ca, cb, carry, f, lane);
+                    else tile_solve<false>(ca, cb, carry, f, lane);
+                    if (off + kTile > p.Z) {                                // only the last tile holds padding cells:
+#pragma unroll
+                        for (int jj = 0; jj < kL; ++jj)                     // exact zeros there, in psi and in the flux
+                            if (off + lane * kL + jj >= p.Z) f[jj] = 0.0;
                     }
                 }
-                const int st = (int)(j % kStages), b = (int)(j & 1);
-                const int64_t off = (int64_t)(c.neg ? nt - 1 - ti : ti) * kTile;
-                const double *stage = ring + (size_t)st * kSlots * kTile + lane * 2;
-                double ca[kL], cb[kL], f[kL];
-                mbar_wait(full + st, (uint32_t)((j / kStages) & 1));
-                tile_maps<READ_PSI>(stage, stage + kTile, stage + 2 * kTile, stage + (3 + warp) * kTile, c.m, c.two_m, ca, cb);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty + st);                     // stage is in registers: release it
-                if (c.neg) tile_solve<true>(ca, cb, carry, f, lane);
-                else tile_solve<false>(ca, cb, carry, f, lane);
-                if (off + kTile > p.Z) {                                    // only the last tile holds padding cells:
+                if (WRITE_PSI) {
+                    if (present) {
 #pragma unroll
-                    for (int jj = 0; jj < kL; ++jj)                         // exact zeros there, in psi and in the flux
-                        if (off + lane * kL + jj >= p.Z) f[jj] = 0.0;
+                        for (int kk = 0; kk < 4; ++kk)
+                            st_stream(pout + kk * 64, make_double2(0.5 * f[2 * kk], 0.5 * f[2 * kk + 1]), pol);
+                    }
+                    pout += step;
                 }
-                if (WRITE_PSI && warp < c.nblk) {
-                    double *pout = p.psi_out + c.row + (int64_t)warp * p.Zp + off + lane * 2;
+                if (!present) {                                             // angle slot a ragged block does not have:
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) st_stream(pout + k * 64, make_double2(0.5 * f[2 * k], 0.5 * f[2 * k + 1]), pol);
+                    for (int jj = 0; jj < kL; ++jj) f[jj] = 0.0;            // whatever came out of stale memory is dropped
                 }
                 double *rw = red + b * (AC * kTile) + warp * kTile + lane * 2;
-                mbar_wait(red_empty + b, (uint32_t)(((j >> 1) & 1) ^ 1));
+                mbar_wait(red_empty + b, bph ^ 1);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)                                 // in+out; the reducer applies the weights
-                    *reinterpret_cast<double2 *>(rw + k * 64) = make_double2(f[2 * k], f[2 * k + 1]);
+                for (int kk = 0; kk < 4; ++kk)                              // in+out; the reducer applies the weights
+                    *reinterpret_cast<double2 *>(rw + kk * 64) = make_double2(f[2 * kk], f[2 * kk + 1]);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(red_full + b);
+                if (++st == kStages) { st = 0; ph ^= 1; }
+                b ^= 1;
+                bph ^= (b == 0);
             }
             // after the head piece: hand the carries to the CTA that continues this row
-            if (piece == 0 && publishes && lane == 0 && warp < c.nblk) {
+            if (k == 0 && publishes && lane == 0 && present) {
                 sy->carry[cta][warp] = carry;
                 st_release(&sy->flag[cta][warp], stamp);
             }
@@ -343,6 +403,31 @@ __global__ void __launch_bounds__(StageCfg<AC>::threads, AC == kACsmall ? 2 : 1)
     if (tid == 0) {
         __threadfence();
         if (atomicInc(&sy->done, gridDim.x - 1) == gridDim.x - 1) atomicAdd(&sy->epoch, 1u);
+    }
+}
+
+// One record per (group, tile): {hs, cdt} of the tile when all its 256 cells are real (no padding) and share
+// bitwise-identical values, {NaN, NaN} otherwise.  One warp per record.
+__global__ void tile_info_kernel(const double *__restrict__ hs, const double *__restrict__ cdt, int64_t Z, int64_t Zp, int G,
+                                 double *__restrict__ info)
+{
+    const int64_t nt = Zp / kTile;
+    const int64_t rec = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (rec >= (int64_t)G * nt) return;
+    const int64_t g = rec / nt, t = rec % nt;
+    const double *h = hs + g * Zp + t * kTile, *c = cdt ? cdt + g * Zp + t * kTile : nullptr;
+    const double h0 = h[0], c0 = c ? c[0] : 0.0;
+    bool same = (t + 1) * kTile <= Z;
+    for (int i = lane; i < kTile; i += 32) {
+        same = same && __double_as_longlong(h[i]) == __double_as_longlong(h0);
+        if (c) same = same && __double_as_longlong(c[i]) == __double_as_longlong(c0);
+    }
+    same = __all_sync(0xffffffffu, same) && h0 == h0 && c0 == c0;
+    if (lane == 0) {
+        const double nan_v = __longlong_as_double(0x7ff8000000000000LL);
+        info[2 * rec] = same ? h0 : nan_v;
+        info[2 * rec + 1] = same ? c0 : nan_v;
     }
 }
 
@@ -427,7 +512,8 @@ static int launch_variant(const SweepArgs &p_in, const ae_ctrl *ctrl, int gate, 
     SweepArgs p = p_in;
     constexpr int slots = RD ? 3 + AC : 2;
     constexpr int threads = StageCfg<AC>::threads;
-    const size_t smem = (size_t)(StageCfg<AC>::stages * slots + 2 * AC) * kTileBytes + (2 * StageCfg<AC>::stages + 4) * sizeof(uint64_t);
+    constexpr int stages = StageCfg<AC, RD>::stages;
+    const size_t smem = (size_t)(stages * slots + 2 * AC) * kTileBytes + stages * 16 + (2 * stages + 4) * sizeof(uint64_t);
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
         AE_CUDA(cudaFuncSetAttribute((const void *)sweep_kernel<AC, RD, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -483,6 +569,8 @@ int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double
     p.Z = s->Z;
     static const char *hints = getenv("AE_SWEEP_L2_HINTS");
     p.l2_hints = !(hints && hints[0] == '0');
+    static const char *nofast = getenv("AE_SWEEP_NO_FAST");                // A/B and parity tests: general path only
+    p.tinfo = (nofast && nofast[0] == '1') ? nullptr : s->tile_info;
     return ac == kACbig ? launch_shape<kACbig>(p, ctrl, gate, st) : launch_shape<kACsmall>(p, ctrl, gate, st);
 }
 
@@ -494,7 +582,7 @@ extern "C" int32_t ae_partial_count(int32_t A, int32_t n_neg)
     return (n_neg + blk - 1) / blk + (A - n_neg + blk - 1) / blk;
 }
 
-// Host-side replay of the kernel's work assignment (same Cursor / unit_row / plan_grid code): the (row block,
+// Host-side replay of the kernel's work assignment (same Segments / unit_row / plan_grid code): the (row block,
 // tile index in sweep order) pairs logical CTA `cta` visits, in order.  Test hook: no GPU needed.
 extern "C" int64_t ae_sweep_plan(int32_t A, int32_t n_neg, int32_t G, int64_t Zp, int32_t resident_ctas, int32_t cta,
                                  int32_t *grid_out, int32_t *gang_out, int32_t *row_blocks, int32_t *tiles, int64_t cap)
@@ -509,18 +597,32 @@ extern "C" int64_t ae_sweep_plan(int32_t A, int32_t n_neg, int32_t G, int64_t Zp
     const int64_t nt = Zp / ae::kTile, NC = grid / p.gs;
     const int gang = cta / p.gs, mb = cta - gang * p.gs;
     const int64_t t0 = gang * p.total_tiles / NC, t1 = (gang + 1) * p.total_tiles / NC, W = t1 - t0;
-    ae::Cursor cur;
-    cur.init(t0, t1, (int)nt);
-    for (int64_t j = 0; j < W; ++j, cur.advance()) {
-        if (j < cap) {
-            if (row_blocks) row_blocks[j] = ae::unit_row(p, cur.rb, mb);
-            if (tiles) tiles[j] = cur.ti;
+    ae::Segments segs;
+    segs.init(t0, t1, (int)nt);
+    int64_t j = 0;
+    for (int k = 0; k < segs.count; ++k) {
+        int rb, ti0, n;
+        segs.get(k, rb, ti0, n);
+        for (int i = 0; i < n; ++i, ++j) {
+            if (j < cap) {
+                if (row_blocks) row_blocks[j] = ae::unit_row(p, rb, mb);
+                if (tiles) tiles[j] = ti0 + i;
+            }
         }
     }
     return W;
 }
 
 extern "C" int64_t ae_sweep_sync_bytes(void) { return (int64_t)sizeof(ae::SweepSync); }
+
+extern "C" int ae_tile_info(const double *hs, const double *cdt, int64_t Z, int64_t Zp, int32_t G, double *info, void *stream)
+{
+    if (!hs || !info || Z < 1 || Zp < Z || Zp % ae::kTile || G < 1) { ae::set_error("ae_tile_info: bad argument"); return AE_BAD_ARG; }
+    const int64_t warps = (int64_t)G * (Zp / ae::kTile);
+    ae::tile_info_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(hs, cdt, Z, Zp, G, info);
+    AE_CUDA(cudaGetLastError());
+    return AE_OK;
+}
 
 extern "C" int ae_sweep_set(const ae_slab *s, const double *q, const double *psi_in, double *psi_out,
                             double *partial, void *sync, void *stream)

@@ -148,7 +148,7 @@ class SlabDevice:
     """
 
     def __init__(self, Z, hx, mu, weight, mat, total, scat, chi, nusf, invspeed, dt=None, s_ext=None,
-                 angles=None, comm: Comm | None = None, device=None, batch=None):
+                 angles=None, comm: Comm | None = None, device=None, batch=None, flags=0):
         torch = _torch()
         self.torch = torch
         self.lib = _lib.load()
@@ -196,6 +196,7 @@ class SlabDevice:
         self._phi_bufs = [torch.zeros(n, **f64), torch.zeros(n, **f64)]      # ping-pong pair, see `phi`
         self.phi_outer = torch.zeros(n, **f64)
         self.reduced = torch.zeros(n, **f64) if comm is not None else None
+        self.phi_fixed = torch.zeros(n, **f64) if dt is not None else None
         self.base = torch.zeros(n, **f64)
         self.q0 = torch.zeros(n, **f64)
         self.q1 = torch.zeros(n, **f64)
@@ -210,11 +211,15 @@ class SlabDevice:
                                 self.t_w.data_ptr(), self.t_mat.data_ptr(), self.t_scat.data_ptr(),
                                 self.t_chi.data_ptr(), self.t_nusf.data_ptr(), self.t_hs.data_ptr(),
                                 self.t_cdt.data_ptr() if self.t_cdt is not None else None,
-                                self.t_sext.data_ptr() if self.t_sext is not None else None)
+                                self.t_sext.data_ptr() if self.t_sext is not None else None, None)
+        self._build_tile_info()
         self.work = _lib.AeWork(self._phi_bufs[0].data_ptr(), self._phi_bufs[1].data_ptr(), self.phi_outer.data_ptr(),
                                 self.base.data_ptr(), self.q0.data_ptr(), self.q1.data_ptr(), self.partial.data_ptr(),
-                                self.reduced.data_ptr() if self.reduced is not None else None, self.scratch.data_ptr(), self.ctrl.data_ptr(), self.ctrl_host.data_ptr(),
-                                self.sync.data_ptr(), comm.handle.value if comm is not None else None, self.P, int(batch))
+                                self.reduced.data_ptr() if self.reduced is not None else None,
+                                self.phi_fixed.data_ptr() if self.phi_fixed is not None else None,
+                                self.scratch.data_ptr(), self.ctrl.data_ptr(), self.ctrl_host.data_ptr(),
+                                self.sync.data_ptr(), comm.handle.value if comm is not None else None, self.P, int(batch),
+                                int(flags), 0)
         self.last_q_index = 0
 
     @classmethod
@@ -226,9 +231,18 @@ class SlabDevice:
                   np.zeros((1, G)), np.zeros((1, G)), np.zeros((1, G)))
         dev.t_hs = dev._upload(layout.to_storage((0.5 * sigT).T, dev.Z))
         dev.slab.hs = dev.t_hs.data_ptr()
+        dev._build_tile_info()
         return dev
 
     # ---- plumbing ------------------------------------------------------------------------
+    def _build_tile_info(self):
+        """Uniform-tile records of the current hs / cdt arrays (ae_tile_info): tiles whose cells share one sigT
+        take the sweep's constant-coefficient path."""
+        self.t_tinfo = self.torch.empty(2 * self.G * (self.Zp // _lib.AE_TILE), dtype=self.torch.float64, device=self.dev)
+        _lib.check(self.lib.ae_tile_info(self.t_hs.data_ptr(), self.t_cdt.data_ptr() if self.t_cdt is not None else None,
+                                         self.Z, self.Zp, self.G, self.t_tinfo.data_ptr(), self.stream))
+        self.slab.tile_info = self.t_tinfo.data_ptr()
+
     @property
     def phi(self):
         """[G][Zp] newest scalar-flux iterate.  The C side ping-pongs two buffers and keeps work.phi on

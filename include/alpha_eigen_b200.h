@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define AE_ABI_VERSION 1
+#define AE_ABI_VERSION 2
 #define AE_TILE 256          /* cells per tile */
 #define AE_LANE_CELLS 8      /* consecutive cells owned by one lane */
 
@@ -65,6 +65,9 @@ typedef struct ae_slab {
     const double *hs;        /* [G][Zp] 0.5*sigT seen by the sweep (group.py:50; time_unit.py:24 adds 1/(v dt)) */
     const double *cdt;       /* [G][Zp] inv_speed/dt (time_unit.py:23) or NULL in steady state */
     const double *s_ext;     /* [G][Zp] fixed external source (group.source at time_unit.py:19) or NULL */
+    const double *tile_info; /* [G][Zp/AE_TILE][2] records written by ae_tile_info for THESE hs / cdt arrays, or NULL.
+                                Lets the sweep skip the per-cell reciprocals in tiles whose cells share one sigT
+                                (material regions, slab.py:33-56); results are bit-identical with and without it */
 } ae_slab;
 
 /* Mutable buffers, all caller-allocated (torch owns the memory). */
@@ -78,6 +81,11 @@ typedef struct ae_work {
     double *q0, *q1;         /* [G][Zp] ping-pong isotropic sweep source */
     double *partial;         /* [P][G][Zp] per-angle-block partial scalar flux */
     double *reduced;         /* [G][Zp] sum of the partials, reduce-scattered over ranks (multi-GPU only, else NULL) */
+    double *phi_fixed;       /* [G][Zp] time steps only: scalar flux driven by the previous step's angular flux alone,
+                                sum_a w_a L_a(cdt*psi^n).  The sweep is linear in its source and this part of the source
+                                does not change inside a step (time_unit.py:23), so it is swept ONCE per step and the
+                                inner iterations sweep the isotropic source only (no psi traffic).  May be NULL when
+                                no time-dependent entry point is used */
     double *norm_scratch;    /* [4 * ae_norm_blocks(Zp) + 2 * G] */
     ae_ctrl *ctrl;           /* device */
     ae_ctrl *ctrl_host;      /* pinned host */
@@ -85,7 +93,13 @@ typedef struct ae_work {
     void *comm;              /* ae_comm handle for the flux exchange, or NULL (single GPU) */
     int32_t P;               /* ae_partial_count(A, n_neg) */
     int32_t batch;           /* source iterations launched between host polls (>=1) */
+    int32_t flags;           /* AE_WORK_* bits, 0 for the default behaviour */
+    int32_t reserved;
 } ae_work;
+
+#define AE_WORK_NO_FUSED 1   /* never take the fused small-slab kernels (streaming kernels + host-driven loops only) */
+#define AE_WORK_REREAD_PSI 2 /* time steps: every inner sweep re-reads psi^n (the literal scheme of time_unit.py:53)
+                                instead of sweeping its contribution once per step into phi_fixed */
 
 /* ---- introspection ---------------------------------------------------------------- */
 int ae_abi_version(void);
@@ -104,6 +118,9 @@ int64_t ae_norm_blocks(int64_t Zp);
  */
 int ae_sweep_set(const ae_slab *s, const double *q, const double *psi_in, double *psi_out,
                  double *partial, void *sync, void *stream);
+/* Uniform-tile records for ae_slab.tile_info: info[g][t] = {hs, cdt} of tile t of group g when its 256 cells are all
+ * real and share bitwise-identical hs (and cdt, when cdt != NULL) values, {NaN, NaN} otherwise.  hs / cdt: [G][Zp]. */
+int ae_tile_info(const double *hs, const double *cdt, int64_t Z, int64_t Zp, int32_t G, double *info, void *stream);
 /* `sync` is a device buffer of ae_sweep_sync_bytes() bytes, zero-filled ONCE by the caller: the
  * mailbox through which persistent CTAs hand running boundary fluxes to each other.  One buffer
  * per stream of sweeps (ae_work carries its own). */

@@ -19,14 +19,14 @@ def test_header_symbols_exported():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ae_abi_version() == 1
+    assert lib.ae_abi_version() == 2
 
 
 def test_struct_sizes_match_header():
     import ctypes as C
     assert C.sizeof(_lib.AeCtrl) == 64
-    assert C.sizeof(_lib.AeSlab) == 16 + 16 + 9 * 8
-    assert C.sizeof(_lib.AeWork) == 13 * 8 + 8
+    assert C.sizeof(_lib.AeSlab) == 16 + 16 + 10 * 8
+    assert C.sizeof(_lib.AeWork) == 14 * 8 + 16
 
 
 @pytest.mark.parametrize("Z", [1, 7, 255, 256, 257, 450, 1800, 5000])

@@ -523,3 +523,71 @@ def test_ragged_angle_block_ignores_stale_shared_memory():
     got = dev.cells_to_host(phi)
     assert np.all(np.isfinite(got))
     assert _rel(got, phi_o) < 1e-13
+
+
+# ------------------------------------------------------------- round 2: uniform tiles, phi_fixed ----
+@pytest.mark.parametrize("Z,A,G,td", [(3000, 8, 2, False), (2560, 16, 3, True), (8000, 64, 5, True), (5000, 96, 3, False),
+                                      (1300, 6, 1, True)])
+def test_uniform_tile_fast_path_is_bit_identical_to_general_path(Z, A, G, td):
+    """Tiles whose cells share one sigT take the constant-coefficient path of the sweep (ae_tile_info records);
+    it is built from the same operation sequence as the general path, so with and without the records the angular
+    and scalar fluxes must agree BIT FOR BIT (steady and time-dependent in-place forms, ganged shapes included)."""
+    p = _mg_problem(Z, A, G, seed=Z % 89 + A)
+    dev = _device(p, dt=0.1 if td else None)
+    info = dev.t_tinfo.cpu().numpy().reshape(G, dev.Zp // 256, 2)
+    uniform = np.isfinite(info[..., 0])
+    assert uniform.any() and not uniform.all()          # material interfaces and the padded tile are general tiles
+    q = dev.cells_to_device(p["rs"].rand(Z, G) + 0.05)
+    psi0 = p["rs"].rand(Z, A, G)
+    out = []
+    for use_info in (True, False):
+        dev.slab.tile_info = dev.t_tinfo.data_ptr() if use_info else None
+        psi = dev.psi_to_device(psi0)
+        phi = dev.sweep_set(q, psi_in=psi if td else None, psi_out=psi)
+        ro = dev.sweep_set(q, psi_in=psi if td else None)                # read-only / phi-only variant
+        out.append((phi.cpu().numpy(), psi.cpu().numpy(), ro.cpu().numpy()))
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("Z,A,G,flags", [(700, 6, 3, 1), (700, 6, 3, 3), (2600, 16, 2, 1), (450, 4, 1, 1)])
+def test_streaming_time_march_with_fixed_flux_matches_oracle(Z, A, G, flags):
+    """The streaming (host-driven) time march: psi^n's contribution to the flux is swept once per step
+    (ae_work.phi_fixed) and the inner iterations sweep the isotropic source alone; flags=3 is the literal scheme
+    that re-reads psi^n in every inner sweep.  Both against the oracle: same iteration counts, flux 1e-10."""
+    from oracle import ae_oracle as orc
+    steps, dt = 3, 0.1
+    p = _mg_problem(Z, A, G, seed=Z + G)
+    psi0 = p["rs"].rand(Z, A, G)
+    s_ext = p["rs"].rand(Z, G) * 0.1
+    res = orc.time_march(p["mu"], p["weight"], p["hx"], p["tables"], s_ext, psi0, dt, steps, want_psi_snap=False)
+    assert res["status"] == 0
+    dev = _device(p, dt=dt, s_ext=s_ext, flags=flags)
+    psi = dev.psi_to_device(psi0)
+    torch = dev.torch
+    phi_snap = torch.zeros(steps * dev.G * dev.Zp, dtype=torch.float64, device=dev.dev)
+    st, outer, inner = dev.time_march(psi, steps, 1e-10, None, phi_snap)
+    assert st == 0
+    assert list(outer) == list(res["outer"]) and list(inner) == list(res["inner"])
+    assert _rel(dev.psi_to_host(psi), res["psi_last"][:, dev.angles, :]) < 1e-10
+    assert _rel(dev.cells_to_host(dev.phi), res["phi_last"]) < 1e-10
+    for s_ in range(steps):
+        row = phi_snap[s_ * dev.G * dev.Zp:(s_ + 1) * dev.G * dev.Zp]
+        assert _rel(dev.cells_to_host(row), res["phi_snap"][:, :, s_]) < 1e-10
+
+
+def test_time_dependent_source_iteration_streaming_fixed_flux():
+    """ae_source_iteration with psi_in on the streaming path: computes phi_fixed itself, same answer and iteration
+    count as the literal scheme and as the fused small-slab kernel."""
+    Z, A, G = 900, 8, 2
+    p = _mg_problem(Z, A, G, seed=5)
+    psi0 = p["rs"].rand(Z, A, G)
+    base = p["rs"].rand(Z, G)
+    got = []
+    for flags in (0, 1, 3):
+        dev = _device(p, dt=0.1, flags=flags)
+        st, it = dev.source_iteration(dev.cells_to_device(base), dev.psi_to_device(psi0), 0.0, 1e-10, 100)
+        assert st == 0
+        got.append((it, dev.cells_to_host(dev.phi)))
+    assert got[0][0] == got[1][0] == got[2][0]
+    assert _rel(got[1][1], got[0][1]) < 1e-12 and _rel(got[2][1], got[0][1]) < 1e-12
