@@ -56,6 +56,7 @@ SYMBOLS = {
     "ae_partial_count": (C.c_int32, [C.c_int32, C.c_int32]),
     "ae_norm_blocks": (C.c_int64, [C.c_int64]),
     "ae_sweep_set": (C.c_int, [C.POINTER(AeSlab), _P, _P, _P, _P, _P, _P]),
+    "ae_sweep_set_phi": (C.c_int, [C.POINTER(AeSlab), _P, _P, _P, c_ip, _P]),
     "ae_tile_info": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int32, _P, _P]),
     "ae_sweep_sync_bytes": (C.c_int64, []),
     "ae_sweep_plan": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, c_ip, c_ip, c_ip, c_ip,

@@ -10,7 +10,7 @@
 
 namespace ae {
 int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double *psi_out, double *partial,
-                 void *sync, const ae_ctrl *ctrl, int gate, cudaStream_t st);
+                 void *sync, const ae_ctrl *ctrl, int gate, int *P_out, cudaStream_t st);
 int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, const double *fixed, const double *phi_in,
                     double *phi_out, double *q_next, int init, double cold, double tol, int iteration, int gate, cudaStream_t st);
 int launch_fission_base(const ae_slab *s, ae_work *w, const double *phi, double *base, int with_ext, cudaStream_t st);
@@ -23,9 +23,9 @@ int comm_all_gather_rows(void *comm, double *rows, int G, int64_t Zp, int with_p
 
 // multi-GPU: local sum of the angle-block partials, then reduce-scatter by rows so that this rank holds the
 // rank-summed flux of ITS cell range in w->reduced (the one exchange of the solve)
-static int exchange_partials(const ae_slab *s, ae_work *w, cudaStream_t st)
+static int exchange_partials(const ae_slab *s, ae_work *w, int P, cudaStream_t st)
 {
-    AE_TRY(ae_reduce_partials(s, w->partial, w->P, w->reduced, st));
+    AE_TRY(ae_reduce_partials(s, w->partial, P, w->reduced, st));
     return comm_reduce_scatter_rows(w->comm, w->reduced, s->G, s->Zp, st);
 }
 int launch_k_update(const ae_slab *s, ae_work *w, double tol, int iteration, cudaStream_t st);
@@ -64,7 +64,7 @@ static int compute_fixed(const ae_slab *s, ae_work *w, const double *psi_in, cud
 {
     if (!w->phi_fixed) { set_error("time-dependent solve: ae_work.phi_fixed is missing"); return AE_BAD_ARG; }
     AE_CUDA(cudaMemsetAsync(w->q1, 0, (size_t)s->G * s->Zp * sizeof(double), st));        // q1 is free until the first update
-    AE_TRY(launch_sweep(s, w->q1, psi_in, nullptr, w->partial, w->sweep_sync, w->ctrl, 0, st));
+    AE_TRY(launch_sweep(s, w->q1, psi_in, nullptr, w->partial, w->sweep_sync, w->ctrl, 0, nullptr, st));
     AE_TRY(ae_reduce_partials(s, w->partial, w->P, w->phi_fixed, st));
     if (w->comm) AE_TRY(comm_reduce_scatter_rows(w->comm, w->phi_fixed, s->G, s->Zp, st)); // valid on this rank's cell range
     return AE_OK;
@@ -109,15 +109,16 @@ static int source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, 
         for (int b = 0; b < nb; ++b) {
             const int i = it + b;                       // 0-based; reference iteration number is i+1
             const int gate = b > 0;                     // first of a batch always runs
-            AE_TRY(launch_sweep(s, q[i & 1], sweep_psi, nullptr, w->partial, w->sweep_sync, w->ctrl, gate, st));
+            int Pw = w->P;                              // partial slabs this sweep writes (fewer from the phi-only kernel)
+            AE_TRY(launch_sweep(s, q[i & 1], sweep_psi, nullptr, w->partial, w->sweep_sync, w->ctrl, gate, &Pw, st));
             if (w->comm) {
                 // angle-sharded sweeps, cell-sharded update: reduce-scatter the flux, update 1/N of the cells,
                 // all-gather the new source (inside launch_finalize)
-                AE_TRY(exchange_partials(s, w, st));
+                AE_TRY(exchange_partials(s, w, Pw, st));
                 AE_TRY(launch_finalize(s, w, w->reduced, 1, fixed, phi[i & 1], phi[(i + 1) & 1], q[(i + 1) & 1], 0, cold, tol,
                                        i + 1, gate, st));
             } else {
-                AE_TRY(launch_finalize(s, w, w->partial, w->P, fixed, phi[i & 1], phi[(i + 1) & 1], q[(i + 1) & 1], 0, cold, tol,
+                AE_TRY(launch_finalize(s, w, w->partial, Pw, fixed, phi[i & 1], phi[(i + 1) & 1], q[(i + 1) & 1], 0, cold, tol,
                                        i + 1, gate, st));
             }
         }
@@ -140,7 +141,7 @@ extern "C" int ae_exchange_partials(const ae_slab *s, ae_work *w, void *stream)
 {
     AE_TRY(check_work(s, w, "ae_exchange_partials"));
     if (!w->comm) { set_error("ae_exchange_partials: no communicator"); return AE_BAD_ARG; }
-    return exchange_partials(s, w, (cudaStream_t)stream);
+    return exchange_partials(s, w, w->P, (cudaStream_t)stream);
 }
 
 extern "C" int ae_flux_update(const ae_slab *s, ae_work *w, const double *partial, int32_t P, double *q_next, double tol,
@@ -189,7 +190,7 @@ extern "C" int ae_power_iteration(const ae_slab *s, ae_work *w, double tol, int3
     if (status == AE_OK && psi_out) {
         // angle.psi_midpoint of the last sweep executed (group.py:59): replay it with the same source
         const double *q = last_q ? w->q1 : w->q0;
-        AE_TRY(launch_sweep(s, q, nullptr, psi_out, w->partial, w->sweep_sync, w->ctrl, 0, st));
+        AE_TRY(launch_sweep(s, q, nullptr, psi_out, w->partial, w->sweep_sync, w->ctrl, 0, nullptr, st));
         AE_CUDA(cudaStreamSynchronize(st));
     }
     if (k_new) *k_new = kn;
@@ -227,7 +228,7 @@ extern "C" int ae_time_step(const ae_slab *s, ae_work *w, const double *psi_prev
     if (status != AE_OK) return status;
     // commit: replay the last sweep with its own source, now writing psi (time_unit.py:26-27)
     const double *q = last_q ? w->q1 : w->q0;
-    AE_TRY(launch_sweep(s, q, psi_prev, psi_next, w->partial, w->sweep_sync, w->ctrl, 0, st));
+    AE_TRY(launch_sweep(s, q, psi_prev, psi_next, w->partial, w->sweep_sync, w->ctrl, 0, nullptr, st));
     return AE_OK;
 }
 

@@ -337,7 +337,32 @@ __global__ void __launch_bounds__(StageCfg<AC>::threads, AC == kACsmall ? 2 : 1)
             const int step = c.neg ? -kTile : kTile;
             int64_t off = (int64_t)(c.neg ? nt - 1 - ti0 : ti0) * kTile;    // first cell of the tile
             double *pout = WRITE_PSI ? p.psi_out + c.row + (int64_t)warp * p.Zp + off + lane * 2 : nullptr;
-            for (int i = 0; i < n; ++i, off += step) {
+            // stores one tile's in+out fluxes: psi (when written) and the block's reduction buffer
+            auto emit = [&](double (&f)[kL]) {
+                if (WRITE_PSI) {
+                    if (present) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            st_stream(pout + kk * 64, make_double2(0.5 * f[2 * kk], 0.5 * f[2 * kk + 1]), pol);
+                    }
+                    pout += step;
+                }
+                if (!present) {                                             // angle slot a ragged block does not have:
+#pragma unroll
+                    for (int jj = 0; jj < kL; ++jj) f[jj] = 0.0;            // whatever came out of stale memory is dropped
+                }
+                double *rw = red + b * (AC * kTile) + warp * kTile + lane * 2;
+                mbar_wait(red_empty + b, bph ^ 1);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)                              // in+out; the reducer applies the weights
+                    *reinterpret_cast<double2 *>(rw + kk * 64) = make_double2(f[2 * kk], f[2 * kk + 1]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(red_full + b);
+                b ^= 1;
+                bph ^= (b == 0);
+            };
+            int i = 0;
+            while (i < n) {
                 const double *stage = ring + (size_t)st * kStageLen + lane * 2;
                 double cb[kL], f[kL];
                 mbar_wait(full + st, ph);
@@ -368,28 +393,10 @@ __global__ void __launch_bounds__(StageCfg<AC>::threads, AC == kACsmall ? 2 : 1)
                             if (off + lane * kL + jj >= p.Z) f[jj] = 0.0;
                     }
                 }
-                if (WRITE_PSI) {
-                    if (present) {
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            st_stream(pout + kk * 64, make_double2(0.5 * f[2 * kk], 0.5 * f[2 * kk + 1]), pol);
-                    }
-                    pout += step;
-                }
-                if (!present) {                                             // angle slot a ragged block does not have:
-#pragma unroll
-                    for (int jj = 0; jj < kL; ++jj) f[jj] = 0.0;            // whatever came out of stale memory is dropped
-                }
-                double *rw = red + b * (AC * kTile) + warp * kTile + lane * 2;
-                mbar_wait(red_empty + b, bph ^ 1);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)                              // in+out; the reducer applies the weights
-                    *reinterpret_cast<double2 *>(rw + kk * 64) = make_double2(f[2 * kk], f[2 * kk + 1]);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(red_full + b);
+                emit(f);
                 if (++st == kStages) { st = 0; ph ^= 1; }
-                b ^= 1;
-                bph ^= (b == 0);
+                ++i;
+                off += step;
             }
             // after the head piece: hand the carries to the CTA that continues this row
             if (k == 0 && publishes && lane == 0 && present) {
@@ -399,6 +406,269 @@ __global__ void __launch_bounds__(StageCfg<AC>::threads, AC == kACsmall ? 2 : 1)
         }
     }
     // last CTA out advances the epoch (stamps of this launch can never match the next one's)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicInc(&sy->done, gridDim.x - 1) == gridDim.x - 1) atomicAdd(&sy->epoch, 1u);
+    }
+}
+
+
+// ---- phi-only sweeps: several rows per warp -----------------------------------------------------------------------
+// The inner iterations of a time step and all steady-state iterations sweep the isotropic source only (no psi in or
+// out).  Through sweep_kernel (one angle per warp) they hit two walls at about the same height (ncu, C3): the
+// SHARED-MEMORY pipe (84 %: every angle-warp reads the block's 2 KB source tile and pushes 2 KB of fluxes through the
+// reduction buffer) and, once that traffic is cut, the LATENCY of the fold / scan chain (27 dependent FP64 and shuffle
+// steps per tile, ~800 cycles, with only 16 such chains in flight per SM; FP64 pipe 27 %).  Here a compute warp carries
+// R angles of a block of 8R (w, w + 8, ...): one read of the source tile feeds R rows, their weighted fluxes are added
+// in registers before they go to the reduction buffer, and the R chains advance in lock step, so 8R chains per SM are
+// in flight with the registers of 10 warps.  Same segments, ring, hand-offs and uniform-tile records as sweep_kernel;
+// a block's partial flux is sum_w (sum_r w_a f_a), and there are ceil(n/8R) blocks per direction -- the launcher
+// reports how many partial slabs it wrote.
+constexpr int kPhiCW = 8;                        // compute warps
+#ifndef AE_PHI_ROWS
+#define AE_PHI_ROWS 4
+#endif
+#ifndef AE_PHI_STAGES
+#define AE_PHI_STAGES 8
+#endif
+#ifndef AE_PHI_RED_BUFS
+#define AE_PHI_RED_BUFS 4        // depth of the reduction ring: absorbs the skew between the compute warps and the reducer
+#endif
+constexpr int kPhiR = AE_PHI_ROWS, kPhiAC = kPhiCW * kPhiR;
+constexpr int kPhiStages = AE_PHI_STAGES, kPhiRB = AE_PHI_RED_BUFS;
+constexpr int kPhiStageLen = 2 * kTile + 2;      // hs tile (general tiles only), q tile, record
+constexpr int kPhiThreads = (kPhiCW + 2) * 32;
+static_assert(kPhiAC <= kMaxBlk, "mailbox slots per CTA");
+
+// General tile of the rows-per-warp kernel (region interface, padded last tile): rows one after the other with the
+// per-cell arithmetic of sweep_kernel, weighted sum written straight to the reduction slot.  Out of line, so that
+// its registers do not count against the lock-step path.  m / hw / carry: R entries (carry in and out).
+__device__ __noinline__ void phi_general_tile(const double *stage, const double *m, const double *hw, double *carry, bool neg,
+                                              int lane, int64_t off, int64_t Z, double *rw, uint64_t *empty_bar,
+                                              uint64_t *red_empty_bar, uint32_t red_parity)
+{
+    double g[kL];
+#pragma unroll 1
+    for (int r = 0; r < kPhiR; ++r) {
+        double ca[kL], cb[kL], f[kL];
+        tile_maps<false>(stage, stage + kTile, nullptr, nullptr, m[r], 2.0 * m[r], ca, cb);
+        if (r == kPhiR - 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar);          // last read of the stage
+        }
+        double c = carry[r];
+        if (neg) tile_solve<true>(ca, cb, c, f, lane);
+        else tile_solve<false>(ca, cb, c, f, lane);
+        carry[r] = c;
+#pragma unroll
+        for (int j = 0; j < kL; ++j) g[j] = r == 0 ? hw[r] * f[j] : fma(hw[r], f[j], g[j]);
+    }
+    if (off + kTile > Z) {                                  // only the last tile holds padding cells: exact zeros there
+#pragma unroll
+        for (int jj = 0; jj < kL; ++jj)
+            if (off + lane * kL + jj >= Z) g[jj] = 0.0;
+    }
+    mbar_wait(red_empty_bar, red_parity);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) *reinterpret_cast<double2 *>(rw + kk * 64) = make_double2(g[2 * kk], g[2 * kk + 1]);
+}
+
+__global__ void __launch_bounds__(kPhiThreads, 1) phi_sweep_kernel(const SweepArgs p, const ae_ctrl *ctrl, int gate)
+{
+    constexpr int AC = kPhiAC, R = kPhiR;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *ring = reinterpret_cast<double *>(smem_raw);                    // [kPhiStages][kPhiStageLen]
+    double *red = ring + kPhiStages * kPhiStageLen;                         // [kPhiRB][kPhiCW][kTile]
+    uint64_t *full = reinterpret_cast<uint64_t *>(red + kPhiRB * kPhiCW * kTile);
+    uint64_t *empty = full + kPhiStages;
+    uint64_t *red_full = empty + kPhiStages;
+    uint64_t *red_empty = red_full + kPhiRB;
+    __shared__ int s_cta;
+    __shared__ __align__(16) double s_ap[AC][kL];                           // per row: a^(jj+1)
+    __shared__ double s_hw[AC];                                             // per row: half quadrature weight
+    if (gate && ctrl->inner_done) return;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    SweepSync *sy = p.sync;
+    if (tid == 0) {
+        s_cta = (int)atomicInc(&sy->ticket, gridDim.x - 1);
+        for (int s = 0; s < kPhiStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kPhiCW); }
+        for (int b = 0; b < kPhiRB; ++b) { mbar_init(red_full + b, kPhiCW); mbar_init(red_empty + b, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int cta = s_cta;
+    const int gang = cta / p.gs, mb = cta - gang * p.gs;
+    const unsigned stamp = sy->epoch + 1;
+    const int nt = (int)(p.Zp / kTile);
+    const int64_t T = p.total_tiles, NC = gridDim.x / p.gs;
+    const int64_t t0 = gang * T / NC, t1 = (gang + 1) * T / NC;
+    const bool publishes = (t1 % nt) != 0;
+    Segments segs;
+    segs.init(t0, t1, nt);
+    const bool info = p.tinfo != nullptr;
+    RowCtx c;
+    int st = 0, b = 0;
+    uint32_t ph = 0, bph = 0;
+
+    if (warp == kPhiCW + 1) {
+        // ================= producer warp ================================================================
+        const uint64_t pol = l2_policy(p.l2_hints ? 2 : 0);
+        for (int k = 0; k < segs.count; ++k) {
+            int rb, ti0, n;
+            segs.get(k, rb, ti0, n);
+            row_setup<AC>(p, unit_row(p, rb, mb), 0, c);
+            const int dir = c.neg ? -1 : 1;
+            int tile = c.neg ? nt - 1 - ti0 : ti0;
+            const double *recs = info ? p.tinfo + 2 * ((int64_t)c.g * nt + tile) : nullptr;
+            double rec_cur = 0.0, rec_nxt = 0.0;
+            if (info && lane < n) rec_nxt = __ldg(recs + 2 * dir * lane);
+            for (int i = 0; i < n; ++i, tile += dir) {
+                if ((i & 31) == 0) {
+                    rec_cur = rec_nxt;
+                    if (info && i + 32 + lane < n) rec_nxt = __ldg(recs + 2 * dir * (i + 32 + lane));
+                }
+                const double rec_h = __shfl_sync(0xffffffffu, rec_cur, i & 31);
+                const bool uniform = info && rec_h == rec_h;
+                double *dst = ring + (size_t)st * kPhiStageLen;
+                const int64_t goff = (int64_t)c.g * p.Zp + (int64_t)tile * kTile;
+                mbar_wait(empty + st, ph ^ 1);
+                if (lane == 0) mbar_expect_tx(full + st, (uint32_t)((uniform ? 1 : 2) * kTileBytes + (info ? 16 : 0)));
+                __syncwarp();
+                if (lane == 0 && !uniform) bulk_g2s(dst, p.hs + goff, kTileBytes, full + st, pol);
+                if (lane == 1) bulk_g2s(dst + kTile, p.q + goff, kTileBytes, full + st, pol);
+                if (info && lane == 31) bulk_g2s(dst + 2 * kTile, recs + 2 * dir * i, 16, full + st, pol);
+                if (++st == kPhiStages) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == kPhiCW) {
+        // ================= reducer warp: the slots already carry the quadrature weights ==============
+        for (int k = 0; k < segs.count; ++k) {
+            int rb, ti0, n;
+            segs.get(k, rb, ti0, n);
+            row_setup<AC>(p, unit_row(p, rb, mb), 0, c);
+            const int step = c.neg ? -kTile : kTile;
+            double *dst = p.partial + c.poff + (int64_t)(c.neg ? nt - 1 - ti0 : ti0) * kTile + lane * 2;
+            for (int i = 0; i < n; ++i, dst += step) {
+                const double *rb_ = red + b * (kPhiCW * kTile) + lane * 2;
+                mbar_wait(red_full + b, bph);
+                double2 acc[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) acc[kk] = *reinterpret_cast<const double2 *>(rb_ + kk * 64);
+#pragma unroll
+                for (int w = 1; w < kPhiCW; ++w)                            // warps in order: deterministic
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const double2 v = *reinterpret_cast<const double2 *>(rb_ + w * kTile + kk * 64);
+                        acc[kk].x += v.x;
+                        acc[kk].y += v.y;
+                    }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(red_empty + b);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) *reinterpret_cast<double2 *>(dst + kk * 64) = acc[kk];
+                if (++b == kPhiRB) { b = 0; bph ^= 1; }
+            }
+        }
+    } else {
+        // ================= compute warps: rows warp, warp + 8, ... of the block ========================
+        const double nan_v = __longlong_as_double(0x7ff8000000000000LL);
+        UniRow u[R];
+        const double *ap = &s_ap[warp][0];                                  // row r: + r * kPhiCW * kL
+        const double *hws = &s_hw[warp];                                    // row r: + r * kPhiCW
+        for (int k = 0; k < segs.count; ++k) {
+            int rb, ti0, n;
+            segs.get(k, rb, ti0, n);
+            const int row = unit_row(p, rb, mb);
+            row_setup<AC>(p, row, 0, c);
+            const int a0 = c.neg ? (row % p.nbg) * AC : p.n_neg + (row % p.nbg - p.nb_neg) * AC;
+            const int nblk = c.nblk;
+            const bool neg = c.neg;
+            double cin[R];                                                  // fluxes entering the tile
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int slot = warp + kPhiCW * r;
+                if (lane == 0) s_hw[slot] = slot < nblk ? 0.5 * p.wgt[a0 + slot] : 0.0;     // half weights (0: absent row)
+                cin[r] = 0.0;                                               // vacuum boundary: group.py:48,54
+            }
+            __syncwarp();
+            if (ti0 != 0) {                                                 // continue rows another CTA started
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int slot = warp + kPhiCW * r;
+                    if (lane == 0 && slot < nblk) {
+                        while (ld_acquire(&sy->flag[cta - p.gs][slot]) != stamp) {}
+                        cin[r] = sy->carry[cta - p.gs][slot];
+                    }
+                    cin[r] = __shfl_sync(0xffffffffu, cin[r], 0);
+                }
+            }
+            double u_h = nan_v;
+            const int step = neg ? -kTile : kTile;
+            int64_t off = (int64_t)(neg ? nt - 1 - ti0 : ti0) * kTile;
+            for (int i = 0; i < n; ++i, off += step) {
+                const double *stage = ring + (size_t)st * kPhiStageLen + lane * 2;
+                double *rw = red + b * (kPhiCW * kTile) + warp * kTile + lane * 2;
+                mbar_wait(full + st, ph);
+                double2 rec = make_double2(nan_v, 0.0);
+                if (info) rec = *reinterpret_cast<const double2 *>(ring + (size_t)st * kPhiStageLen + 2 * kTile);
+                if (rec.x == rec.x) {
+                    if (!(rec.x == u_h)) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const int slot = warp + kPhiCW * r;
+                            const double m = fabs(p.mu_ihx[a0 + (slot < nblk ? slot : 0)]);
+                            if (neg) row_setup_uniform<true>(m, rec.x, lane, &s_ap[slot][0], u[r]);
+                            else row_setup_uniform<false>(m, rec.x, lane, &s_ap[slot][0], u[r]);
+                        }
+                        u_h = rec.x;
+                    }
+                    double x[R][kL], g[kL];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const double2 s = *reinterpret_cast<const double2 *>(stage + kTile + kk * 64);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) { x[r][2 * kk] = s.x * u[r].r; x[r][2 * kk + 1] = s.y * u[r].r; }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty + st);
+#if defined(AE_PHI_SKELETON) && AE_PHI_SKELETON == 1   // diagnostic build: handshakes and memory traffic only, no scan
+#pragma unroll
+                    for (int j = 0; j < kL; ++j) { g[j] = 0.0; for (int r = 0; r < R; ++r) g[j] += x[r][j]; }
+#else
+                    if (neg) phi_rows<true, R>(x, u, ap, kPhiCW * kL, hws, kPhiCW, cin, g, lane);
+                    else phi_rows<false, R>(x, u, ap, kPhiCW * kL, hws, kPhiCW, cin, g, lane);
+#endif
+                    mbar_wait(red_empty + b, bph ^ 1);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) *reinterpret_cast<double2 *>(rw + kk * 64) = make_double2(g[2 * kk], g[2 * kk + 1]);
+                } else {
+                    double tm[R], thw[R], tc[R];                            // copies: their address goes to the out-of-line path
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int slot = warp + kPhiCW * r;
+                        tm[r] = fabs(p.mu_ihx[a0 + (slot < nblk ? slot : 0)]); thw[r] = hws[r * kPhiCW]; tc[r] = cin[r];
+                    }
+                    phi_general_tile(stage, tm, thw, tc, neg, lane, off, p.Z, rw, empty + st, red_empty + b, bph ^ 1);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) cin[r] = tc[r];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(red_full + b);
+                if (++st == kPhiStages) { st = 0; ph ^= 1; }
+                if (++b == kPhiRB) { b = 0; bph ^= 1; }
+            }
+            if (k == 0 && publishes && lane == 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int slot = warp + kPhiCW * r;
+                    if (slot < nblk) { sy->carry[cta][slot] = cin[r]; st_release(&sy->flag[cta][slot], stamp); }
+                }
+            }
+        }
+    }
     __syncthreads();
     if (tid == 0) {
         __threadfence();
@@ -531,10 +801,45 @@ static int launch_variant(const SweepArgs &p_in, const ae_ctrl *ctrl, int gate, 
     return AE_OK;
 }
 
+
+static int launch_phi(const SweepArgs &p_in, const ae_ctrl *ctrl, int gate, int *P_out, cudaStream_t st)
+{
+    SweepArgs p = p_in;
+    // this kernel's own block shape: 8R angles per block
+    p.nb_neg = (p.n_neg + kPhiAC - 1) / kPhiAC;
+    p.nbg = p.nb_neg + (p.A - p.n_neg + kPhiAC - 1) / kPhiAC;
+    p.total_tiles = (int64_t)p.G * p.nbg * (p.Zp / kTile);
+    p.gs = 1; p.subs = p.nb_neg;
+    const size_t smem = (size_t)(kPhiStages * kPhiStageLen + kPhiRB * kPhiCW * kTile) * sizeof(double) + (2 * kPhiStages + 2 * kPhiRB) * sizeof(uint64_t);
+    static int ctas_per_sm = 0, sms = 0;
+    if (!ctas_per_sm) {
+        AE_CUDA(cudaFuncSetAttribute((const void *)phi_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int n = 0, dev = 0;
+        AE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, phi_sweep_kernel, kPhiThreads, smem));
+        if (n < 1) { set_error("phi sweep kernel does not fit on an SM"); return AE_CUDA_ERROR; }
+        AE_CUDA(cudaGetDevice(&dev));
+        AE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        ctas_per_sm = n;
+    }
+    const int64_t grid = plan_grid(p, (int64_t)sms * ctas_per_sm);
+    phi_sweep_kernel<<<(unsigned)grid, kPhiThreads, smem, st>>>(p, ctrl, gate);
+    AE_CUDA(cudaGetLastError());
+    *P_out = p.nbg;
+    return AE_OK;
+}
+
 template <int AC>
-static int launch_shape(const SweepArgs &p, const ae_ctrl *ctrl, int gate, cudaStream_t st)
+static int launch_shape(const SweepArgs &p, const ae_ctrl *ctrl, int gate, int *P_out, cudaStream_t st)
 {
     const bool rd = p.psi_in != nullptr, wr = p.psi_out != nullptr;
+    static const char *rows1 = getenv("AE_SWEEP_PHI_ROWS");                // "1": phi-only sweeps through sweep_kernel (A/B)
+    // phi-only sweeps of many-angle problems: the rows-per-warp kernel, when the caller can take its partial count and
+    // its wider blocks (8R angles) are at least 7/8 full (angle-sharded ranks may hold too few angles per direction)
+    const int nneg = p.n_neg, npos = p.A - p.n_neg;
+    const int padded = ((nneg + kPhiAC - 1) / kPhiAC + (npos + kPhiAC - 1) / kPhiAC) * kPhiAC;
+    if (AC == kACbig && !rd && !wr && P_out && 8 * p.A >= 7 * padded && !(rows1 && rows1[0] == '1'))
+        return launch_phi(p, ctrl, gate, P_out, st);
+    if (P_out) *P_out = p.nbg;
     if (rd && wr) return launch_variant<AC, true, true>(p, ctrl, gate, st);
     if (rd) return launch_variant<AC, true, false>(p, ctrl, gate, st);
     if (wr) return launch_variant<AC, false, true>(p, ctrl, gate, st);
@@ -554,8 +859,9 @@ static int shape_args(int A, int n_neg, int G, int64_t Zp, SweepArgs &p)
 }
 
 // internal launcher shared with the solver loops (gate: skip when ctrl->inner_done is set)
+// *P_out (may be NULL): number of partial slabs written.  NULL pins it to ae_partial_count(A, n_neg).
 int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double *psi_out, double *partial,
-                 void *sync, const ae_ctrl *ctrl, int gate, cudaStream_t st)
+                 void *sync, const ae_ctrl *ctrl, int gate, int *P_out, cudaStream_t st)
 {
     if (!s || !q || !partial || !sync || s->Zp % kTile || s->A <= 0 || s->G <= 0) {
         set_error("ae_sweep_set: bad argument");
@@ -571,7 +877,7 @@ int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double
     p.l2_hints = !(hints && hints[0] == '0');
     static const char *nofast = getenv("AE_SWEEP_NO_FAST");                // A/B and parity tests: general path only
     p.tinfo = (nofast && nofast[0] == '1') ? nullptr : s->tile_info;
-    return ac == kACbig ? launch_shape<kACbig>(p, ctrl, gate, st) : launch_shape<kACsmall>(p, ctrl, gate, st);
+    return ac == kACbig ? launch_shape<kACbig>(p, ctrl, gate, P_out, st) : launch_shape<kACsmall>(p, ctrl, gate, P_out, st);
 }
 
 }  // namespace ae
@@ -627,7 +933,16 @@ extern "C" int ae_tile_info(const double *hs, const double *cdt, int64_t Z, int6
 extern "C" int ae_sweep_set(const ae_slab *s, const double *q, const double *psi_in, double *psi_out,
                             double *partial, void *sync, void *stream)
 {
-    return ae::launch_sweep(s, q, psi_in, psi_out, partial, sync, nullptr, 0, (cudaStream_t)stream);
+    return ae::launch_sweep(s, q, psi_in, psi_out, partial, sync, nullptr, 0, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int ae_sweep_set_phi(const ae_slab *s, const double *q, double *partial, void *sync, int32_t *P_out, void *stream)
+{
+    if (!P_out) { ae::set_error("ae_sweep_set_phi: P_out missing"); return AE_BAD_ARG; }
+    int P = 0;
+    const int rc = ae::launch_sweep(s, q, nullptr, nullptr, partial, sync, nullptr, 0, &P, (cudaStream_t)stream);
+    *P_out = P;
+    return rc;
 }
 
 extern "C" int ae_reduce_partials(const ae_slab *s, const double *partial, int32_t P, double *phi, void *stream)

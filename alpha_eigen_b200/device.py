@@ -344,6 +344,20 @@ class SlabDevice:
             self.comm.allreduce_(phi)
         return phi
 
+    def sweep_set_phi(self, q):
+        """ae_sweep_set_phi + ae_reduce_partials: scalar flux [G][Zp] of a sweep set without angular flux in or out
+        (the kernel the solver loops use for their phi-only iterations; it may write fewer partial slabs)."""
+        P = C.c_int32(0)
+        _lib.check(self.lib.ae_sweep_set_phi(C.byref(self.slab), q.data_ptr(), self.partial.data_ptr(), self.sync.data_ptr(),
+                                             C.byref(P), self.stream))
+        phi = self.torch.empty(self.G * self.Zp, dtype=self.torch.float64, device=self.dev)
+        _lib.check(self.lib.ae_reduce_partials(C.byref(self.slab), self.partial.data_ptr(), P.value, phi.data_ptr(),
+                                               self.stream))
+        if self.comm is not None:
+            self.comm.allreduce_(phi)
+        self.last_phi_partials = P.value
+        return phi
+
     def flux_update(self, partial, P, q_next, tol=0.0, iteration=0):
         """ae_flux_update: phi assembly + norm + next scatter source (w->base must be set)."""
         _lib.check(self.lib.ae_flux_update(C.byref(self.slab), C.byref(self.work), partial.data_ptr(), P,

@@ -177,6 +177,8 @@ def main():
     ap.add_argument("--skip-long", action="store_true")
     ap.add_argument("--skip-c5", action="store_true")
     ap.add_argument("--only-c5", action="store_true")
+    ap.add_argument("--only-c3", action="store_true")
+    ap.add_argument("--c3-steps", type=int, default=200)
     ap.add_argument("--c5-members", type=int, default=128, help="members of the 1024-member ensemble to run (one GPU's share)")
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
@@ -188,6 +190,10 @@ def main():
         f.write(s + "\n")
         f.flush()
 
+    if args.only_c3:
+        case_c3_alpha(out, steps=args.c3_steps)
+        f.close()
+        return
     if args.only_c5:
         case_c5_batched(out, E=args.c5_members)
         case_c5_batched(out, E=args.c5_members, snapshots="phi")

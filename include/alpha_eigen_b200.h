@@ -118,6 +118,10 @@ int64_t ae_norm_blocks(int64_t Zp);
  */
 int ae_sweep_set(const ae_slab *s, const double *q, const double *psi_in, double *psi_out,
                  double *partial, void *sync, void *stream);
+/* The same for a sweep without angular flux in or out (every steady-state iteration, the inner iterations of a
+ * time step): may run a kernel with wider angle blocks that writes FEWER partial slabs; *P_out receives how many
+ * (<= ae_partial_count), the value to hand to ae_reduce_partials / ae_flux_update. */
+int ae_sweep_set_phi(const ae_slab *s, const double *q, double *partial, void *sync, int32_t *P_out, void *stream);
 /* Uniform-tile records for ae_slab.tile_info: info[g][t] = {hs, cdt} of tile t of group g when its 256 cells are all
  * real and share bitwise-identical hs (and cdt, when cdt != NULL) values, {NaN, NaN} otherwise.  hs / cdt: [G][Zp]. */
 int ae_tile_info(const double *hs, const double *cdt, int64_t Z, int64_t Zp, int32_t G, double *info, void *stream);

@@ -545,9 +545,12 @@ def test_uniform_tile_fast_path_is_bit_identical_to_general_path(Z, A, G, td):
         psi = dev.psi_to_device(psi0)
         phi = dev.sweep_set(q, psi_in=psi if td else None, psi_out=psi)
         ro = dev.sweep_set(q, psi_in=psi if td else None)                # read-only / phi-only variant
-        out.append((phi.cpu().numpy(), psi.cpu().numpy(), ro.cpu().numpy()))
+        ph = dev.sweep_set_phi(q)                                        # rows-per-warp kernel when A has 16-angle blocks
+        out.append((phi.cpu().numpy(), psi.cpu().numpy(), ro.cpu().numpy(), ph.cpu().numpy()))
     for a, b in zip(*out):
         assert np.array_equal(a, b)
+    if not td:                                                           # the two phi-only kernels sum the angles in different orders
+        assert _rel(out[0][3], out[0][2]) < 1e-13
 
 
 @pytest.mark.parametrize("Z,A,G,flags", [(700, 6, 3, 1), (700, 6, 3, 3), (2600, 16, 2, 1), (450, 4, 1, 1)])
@@ -591,3 +594,20 @@ def test_time_dependent_source_iteration_streaming_fixed_flux():
         got.append((it, dev.cells_to_host(dev.phi)))
     assert got[0][0] == got[1][0] == got[2][0]
     assert _rel(got[1][1], got[0][1]) < 1e-12 and _rel(got[2][1], got[0][1]) < 1e-12
+
+
+@pytest.mark.parametrize("Z,A,G", [(8000, 64, 5), (5000, 96, 3), (3000, 40, 2), (12000, 256, 2), (700, 34, 1)])
+def test_phi_only_rows_per_warp_kernel_matches_oracle(Z, A, G):
+    """ae_sweep_set_phi (several angles per warp, wider angle blocks, fewer partial slabs) against the oracle's sweep
+    set, including ragged blocks (40, 34, 96 angles) and rows cut between CTAs."""
+    from oracle import ae_oracle as orc
+    p = _mg_problem(Z, A, G, seed=A + G)
+    dev = _device(p)
+    q = p["rs"].rand(Z, G) + 0.05
+    sigT = p["tables"].total[p["tables"].mat]
+    phi_o = orc.sweep_set(p["mu"], p["weight"], p["hx"], q, sigT)
+    phi = dev.sweep_set_phi(dev.cells_to_device(q))
+    assert dev.last_phi_partials <= dev.P
+    assert _rel(dev.cells_to_host(phi), phi_o) < 1e-13
+    raw = phi.cpu().numpy().reshape(G, dev.Zp)
+    assert np.count_nonzero(raw) <= Z * G                                # padding cells are exact zeros

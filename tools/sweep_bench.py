@@ -32,9 +32,15 @@ def main():
         dev.slab.tile_info = info_ptr if use_info else None
         for name, pin, pout in (("rw", psi, psi), ("ro", psi, None), ("phi", None, None)):
             ptr = lambda t: t.data_ptr() if t is not None else None
+            import ctypes as C
+            Pw = C.c_int32(0)
             def run():
-                rc = dev.lib.ae_sweep_set(dev.slab, q.data_ptr(), ptr(pin), ptr(pout), dev.partial.data_ptr(),
-                                          dev.sync.data_ptr(), dev.stream)
+                if name == "phi":       # the kernel the solver loops use for phi-only iterations
+                    rc = dev.lib.ae_sweep_set_phi(dev.slab, q.data_ptr(), dev.partial.data_ptr(), dev.sync.data_ptr(),
+                                                  C.byref(Pw), dev.stream)
+                else:
+                    rc = dev.lib.ae_sweep_set(dev.slab, q.data_ptr(), ptr(pin), ptr(pout), dev.partial.data_ptr(),
+                                              dev.sync.data_ptr(), dev.stream)
                 assert rc == 0, rc
             for _ in range(3):
                 run()
