@@ -21,6 +21,7 @@ struct Nccl {
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*ReduceScatter)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
@@ -49,12 +50,13 @@ static int load_nccl()
     AE_SYM(AllReduce, "ncclAllReduce");
     AE_SYM(ReduceScatter, "ncclReduceScatter");
     AE_SYM(AllGather, "ncclAllGather");
+    AE_SYM(Broadcast, "ncclBroadcast");
     AE_SYM(GroupStart, "ncclGroupStart");
     AE_SYM(GroupEnd, "ncclGroupEnd");
     AE_SYM(CommDestroy, "ncclCommDestroy");
     AE_SYM(GetErrorString, "ncclGetErrorString");
 #undef AE_SYM
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.ReduceScatter || !g_nccl.AllGather ||
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.ReduceScatter || !g_nccl.AllGather || !g_nccl.Broadcast ||
         !g_nccl.GroupStart || !g_nccl.GroupEnd || !g_nccl.CommDestroy) {
         set_error("NCCL symbols missing");
         return AE_CUDA_ERROR;
@@ -109,9 +111,49 @@ int comm_all_gather_rows(void *comm, double *rows, int G, int64_t Zp, int with_p
     return AE_OK;
 }
 
+// Balanced contiguous partition of G groups over the ranks: the first G % n ranks own one group more.
+void group_range(int G, int nranks, int rank, int *g0, int *gl)
+{
+    const int base = G / nranks, rem = G % nranks;
+    *gl = base + (rank < rem ? 1 : 0);
+    *g0 = rank * base + (rank < rem ? rank : rem);
+}
+
+// Group-sharded ranks: rows[g][Zp], rank r owns the rows of its groups; every rank ends up with all rows.  The blocks
+// have unequal sizes (70 groups over 8 ranks: 9,9,9,9,9,9,8,8), so this is one broadcast per owner inside one NCCL
+// group (in place); optionally the (num, den) pairs of a sharded norm travel in the same group.
+int comm_all_gather_groups(void *comm, double *rows, int G, int64_t Zp, int with_pairs, cudaStream_t st)
+{
+    Comm *c = (Comm *)comm;
+    AE_NCCL(g_nccl.GroupStart());
+    for (int r = 0; r < c->nranks && rows; ++r) {
+        int g0, gl;
+        group_range(G, c->nranks, r, &g0, &gl);
+        double *blk = rows + (int64_t)g0 * Zp;
+        if (gl > 0) AE_NCCL(g_nccl.Broadcast(blk, blk, (size_t)gl * Zp, ncclFloat64, r, c->nccl, st));
+    }
+    if (with_pairs) AE_NCCL(g_nccl.AllGather(c->pair_local, c->pairs, 2, ncclFloat64, c->nccl, st));
+    AE_NCCL(g_nccl.GroupEnd());
+    return AE_OK;
+}
+
 }  // namespace ae
 
 using namespace ae;
+
+extern "C" void ae_group_range(int32_t G, int32_t nranks, int32_t rank, int32_t *g0, int32_t *gl)
+{
+    int a = 0, b = 0;
+    group_range(G, nranks > 0 ? nranks : 1, rank, &a, &b);
+    if (g0) *g0 = a;
+    if (gl) *gl = b;
+}
+
+extern "C" int ae_comm_gather_groups(void *comm, double *rows, int32_t G, int64_t Zp, void *stream)
+{
+    if (!comm || !g_nccl.h) { set_error("ae_comm_gather_groups: no communicator"); return AE_BAD_ARG; }
+    return comm_all_gather_groups(comm, rows, G, Zp, 0, (cudaStream_t)stream);
+}
 
 extern "C" int ae_comm_unique_id(void *id128)
 {

@@ -46,7 +46,7 @@ int check_work(const ae_slab *s, const ae_work *w, const char *who)
         set_error("%s: incomplete ae_work / ae_slab", who);
         return AE_BAD_ARG;
     }
-    if (w->comm && !w->reduced) { set_error("%s: multi-GPU work needs the `reduced` buffer", who); return AE_BAD_ARG; }
+    if (w->comm && s->gl <= 0 && !w->reduced) { set_error("%s: angle-sharded multi-GPU work needs the `reduced` buffer", who); return AE_BAD_ARG; }
     return AE_OK;
 }
 
@@ -66,7 +66,7 @@ static int compute_fixed(const ae_slab *s, ae_work *w, const double *psi_in, cud
     AE_CUDA(cudaMemsetAsync(w->q1, 0, (size_t)s->G * s->Zp * sizeof(double), st));        // q1 is free until the first update
     AE_TRY(launch_sweep(s, w->q1, psi_in, nullptr, w->partial, w->sweep_sync, w->ctrl, 0, nullptr, st));
     AE_TRY(ae_reduce_partials(s, w->partial, w->P, w->phi_fixed, st));
-    if (w->comm) AE_TRY(comm_reduce_scatter_rows(w->comm, w->phi_fixed, s->G, s->Zp, st)); // valid on this rank's cell range
+    if (w->comm && s->gl <= 0) AE_TRY(comm_reduce_scatter_rows(w->comm, w->phi_fixed, s->G, s->Zp, st)); // valid on this rank's cell range
     return AE_OK;
 }
 
@@ -111,7 +111,7 @@ static int source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, 
             const int gate = b > 0;                     // first of a batch always runs
             int Pw = w->P;                              // partial slabs this sweep writes (fewer from the phi-only kernel)
             AE_TRY(launch_sweep(s, q[i & 1], sweep_psi, nullptr, w->partial, w->sweep_sync, w->ctrl, gate, &Pw, st));
-            if (w->comm) {
+            if (w->comm && s->gl <= 0) {
                 // angle-sharded sweeps, cell-sharded update: reduce-scatter the flux, update 1/N of the cells,
                 // all-gather the new source (inside launch_finalize)
                 AE_TRY(exchange_partials(s, w, Pw, st));
@@ -129,7 +129,7 @@ static int source_iteration(const ae_slab *s, ae_work *w, const double *psi_in, 
     if (iters) *iters = n_done;
     if (last_q) *last_q = (n_done - 1) & 1;             // the sweep of iteration n read q[(n-1)&1]
     if (n_done & 1) { w->phi = phi[1]; w->phi_alt = phi[0]; }   // iteration n wrote phi[n&1]
-    if (w->comm) AE_TRY(comm_all_gather_rows(w->comm, w->phi, s->G, s->Zp, 0, st));     // callers see the whole flux
+    if (w->comm && s->gl <= 0) AE_TRY(comm_all_gather_rows(w->comm, w->phi, s->G, s->Zp, 0, st));     // callers see the whole flux
     return status;
 }
 
@@ -140,7 +140,7 @@ using namespace ae;
 extern "C" int ae_exchange_partials(const ae_slab *s, ae_work *w, void *stream)
 {
     AE_TRY(check_work(s, w, "ae_exchange_partials"));
-    if (!w->comm) { set_error("ae_exchange_partials: no communicator"); return AE_BAD_ARG; }
+    if (!w->comm || s->gl > 0) { set_error("ae_exchange_partials: needs an angle-sharded communicator (group-sharded ranks have nothing to reduce)"); return AE_BAD_ARG; }
     return exchange_partials(s, w, w->P, (cudaStream_t)stream);
 }
 

@@ -16,6 +16,10 @@
 // reduce-scattered by rows so that rank r receives the summed flux of its cells only, does 1/N of
 // the update work, and the new sources are all-gathered; the two sums of a norm travel as a
 // (num, den) pair in the same NCCL group and are combined in rank order on every rank.
+// With enough groups (G >= 2 N) the ranks are sharded by GROUPS instead: a rank sweeps its groups with all angles, so
+// their flux is complete on it -- no reduction; it assembles those rows over all cells, the rows are all-gathered (one
+// collective per iteration instead of two) and it builds the scatter / fission sources of its own groups from the
+// full flux.
 #include <stdlib.h>
 #include "ae_common.cuh"
 
@@ -108,6 +112,8 @@ struct FinArgs {
     NormOut norm;
     int64_t Z, Zp;
     int64_t c0, cn;             // cell range of this rank (multiples of 256)
+    int g0, gl;                 // group rows this rank updates: all G, or its own groups when group-sharded
+                                // (then partial holds only those gl rows per slab)
     int P, G, M;
     int init;                   // 1: phi := cold (no norm), 0: phi := sum of partials
     int gate;
@@ -182,9 +188,9 @@ __global__ void __launch_bounds__(256, 6) flux_assemble_kernel(const FinArgs p)
 {
     __shared__ double red[64];
     if (p.gate && p.norm.ctrl->inner_done) return;
-    const int64_t n = (int64_t)p.G * p.Zp;
-    const int64_t row = (int64_t)blockIdx.y * p.Zp + p.c0;
-    const double *part = p.partial + row;
+    const int64_t n = (int64_t)p.gl * p.Zp;                      // slab stride of the partials (this rank's rows)
+    const int64_t row = (int64_t)(p.g0 + blockIdx.y) * p.Zp + p.c0;
+    const double *part = p.partial + (int64_t)blockIdx.y * p.Zp + p.c0;
     const double *fix = p.fixed ? p.fixed + row : nullptr;
     const double *old = p.phi_in + row;
     double *out = p.phi + row;
@@ -230,6 +236,10 @@ __global__ void flux_init_kernel(const FinArgs p)
 // row, for 32 FMAs -- FP64-pipe bound instead of load-issue bound.  The scatter matrix of the tile's
 // material is staged once per CTA in shared memory (row stride padded to a multiple of 8); the rare
 // tile that straddles a material interface takes the per-cell global-memory path.
+// (Round 2 tried this product on the FP64 tensor path -- mma.sync m8n8k4 with S^T and the flux tile in shared memory,
+// zero blocks of S^T masked out, one and two CTAs per SM, fused with the flux assembly or not: 217-340 us per C3
+// iteration against 193 us for this kernel.  The product is not what limits it: 3 x G separate 1 KB runs per tile is a
+// poor DRAM access pattern, see DESIGN.md.)
 constexpr int kGB = 8;
 constexpr int kSC = 128;                // cells per CTA
 constexpr int kSWarps = 10;             // warps per CTA (each loops over its group blocks)
@@ -270,6 +280,7 @@ __global__ void __launch_bounds__(32 * kSWarps, 2) scatter_source_kernel(const F
         for (int blk = gb; blk < gblocks; blk += blockDim.y) {
             const int g0 = blk * kGB;
             const int ng = min(kGB, p.G - g0);
+            if (g0 + ng <= p.g0 || g0 >= p.g0 + p.gl) continue;     // group-sharded: only this rank's output groups
             double acc[4][kGB];
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(32 * kSWarps, 2) scatter_source_kernel(const F
             }
 #pragma unroll
             for (int j = 0; j < kGB; ++j)
-                if (j < ng) {
+                if (j < ng && g0 + j >= p.g0 && g0 + j < p.g0 + p.gl) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const int64_t i = (int64_t)(g0 + j) * p.Zp + s0 + lane + 32 * c;
@@ -322,14 +333,14 @@ __global__ void __launch_bounds__(32 * kSWarps, 2) scatter_source_kernel(const F
 __global__ void __launch_bounds__(kCB) fission_base_kernel(const double *__restrict__ phi, const double *__restrict__ s_ext,
                                                            const int32_t *__restrict__ mat, const double *__restrict__ chi,
                                                            const double *__restrict__ nusf, int64_t Zp, int64_t c0, int64_t cn,
-                                                           int G, double *__restrict__ base)
+                                                           int G, int g0, int gl, double *__restrict__ base)
 {
     const int64_t s = c0 + (int64_t)blockIdx.x * kCB + threadIdx.x;
     if (s >= c0 + cn) return;
     const int m = mat[s];
     double acc = 0.0;
     for (int gp = 0; gp < G; ++gp) acc = fma(nusf[m * G + gp], phi[(int64_t)gp * Zp + s], acc);
-    for (int g = 0; g < G; ++g) {
+    for (int g = g0; g < g0 + gl; ++g) {                        // the rows this rank sweeps (all, unless group-sharded)
         const int64_t i = (int64_t)g * Zp + s;
         const double f = 0.5 * chi[m * G + g] * acc;
         base[i] = s_ext ? s_ext[i] + f : f;
@@ -339,14 +350,15 @@ __global__ void __launch_bounds__(kCB) fission_base_kernel(const double *__restr
 // k.new = ||nusf*phi_new|| / ||nusf*phi_old||  (group.py:108), convergence flag (group.py:109)
 __global__ void __launch_bounds__(kCB) k_update_kernel(const double *__restrict__ phi_new, const double *__restrict__ phi_old,
                                                        const int32_t *__restrict__ mat, const double *__restrict__ nusf,
-                                                       int64_t Z, int64_t Zp, int64_t c0, int64_t cn, int G, NormOut norm)
+                                                       int64_t Z, int64_t Zp, int64_t c0, int64_t cn, int G, int g0, int gl,
+                                                       NormOut norm)
 {
     __shared__ double red[64];
     const int64_t s = c0 + (int64_t)blockIdx.x * kCB + threadIdx.x;
     double num = 0.0, den = 0.0;
     if (s < c0 + cn && logical_cell(s) < Z) {
         const int m = mat[s];
-        for (int g = 0; g < G; ++g) {
+        for (int g = g0; g < g0 + gl; ++g) {                    // this rank's share of the two sums
             const double f = nusf[m * G + g];
             const double a = f * phi_new[(int64_t)g * Zp + s], b = f * phi_old[(int64_t)g * Zp + s];
             num = fma(a, a, num);
@@ -364,21 +376,24 @@ __global__ void scale_by_k_kernel(const double *__restrict__ phi_new, const ae_c
         phi_old[i] = phi_new[i] / k;
 }
 
-// time_unit.py:41 outer change; also phi_outer := phi for the next outer iteration (time_unit.py:36)
-__global__ void __launch_bounds__(kCB) outer_check_kernel(const double *__restrict__ phi, double *__restrict__ phi_outer,
-                                                          int64_t Zp, int64_t c0, int64_t cn, int G, NormOut norm)
+// time_unit.py:41 outer change; also phi_outer := phi for the next outer iteration (time_unit.py:36).  Flat over
+// the (group, cell pair) entries of the rank's cell range: grid (x over cell pairs, y = group), many loads in flight.
+__global__ void __launch_bounds__(256) outer_check_kernel(const double *__restrict__ phi, double *__restrict__ phi_outer,
+                                                          int64_t Zp, int64_t c0, int64_t cn, int g0, int gl, NormOut norm)
 {
     __shared__ double red[64];
-    const int64_t s = c0 + (int64_t)blockIdx.x * kCB + threadIdx.x;
+    const int64_t row = (int64_t)blockIdx.y * Zp + c0;
+    const bool mine = (int)blockIdx.y >= g0 && (int)blockIdx.y < g0 + gl;   // group-sharded: rows of other ranks are only copied
     double num = 0.0, den = 0.0;
-    if (s < c0 + cn) {
-        for (int g = 0; g < G; ++g) {
-            const int64_t i = (int64_t)g * Zp + s;
-            const double v = phi[i], d = v - phi_outer[i];      // padding cells are 0 in both
-            num = fma(d, d, num);
-            den = fma(v, v, den);
-            phi_outer[i] = v;
+    for (int64_t i = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); i < cn; i += 2 * (int64_t)gridDim.x * blockDim.x) {
+        const double2 v = *reinterpret_cast<const double2 *>(phi + row + i);
+        const double2 o = *reinterpret_cast<const double2 *>(phi_outer + row + i);     // padding cells are 0 in both
+        const double dx = v.x - o.x, dy = v.y - o.y;
+        if (mine) {
+            num = fma(dx, dx, fma(dy, dy, num));
+            den = fma(v.x, v.x, fma(v.y, v.y, den));
         }
+        *reinterpret_cast<double2 *>(phi_outer + row + i) = v;
     }
     grid_sum2(num, den, norm, red);
 }
@@ -401,13 +416,15 @@ int comm_all_gather_rows(void *comm, double *rows, int G, int64_t Zp, int with_p
 
 static int per_cell_blocks(int64_t cells) { return (int)((cells + kCB - 1) / kCB); }
 
-struct Shard { int64_t c0, cn; };
+struct Shard { int64_t c0, cn; int g0, gl; };
 static Shard shard_of(const ae_slab *s, const ae_work *w)
 {
+    if (s->gl > 0) return Shard{0, s->Zp, s->g0, s->gl};         // group-sharded: own groups, all cells
     const int n = comm_size(w->comm), r = comm_rank(w->comm);
     const int64_t cn = s->Zp / n;
-    return Shard{r * cn, cn};
+    return Shard{r * cn, cn, 0, s->G};                           // angle-sharded sweeps: own cells, all groups
 }
+int comm_all_gather_groups(void *comm, double *rows, int G, int64_t Zp, int with_pairs, cudaStream_t st);
 
 static NormOut norm_out(ae_work *w, int mode, double tol, int iteration)
 {
@@ -419,7 +436,8 @@ static NormOut norm_out(ae_work *w, int mode, double tol, int iteration)
 static int finish_sharded_norm(const ae_slab *s, ae_work *w, double *rows, int mode, double tol, int iteration, int gate,
                                cudaStream_t st)
 {
-    AE_TRY(comm_all_gather_rows(w->comm, rows, s->G, s->Zp, 1, st));
+    if (s->gl > 0) AE_TRY(comm_all_gather_groups(w->comm, rows, s->G, s->Zp, 1, st));
+    else AE_TRY(comm_all_gather_rows(w->comm, rows, s->G, s->Zp, 1, st));
     norm_finalize_kernel<<<1, 1, 0, st>>>(comm_pairs(w->comm), comm_size(w->comm), mode, w->ctrl, tol, iteration, gate);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
@@ -429,11 +447,12 @@ int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, 
                     double *phi_out, double *q_next, int init, double cold, double tol, int iteration, int gate, cudaStream_t st)
 {
     const Shard sh = shard_of(s, w);
-    if (s->Zp % (kTile * comm_size(w->comm))) { set_error("Zp must be a multiple of 256 * ranks"); return AE_BAD_ARG; }
+    if (s->gl <= 0 && s->Zp % (kTile * comm_size(w->comm))) { set_error("Zp must be a multiple of 256 * ranks"); return AE_BAD_ARG; }
+    if (s->gl > 0 && s->G <= kGSmall) { set_error("group sharding needs more than %d groups", kGSmall); return AE_BAD_ARG; }
     FinArgs p;
     p.partial = partial; p.base = w->base; p.fixed = fixed; p.mat = s->mat; p.scat = s->scat; p.phi_in = phi_in; p.phi = phi_out;
     p.q_next = q_next; p.norm = norm_out(w, kNormInner, tol, iteration);
-    p.Z = s->Z; p.Zp = s->Zp; p.c0 = sh.c0; p.cn = sh.cn; p.P = P; p.G = s->G; p.M = s->M;
+    p.Z = s->Z; p.Zp = s->Zp; p.c0 = sh.c0; p.cn = sh.cn; p.g0 = sh.g0; p.gl = sh.gl; p.P = P; p.G = s->G; p.M = s->M;
     p.init = init; p.gate = gate; p.cold = cold;
     if (s->G <= kGSmall) {
         finalize_small_kernel<<<per_cell_blocks(sh.cn), kCB, 0, st>>>(p);
@@ -451,9 +470,11 @@ int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, 
             if (bx > cap) bx = cap;
             if (bx > (148 * 48 + s->G - 1) / s->G) bx = (148 * 48 + s->G - 1) / s->G;
             if (bx < 1) bx = 1;
-            flux_assemble_kernel<<<dim3((unsigned)bx, s->G), 256, 0, st>>>(p);
+            flux_assemble_kernel<<<dim3((unsigned)bx, sh.gl), 256, 0, st>>>(p);
         }
         AE_CUDA(cudaGetLastError());
+        // group-sharded: the scatter source needs every group's new flux -- the one exchange of the iteration
+        if (w->comm && s->gl > 0 && !init) AE_TRY(finish_sharded_norm(s, w, phi_out, kNormInner, tol, iteration, gate, st));
         const int gblocks = (s->G + kGB - 1) / kGB;
         const size_t smem = (size_t)s->G * (gblocks * kGB + kSC) * sizeof(double);
         if (smem > 220 * 1024) { set_error("flux update: scatter matrix of G=%d does not fit in shared memory", s->G); return AE_BAD_ARG; }
@@ -464,7 +485,7 @@ int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, 
         scatter_source_kernel<<<(unsigned)sgrid, dim3(32, gblocks < kSWarps ? gblocks : kSWarps), smem, st>>>(p);
         AE_CUDA(cudaGetLastError());
     }
-    if (w->comm) {
+    if (w->comm && s->gl <= 0) {
         if (init) AE_TRY(comm_all_gather_rows(w->comm, q_next, s->G, s->Zp, 0, st));
         else AE_TRY(finish_sharded_norm(s, w, q_next, kNormInner, tol, iteration, gate, st));
     }
@@ -475,7 +496,7 @@ int launch_fission_base(const ae_slab *s, ae_work *w, const double *phi, double 
 {
     const Shard sh = shard_of(s, w);
     fission_base_kernel<<<per_cell_blocks(sh.cn), kCB, 0, st>>>(phi, with_ext ? s->s_ext : nullptr, s->mat, s->chi, s->nusf,
-                                                                 s->Zp, sh.c0, sh.cn, s->G, base);
+                                                                 s->Zp, sh.c0, sh.cn, s->G, sh.g0, sh.gl, base);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }
@@ -484,7 +505,7 @@ int launch_k_update(const ae_slab *s, ae_work *w, double tol, int iteration, cud
 {
     const Shard sh = shard_of(s, w);
     k_update_kernel<<<per_cell_blocks(sh.cn), kCB, 0, st>>>(w->phi, w->phi_outer, s->mat, s->nusf, s->Z, s->Zp, sh.c0, sh.cn,
-                                                             s->G, norm_out(w, kNormK, tol, iteration));
+                                                             s->G, sh.g0, sh.gl, norm_out(w, kNormK, tol, iteration));
     AE_CUDA(cudaGetLastError());
     if (w->comm) AE_TRY(finish_sharded_norm(s, w, nullptr, kNormK, tol, iteration, 0, st));
     const int64_t n = (int64_t)s->G * s->Zp;
@@ -497,7 +518,13 @@ int launch_k_update(const ae_slab *s, ae_work *w, double tol, int iteration, cud
 int launch_outer_check(const ae_slab *s, ae_work *w, cudaStream_t st)
 {
     const Shard sh = shard_of(s, w);
-    outer_check_kernel<<<per_cell_blocks(sh.cn), kCB, 0, st>>>(w->phi, w->phi_outer, s->Zp, sh.c0, sh.cn, s->G,
+    // norm_scratch holds 2 * (per_cell_blocks(Zp) + 512) (num, den) pairs
+    int64_t bx = (sh.cn / 2 + 255) / 256;
+    const int64_t cap = (2 * ((int64_t)per_cell_blocks(s->Zp) + 512)) / s->G;
+    if (bx > cap) bx = cap;
+    if (bx > (148 * 16 + s->G - 1) / s->G) bx = (148 * 16 + s->G - 1) / s->G;
+    if (bx < 1) bx = 1;
+    outer_check_kernel<<<dim3((unsigned)bx, s->G), 256, 0, st>>>(w->phi, w->phi_outer, s->Zp, sh.c0, sh.cn, sh.g0, sh.gl,
                                                                 norm_out(w, kNormOuter, 0.0, 0));
     AE_CUDA(cudaGetLastError());
     if (w->comm) AE_TRY(finish_sharded_norm(s, w, nullptr, kNormOuter, 0.0, 0, 0, st));

@@ -869,14 +869,18 @@ int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double
     }
     if (psi_in && !s->cdt) { set_error("ae_sweep_set: psi_in given but slab has no cdt"); return AE_BAD_ARG; }
     SweepArgs p;
-    const int ac = shape_args(s->A, s->n_neg, s->G, s->Zp, p);
-    p.hs = s->hs; p.cdt = s->cdt; p.q = q; p.mu_ihx = s->mu_ihx; p.wgt = s->wgt;
+    // group-sharded rank: the sweep sees a slab of its gl groups -- rows [g0, g0+gl) of the per-cell arrays (contiguous),
+    // psi and partial already hold only those groups
+    const int G = s->gl > 0 ? s->gl : s->G;
+    const int64_t goff = s->gl > 0 ? (int64_t)s->g0 * s->Zp : 0;
+    const int ac = shape_args(s->A, s->n_neg, G, s->Zp, p);
+    p.hs = s->hs + goff; p.cdt = s->cdt ? s->cdt + goff : nullptr; p.q = q + goff; p.mu_ihx = s->mu_ihx; p.wgt = s->wgt;
     p.psi_in = psi_in; p.psi_out = psi_out; p.partial = partial; p.sync = (SweepSync *)sync;
     p.Z = s->Z;
     static const char *hints = getenv("AE_SWEEP_L2_HINTS");
     p.l2_hints = !(hints && hints[0] == '0');
     static const char *nofast = getenv("AE_SWEEP_NO_FAST");                // A/B and parity tests: general path only
-    p.tinfo = (nofast && nofast[0] == '1') ? nullptr : s->tile_info;
+    p.tinfo = ((nofast && nofast[0] == '1') || !s->tile_info) ? nullptr : s->tile_info + 2 * (goff / kTile);
     return ac == kACbig ? launch_shape<kACbig>(p, ctrl, gate, P_out, st) : launch_shape<kACsmall>(p, ctrl, gate, P_out, st);
 }
 
@@ -948,7 +952,9 @@ extern "C" int ae_sweep_set_phi(const ae_slab *s, const double *q, double *parti
 extern "C" int ae_reduce_partials(const ae_slab *s, const double *partial, int32_t P, double *phi, void *stream)
 {
     if (!s || !partial || !phi || P < 1) { ae::set_error("ae_reduce_partials: bad argument"); return AE_BAD_ARG; }
-    const int64_t n = (int64_t)s->G * s->Zp;
+    // group-sharded rank: the partials hold its gl groups; their sum goes to rows [g0, g0+gl) of phi
+    const int64_t n = (int64_t)(s->gl > 0 ? s->gl : s->G) * s->Zp;
+    if (s->gl > 0) phi += (int64_t)s->g0 * s->Zp;
     int64_t bx = (n / 2 + 255) / 256;
     if (bx > 148 * 32) bx = 148 * 32;
     ae::reduce_partials_kernel<<<(unsigned)bx, 256, 0, (cudaStream_t)stream>>>(partial, P, n, phi);

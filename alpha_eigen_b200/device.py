@@ -29,6 +29,22 @@ def shard_angles(mu: np.ndarray, rank: int, world: int) -> np.ndarray:
     return np.concatenate([mine[mu[mine] < 0], mine[mu[mine] >= 0]])
 
 
+def group_range(G: int, rank: int, world: int):
+    """(first group, number of groups) of `rank` in the balanced contiguous partition of G groups (ae_group_range)."""
+    base, rem = divmod(int(G), int(world))
+    return rank * base + min(rank, rem), base + (1 if rank < rem else 0)
+
+
+def shard_mode_for(G: int, world: int) -> str:
+    """How `world` ranks split the (angle x group) rows of a sweep set.  With at least two groups
+    per rank (and more groups than the one-thread-per-cell update kernel handles) ranks own whole GROUPS with all
+    angles: a group's flux needs no reduction and the only exchange is one all-gather of the new flux.  Otherwise
+    (one-group problems, few groups) ranks own ANGLES of every group and the flux is reduce-scattered."""
+    if world <= 1:
+        return "single"
+    return "group" if (G >= 2 * world and G > 8) else "angle"
+
+
 class Comm:
     """NCCL communicator created from a torch.distributed rendezvous (one process per GPU)."""
 
@@ -61,23 +77,24 @@ class Comm:
 
 
 class HostPipe:
-    """Double-buffered, cell-sharded host I/O for a stream of steps whose sources come from (and whose fluxes go
-    to) pinned host memory: the upload of step i+1's source and the download of step i-1's flux run on their own
-    CUDA streams (the copy engines) while step i's kernels run, so in steady state a step costs
-    max(kernels, copies) instead of their sum.  Usage per step i:
+    """Double-buffered, sharded host I/O for a stream of steps whose sources come from (and whose fluxes go to)
+    pinned host memory: the upload of step i+1's source and the download of step i-1's flux run on their own CUDA
+    streams (the copy engines) while step i's kernels run, so in steady state a step costs max(kernels, copies)
+    instead of their sum.  A rank moves only ITS share: its cell range of every group when the sweeps are
+    angle-sharded (the ranges are then all-gathered on the device), its own groups when they are group-sharded (no
+    exchange at all: a rank only ever reads the source rows of the groups it sweeps).  Usage per step i:
 
         pipe.feed(i, rows)              # main stream: wait for upload i, pack it into rows [G][Zp] (+ all-gather)
         pipe.upload(i + 1, next_host)   # copy stream: H2D of the next source, overlaps the kernels below
         ... kernels of step i ...
-        pipe.drain(i, flux_rows, out_host)   # main: unpack this rank's cells; copy stream: D2H into out_host
+        pipe.drain(i, flux_rows, out_host)   # main: unpack this rank's share; copy stream: D2H into out_host
 
     and pipe.wait() before the host touches the last results.  upload(0, ...) primes the pipe."""
 
     def __init__(self, dev: "SlabDevice"):
         torch = dev.torch
         self.dev = dev
-        _, count, _, _ = dev.cell_range()
-        n = max(count, 1) * dev.G
+        n = max(self.shard_shape()[0], 1) * self.shard_shape()[1]
         f64 = dict(dtype=torch.float64, device=dev.dev)
         self.stage_in = [torch.empty(n, **f64) for _ in range(2)]
         self.stage_out = [torch.empty(n, **f64) for _ in range(2)]
@@ -86,8 +103,15 @@ class HostPipe:
         self.in_ready, self.in_free, self.out_ready, self.out_free = ev(), ev(), ev(), ev()
         self.in_used, self.out_used = [False, False], [False, False]
 
+    def shard_shape(self):
+        """(cells, groups) of the host arrays this rank uploads / downloads per step."""
+        dev = self.dev
+        if dev.gl > 0:
+            return dev.Z, dev.gl
+        return dev.cell_range()[1], dev.G
+
     def upload(self, i, shard_host):
-        """Start the H2D copy of step i's source: pinned (count, G) tensor with this rank's cells."""
+        """Start the H2D copy of step i's source: pinned (cells, groups) tensor with this rank's share."""
         torch, k = self.dev.torch, i & 1
         with torch.cuda.stream(self.copy_in):
             if self.in_used[k]:
@@ -97,11 +121,16 @@ class HostPipe:
         self.in_used[k] = True
 
     def feed(self, i, rows):
-        """On the current stream: pack the uploaded source of step i into `rows` [G][Zp] (all ranks gather)."""
+        """On the current stream: pack the uploaded source of step i into `rows` [G][Zp]."""
         dev, k = self.dev, i & 1
         main = dev.torch.cuda.current_stream(dev.dev)
-        _, count, s0, cells = dev.cell_range()
         main.wait_event(self.in_ready[k])
+        if dev.gl > 0:                                              # own groups, all cells: rows [g0, g0+gl)
+            _lib.check(dev.lib.ae_pack_cells(self.stage_in[k].data_ptr(), dev.Z, dev.Zp, dev.gl,
+                                             rows.data_ptr() + 8 * dev.g0 * dev.Zp, dev.stream))
+            self.in_free[k].record(main)
+            return
+        _, count, s0, cells = dev.cell_range()
         _lib.check(dev.lib.ae_pack_cells_range(self.stage_in[k].data_ptr(), count, cells, dev.Zp, dev.G,
                                                rows.data_ptr() + 8 * s0, dev.stream))
         self.in_free[k].record(main)
@@ -109,15 +138,19 @@ class HostPipe:
             _lib.check(dev.lib.ae_comm_gather_rows(dev.comm.handle, rows.data_ptr(), dev.G, dev.Zp, dev.stream))
 
     def drain(self, i, rows, shard_host):
-        """Unpack this rank's cell range of `rows` [G][Zp] (current stream) and start its D2H copy."""
+        """Unpack this rank's share of `rows` [G][Zp] (current stream) and start its D2H copy."""
         dev, k = self.dev, i & 1
         torch = dev.torch
         main = torch.cuda.current_stream(dev.dev)
-        _, count, s0, cells = dev.cell_range()
         if self.out_used[k]:
             main.wait_event(self.out_free[k])                       # the download of step i-2 has left this slot
-        _lib.check(dev.lib.ae_unpack_cells_range(rows.data_ptr() + 8 * s0, count, cells, dev.Zp, dev.G,
-                                                 self.stage_out[k].data_ptr(), dev.stream))
+        if dev.gl > 0:
+            _lib.check(dev.lib.ae_unpack_cells(rows.data_ptr() + 8 * dev.g0 * dev.Zp, dev.Z, dev.Zp, dev.gl,
+                                               self.stage_out[k].data_ptr(), dev.stream))
+        else:
+            _, count, s0, cells = dev.cell_range()
+            _lib.check(dev.lib.ae_unpack_cells_range(rows.data_ptr() + 8 * s0, count, cells, dev.Zp, dev.G,
+                                                     self.stage_out[k].data_ptr(), dev.stream))
         self.out_ready[k].record(main)
         with torch.cuda.stream(self.copy_out):
             self.copy_out.wait_event(self.out_ready[k])
@@ -148,7 +181,7 @@ class SlabDevice:
     """
 
     def __init__(self, Z, hx, mu, weight, mat, total, scat, chi, nusf, invspeed, dt=None, s_ext=None,
-                 angles=None, comm: Comm | None = None, device=None, batch=None, flags=0):
+                 angles=None, comm: Comm | None = None, device=None, batch=None, flags=0, group_range_=None):
         torch = _torch()
         self.torch = torch
         self.lib = _lib.load()
@@ -162,11 +195,18 @@ class SlabDevice:
         self.angles = np.asarray(angles, dtype=np.int64)              # device angle a <-> reference angle angles[a]
         self.Z, self.hx = int(Z), float(hx)
         world = comm.world if comm is not None else 1
-        self.Zp = layout.padded_cells(self.Z, world)                  # equal 256-cell-aligned cell ranges per rank
+        # group-sharded: this rank sweeps groups [g0, g0+gl) with all angles; cells are not sharded then
+        self.g0, self.gl = (int(group_range_[0]), int(group_range_[1])) if group_range_ is not None else (0, 0)
+        self.shard_mode = "single" if comm is None else ("group" if self.gl > 0 else "angle")
+        self.Zp = layout.padded_cells(self.Z, 1 if self.gl > 0 else world)   # angle mode: equal 256-cell-aligned cell ranges per rank
         self.A_total = len(mu)
         self.A = len(self.angles)
         total = np.asarray(total, dtype=np.float64)
         self.M, self.G = total.shape
+        if self.gl > 0:
+            assert comm is not None and 0 <= self.g0 and self.g0 + self.gl <= self.G
+        self.Gl = self.gl if self.gl > 0 else self.G                  # groups whose psi / partials live on this rank
+        self.groups = np.arange(self.g0, self.g0 + self.Gl)
         self.dt = dt
         self.comm = comm
         mu_loc, w_loc = mu[self.angles], weight[self.angles]
@@ -195,12 +235,12 @@ class SlabDevice:
         f64 = dict(dtype=torch.float64, device=self.dev)
         self._phi_bufs = [torch.zeros(n, **f64), torch.zeros(n, **f64)]      # ping-pong pair, see `phi`
         self.phi_outer = torch.zeros(n, **f64)
-        self.reduced = torch.zeros(n, **f64) if comm is not None else None
+        self.reduced = torch.zeros(n, **f64) if (comm is not None and self.gl == 0) else None
         self.phi_fixed = torch.zeros(n, **f64) if dt is not None else None
         self.base = torch.zeros(n, **f64)
         self.q0 = torch.zeros(n, **f64)
         self.q1 = torch.zeros(n, **f64)
-        self.partial = torch.zeros(self.P * n, **f64)
+        self.partial = torch.zeros(self.P * self.Gl * self.Zp, **f64)
         self.scratch = torch.zeros(4 * int(self.lib.ae_norm_blocks(self.Zp)) + 2 * self.G, **f64)
         self.sync = torch.zeros(int(self.lib.ae_sweep_sync_bytes()), dtype=torch.uint8, device=self.dev)
         self.ctrl = torch.zeros(C.sizeof(_lib.AeCtrl), dtype=torch.uint8, device=self.dev)
@@ -211,7 +251,7 @@ class SlabDevice:
                                 self.t_w.data_ptr(), self.t_mat.data_ptr(), self.t_scat.data_ptr(),
                                 self.t_chi.data_ptr(), self.t_nusf.data_ptr(), self.t_hs.data_ptr(),
                                 self.t_cdt.data_ptr() if self.t_cdt is not None else None,
-                                self.t_sext.data_ptr() if self.t_sext is not None else None, None)
+                                self.t_sext.data_ptr() if self.t_sext is not None else None, None, self.g0, self.gl)
         self._build_tile_info()
         self.work = _lib.AeWork(self._phi_bufs[0].data_ptr(), self._phi_bufs[1].data_ptr(), self.phi_outer.data_ptr(),
                                 self.base.data_ptr(), self.q0.data_ptr(), self.q1.data_ptr(), self.partial.data_ptr(),
@@ -221,6 +261,19 @@ class SlabDevice:
                                 self.sync.data_ptr(), comm.handle.value if comm is not None else None, self.P, int(batch),
                                 int(flags), 0)
         self.last_q_index = 0
+
+    @classmethod
+    def sharded(cls, Z, hx, mu, weight, mat, total, scat, chi, nusf, invspeed, comm=None, **kw):
+        """The problem as THIS rank of `comm` holds it: whole groups when there are enough of them, else angles
+        (shard_mode_for); a plain single-GPU problem without a communicator."""
+        if comm is None:
+            return cls(Z, hx, mu, weight, mat, total, scat, chi, nusf, invspeed, **kw)
+        G = np.asarray(total).shape[1]
+        if shard_mode_for(G, comm.world) == "group":
+            return cls(Z, hx, mu, weight, mat, total, scat, chi, nusf, invspeed, comm=comm,
+                       group_range_=group_range(G, comm.rank, comm.world), **kw)
+        return cls(Z, hx, mu, weight, mat, total, scat, chi, nusf, invspeed, comm=comm,
+                   angles=shard_angles(np.asarray(mu, dtype=np.float64), comm.rank, comm.world), **kw)
 
     @classmethod
     def for_sweep(cls, Z, hx, mu, weight, sigT):
@@ -282,8 +335,8 @@ class SlabDevice:
     # ---- cell-sharded host I/O (several GPUs): this rank feeds / reads only its own cell range ------------
     def cell_range(self):
         """(first logical cell, logical cells, storage offset, storage cells) of this rank's share of a row."""
-        world = self.comm.world if self.comm is not None else 1
-        rank = self.comm.rank if self.comm is not None else 0
+        world = self.comm.world if (self.comm is not None and self.gl == 0) else 1
+        rank = self.comm.rank if (self.comm is not None and self.gl == 0) else 0
         zs = self.Zp // world
         z0 = rank * zs
         return z0, max(0, min(self.Z, z0 + zs) - z0), z0, zs
@@ -309,26 +362,27 @@ class SlabDevice:
         torch.cuda.current_stream(self.dev).synchronize()
 
     def psi_to_device(self, psi):
-        """(Z, A_total, G) logical, reference angle order -> [G][A][Zp] for the local angles."""
+        """(Z, A_total, G) logical, reference angle order -> [Gl][A][Zp] for the local angles and groups."""
         torch = self.torch
-        h = torch.from_numpy(np.ascontiguousarray(np.asarray(psi, dtype=np.float64).reshape(self.Z, self.A_total, self.G)))
+        a = np.asarray(psi, dtype=np.float64).reshape(self.Z, self.A_total, self.G)[:, :, self.g0:self.g0 + self.Gl]
+        h = torch.from_numpy(np.ascontiguousarray(a))
         d = h.to(self.dev)
-        out = torch.empty(self.G * self.A * self.Zp, dtype=torch.float64, device=self.dev)
-        _lib.check(self.lib.ae_pack_psi(d.data_ptr(), self.Z, self.Zp, self.A_total, self.G, self.t_aidx.data_ptr(), self.A,
+        out = torch.empty(self.Gl * self.A * self.Zp, dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.ae_pack_psi(d.data_ptr(), self.Z, self.Zp, self.A_total, self.Gl, self.t_aidx.data_ptr(), self.A,
                                         out.data_ptr(), self.stream))
         return out
 
     def psi_to_host(self, t):
-        """[G][A][Zp] -> (Z, A, G) for the local angles (device angle order)."""
+        """[Gl][A][Zp] -> (Z, A, Gl) for the local angles (device angle order) and groups."""
         torch = self.torch
-        d = torch.zeros(self.Z * self.A_total * self.G, dtype=torch.float64, device=self.dev)
-        _lib.check(self.lib.ae_unpack_psi(t.data_ptr(), self.Z, self.Zp, self.A_total, self.G, self.t_aidx.data_ptr(), self.A,
+        d = torch.zeros(self.Z * self.A_total * self.Gl, dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.ae_unpack_psi(t.data_ptr(), self.Z, self.Zp, self.A_total, self.Gl, self.t_aidx.data_ptr(), self.A,
                                           d.data_ptr(), self.stream))
-        full = d.cpu().numpy().reshape(self.Z, self.A_total, self.G)
+        full = d.cpu().numpy().reshape(self.Z, self.A_total, self.Gl)
         return np.ascontiguousarray(full[:, self.angles, :])
 
     def new_psi(self):
-        return self.torch.zeros(self.G * self.A * self.Zp, dtype=self.torch.float64, device=self.dev)
+        return self.torch.zeros(self.Gl * self.A * self.Zp, dtype=self.torch.float64, device=self.dev)
 
     # ---- C entry points --------------------------------------------------------------------
     def sweep_set(self, q, psi_in=None, psi_out=None):
@@ -340,9 +394,17 @@ class SlabDevice:
         phi = self.torch.empty(self.G * self.Zp, dtype=self.torch.float64, device=self.dev)
         _lib.check(self.lib.ae_reduce_partials(C.byref(self.slab), self.partial.data_ptr(), self.P, phi.data_ptr(),
                                                self.stream))
-        if self.comm is not None:
-            self.comm.allreduce_(phi)
+        self._complete_flux(phi)
         return phi
+
+    def _complete_flux(self, phi):
+        """Make a locally reduced flux [G][Zp] whole: sum over ranks (angle-sharded) or gather the ranks' groups."""
+        if self.comm is None:
+            return
+        if self.gl > 0:
+            _lib.check(self.lib.ae_comm_gather_groups(self.comm.handle, phi.data_ptr(), self.G, self.Zp, self.stream))
+        else:
+            self.comm.allreduce_(phi)
 
     def sweep_set_phi(self, q):
         """ae_sweep_set_phi + ae_reduce_partials: scalar flux [G][Zp] of a sweep set without angular flux in or out
@@ -353,8 +415,7 @@ class SlabDevice:
         phi = self.torch.empty(self.G * self.Zp, dtype=self.torch.float64, device=self.dev)
         _lib.check(self.lib.ae_reduce_partials(C.byref(self.slab), self.partial.data_ptr(), P.value, phi.data_ptr(),
                                                self.stream))
-        if self.comm is not None:
-            self.comm.allreduce_(phi)
+        self._complete_flux(phi)
         self.last_phi_partials = P.value
         return phi
 

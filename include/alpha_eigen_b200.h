@@ -68,6 +68,10 @@ typedef struct ae_slab {
     const double *tile_info; /* [G][Zp/AE_TILE][2] records written by ae_tile_info for THESE hs / cdt arrays, or NULL.
                                 Lets the sweep skip the per-cell reciprocals in tiles whose cells share one sigT
                                 (material regions, slab.py:33-56); results are bit-identical with and without it */
+    int32_t g0, gl;          /* group-sharded ranks (several GPUs, G >= 2 ranks): this rank sweeps groups [g0, g0+gl) with ALL
+                                angles and psi / partial hold only those groups ([gl][A][Zp], [P][gl][Zp]); every other array
+                                keeps all G rows.  A group's flux is then complete on its owner: no reduction, one all-gather
+                                of the new flux per source iteration.  gl = 0: not group-sharded (one GPU, or angle-sharded) */
 } ae_slab;
 
 /* Mutable buffers, all caller-allocated (torch owns the memory). */
@@ -244,6 +248,10 @@ int ae_dmd_from_r(const double *r, int32_t K, double dt, double rank_tol,
 int ae_comm_unique_id(void *id128);                                     /* host, 128 bytes */
 int ae_comm_init(void **comm, int32_t rank, int32_t nranks, const void *id128);
 int ae_comm_allreduce_sum(void *comm, double *buf, int64_t count, void *stream);
+/* Group-sharded ranks: rows [G][Zp], rank r contributes rows [g0_r, g0_r + gl_r) of the balanced contiguous
+ * partition of the G groups (ae_group_range), in place. */
+int ae_comm_gather_groups(void *comm, double *rows, int32_t G, int64_t Zp, void *stream);
+void ae_group_range(int32_t G, int32_t nranks, int32_t rank, int32_t *g0, int32_t *gl);
 /* rows [G][Zp]: every rank contributes its cell range of every row, in place (all-gather). */
 int ae_comm_gather_rows(void *comm, double *rows, int32_t G, int64_t Zp, void *stream);
 int ae_comm_destroy(void *comm);

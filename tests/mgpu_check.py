@@ -2,8 +2,9 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
 
-Angle-sharded power iteration, time march and DMD (row-sharded TSQR + Gram) against the single-process
-oracle: identical iteration counts, k to 1e-9, flux to 1e-10, alpha to the single-GPU answer.
+Angle-sharded (one-group K-P) and group-sharded (16-group synthetic slab) power iteration, time march and DMD
+(row-sharded TSQR + Gram) against the single-process oracle: identical iteration counts, k to 1e-9, flux to 1e-10,
+alpha to the single-GPU answer.
 """
 import os
 import sys
@@ -61,9 +62,45 @@ def main():
     G = devt.gram(snap, n_psi, first, K + 1).cpu().numpy().reshape(K + 1, K + 1)
     Sf = res["psi_snap"].reshape(-1, steps)[:, first:first + K + 1]
     assert np.max(np.abs(G - Sf.T @ Sf)) < 1e-13 * np.max(np.abs(Sf.T @ Sf))
+    # ---- group-sharded: 16 groups, S64 (the rows-per-warp phi kernel), streaming kernels ---------------------------
+    from alpha_eigen_b200.synthetic import synthetic_problem
+    q = synthetic_problem(1500, 64, 16)
+    qt = orc.Tables(q["mat"], q["total"], q["scat"], q["chi"], q["nusf"], q["invspeed"])
+    rs = np.random.RandomState(5)
+    half = rs.rand(q["Z"], q["G"])
+    phi0 = half + half[::-1]
+    mk = lambda **kw: SlabDevice.sharded(q["Z"], q["hx"], q["mu"], q["weight"], qt.mat, qt.total, qt.scat, qt.chi, qt.nusf,
+                                         qt.invspeed, comm=comm, flags=1, **kw)
+    dg = mk()
+    assert dg.shard_mode == ("group" if world <= 8 else "angle"), dg.shard_mode
+    rg = dg.power_iteration(phi0)
+    og = orc.power_iteration(q["mu"], q["weight"], q["hx"], qt, phi0)
+    assert rg["status"] == 0 and list(rg["si_hist"]) == list(og["si_hist"]), (rg["si_hist"], og["si_hist"])
+    assert abs(rg["k_new"] - og["k_new"]) < 1e-9, (rg["k_new"], og["k_new"])
+    assert rel(rg["phi_new"], og["phi_new"]) < 1e-10
+    psi0 = rs.rand(q["Z"], q["A"], q["G"])
+    s_ext = rs.rand(q["Z"], q["G"]) * 0.1
+    dgt = mk(dt=0.1, s_ext=s_ext)
+    pg = dgt.psi_to_device(psi0)
+    gsteps = 10
+    n_pg = dgt.Gl * dgt.A * dgt.Zp
+    gsnap = torch.zeros(gsteps * n_pg, dtype=torch.float64, device=dgt.dev)
+    st, outer, inner = dgt.time_march(pg, gsteps, 1e-10, gsnap, None)
+    rm = orc.time_march(q["mu"], q["weight"], q["hx"], qt, s_ext, psi0, 0.1, gsteps)
+    assert st == 0 and list(outer) == list(rm["outer"]) and list(inner) == list(rm["inner"])
+    assert rel(dgt.cells_to_host(dgt.phi), rm["phi_last"]) < 1e-10
+    assert rel(dgt.psi_to_host(pg), rm["psi_last"][:, dgt.angles, :][..., dgt.groups]) < 1e-10
+    gfirst, gK = dmd_window(gsteps)
+    Rg = dgt.tsqr(gsnap, n_pg, gfirst, gK + 1)                       # rows of this rank's groups; factors merged across ranks
+    alg, sigg, rkg = dgt.dmd_from_r(Rg, gK, 0.1)
+    Sg = rm["psi_snap"].reshape(-1, gsteps)[:, gfirst:gfirst + gK]
+    svg = np.linalg.svd(Sg, compute_uv=False)
+    assert np.max(np.abs(sigg[:len(svg)] - svg)) < 1e-13 * svg[0], np.max(np.abs(sigg[:len(svg)] - svg)) / svg[0]
     if rank == 0:
         print(f"mgpu_check ok on {world} GPUs: k={rd['k_new']:.15f} (oracle {ro['k_new']:.15f}), "
-              f"alpha0={srt(al)[0]:.12g} (reference routine {srt(ref)[0]:.12g}, rel diff {dom_err:.2e}), rank {r}")
+              f"alpha0={srt(al)[0]:.12g} (reference routine {srt(ref)[0]:.12g}, rel diff {dom_err:.2e}), rank {r}; "
+              f"group-sharded 16-group slab: k={rg['k_new']:.15f} (oracle {og['k_new']:.15f}), {gsteps} steps, "
+              f"iterations {int(np.sum(inner))} == oracle")
     distributed.shutdown()
 
 
