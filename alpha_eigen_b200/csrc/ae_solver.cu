@@ -239,7 +239,8 @@ extern "C" int ae_time_march(const ae_slab *s, ae_work *w, double *psi, double *
     cudaStream_t st = (cudaStream_t)stream;
     AE_TRY(check_work(s, w, "ae_time_march"));
     if (!psi) { set_error("ae_time_march: psi missing"); return AE_BAD_ARG; }
-    const size_t n_phi = (size_t)s->G * s->Zp, n_psi = n_phi * s->A;
+    // psi holds the groups this rank sweeps (all of them unless group-sharded); phi always has all G rows
+    const size_t n_phi = (size_t)s->G * s->Zp, n_psi = (size_t)(s->gl > 0 ? s->gl : s->G) * s->Zp * s->A;
     // small slabs: every step, loop and snapshot in one cooperative kernel (ae_small.cu)
     if (num_steps > 0) {
         int32_t *d_hist = nullptr;

@@ -21,7 +21,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 
 from . import _lib, distributed
-from .device import SlabDevice, shard_angles
+from .device import SlabDevice
 from .synthetic import synthetic_materials, region_index
 from .time_unit import dmd_window
 
@@ -49,12 +49,11 @@ def synthetic_ensemble(E, Z, A, G, seed=2021, length=9.0):
 def solve_member(p, dt, num_steps, comm=None, tol=1e-10, rank_tol=1e-13, keep_snapshots=False):
     """Time march + DMD of one member on the current CUDA stream.  Returns a dict with alphas etc."""
     import torch
-    angles = shard_angles(p["mu"], comm.rank, comm.world) if comm is not None else None
-    dev = SlabDevice(p["Z"], p["hx"], p["mu"], p["weight"], p["mat"], p["total"], p["scat"], p["chi"], p["nusf"],
-                     p["invspeed"], dt=dt, s_ext=p.get("s_ext"), angles=angles, comm=comm)
+    dev = SlabDevice.sharded(p["Z"], p["hx"], p["mu"], p["weight"], p["mat"], p["total"], p["scat"], p["chi"], p["nusf"],
+                             p["invspeed"], comm=comm, dt=dt, s_ext=p.get("s_ext"))
     psi0 = np.repeat(0.5 * p["phi0"][:, None, :], p["A"], axis=1)          # isotropic psi0 = phi0 / 2
     psi = dev.psi_to_device(psi0)
-    n_psi = dev.G * dev.A * dev.Zp
+    n_psi = dev.Gl * dev.A * dev.Zp
     snap = torch.zeros(num_steps * n_psi, dtype=torch.float64, device=dev.dev)
     st, outer, inner = dev.time_march(psi, num_steps, tol, snap, None)
     out = dict(status=st, outer=outer, inner=inner)
@@ -64,6 +63,7 @@ def solve_member(p, dt, num_steps, comm=None, tol=1e-10, rank_tol=1e-13, keep_sn
     if keep_snapshots:
         out["psi_last"] = dev.psi_to_host(psi)
         out["angles"] = dev.angles
+        out["groups"] = dev.groups
         out["snap"] = snap
         out["dev"] = dev
     return out

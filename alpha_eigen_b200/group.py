@@ -7,7 +7,7 @@ the reference; the method bodies hand the arithmetic to the sm_100a kernels thro
 import numpy as np
 
 from . import _lib, distributed
-from .device import SlabDevice, shard_angles
+from .device import SlabDevice
 from .eigenvalue import Eigenvalue
 from .material import material_row
 from .one_direction import OneDirection
@@ -137,9 +137,7 @@ class OneGroup:
             return hit[1]
         comm = distributed.communicator()
         mu = np.asarray(self.slab.mu, dtype=np.float64)
-        angles = shard_angles(mu, comm.rank, comm.world) if comm is not None else None
-        dev = SlabDevice(self.slab.num_zones, self.slab.hx, mu, self.slab.weight, *tabs, dt=dt, s_ext=sx,
-                         angles=angles, comm=comm)
+        dev = SlabDevice.sharded(self.slab.num_zones, self.slab.hx, mu, self.slab.weight, *tabs, comm=comm, dt=dt, s_ext=sx)
         self._dev[dt] = (key, dev)
         return dev
 
@@ -151,9 +149,16 @@ class OneGroup:
         self._psi_replay = None
         psi = dev.new_psi()
         dev.sweep_set(dev.q1 if dev.last_q_index else dev.q0, psi_in=psi_in, psi_out=psi)
-        host = dev.psi_to_host(psi)                 # (Z, A_local, G)
+        self._store_psi(dev, dev.psi_to_host(psi))
+
+    def _store_psi(self, dev, host):
+        """host: (Z, A_local, G_local) angular flux of this rank's rows -> angle[n].psi_midpoint (Z, G); entries of
+        rows other ranks own stay zero."""
+        Z, G = self.slab.num_zones, self.slab.num_groups
         for a, n in enumerate(dev.angles):
-            self.angle[n]._psi_midpoint = host[:, a, :].copy()
+            full = np.zeros((Z, G))
+            full[:, dev.groups] = host[:, a, :]
+            self.angle[n]._psi_midpoint = full
 
     # ------------------------------------------------------------------ solver surface ----
     def sweep1D(self, angle, source, sigT=None):

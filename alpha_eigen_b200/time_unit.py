@@ -65,14 +65,14 @@ class TimeUnit:
 
     @property
     def psi(self):
-        """(Z, A, G, steps), reference angle order; angles owned by other ranks are zero."""
+        """(Z, A, G, steps), reference angle order; angles / groups owned by other ranks are zero."""
         if self._psi_host is None:
             s = self.slab
             out = np.zeros((s.num_zones, s.num_angles, s.num_groups, self.num_steps))
             if self._psi_snap is not None:
                 dev = self._dev
-                a = from_storage(self._psi_snap.cpu().numpy().reshape(self.num_steps, dev.G, dev.A, dev.Zp), dev.Z)
-                out[:, dev.angles, :, :] = np.transpose(a, (3, 2, 1, 0))
+                a = from_storage(self._psi_snap.cpu().numpy().reshape(self.num_steps, dev.Gl, dev.A, dev.Zp), dev.Z)
+                out[np.ix_(np.arange(s.num_zones), dev.angles, dev.groups)] = np.transpose(a, (3, 2, 1, 0))
             self._psi_host = out
         return self._psi_host
 
@@ -97,7 +97,7 @@ class TimeUnit:
         self._dev = dev
         psi = dev.psi_to_device(self._initial_psi())
         f64 = dict(dtype=torch.float64, device=dev.dev)
-        self._psi_snap = torch.zeros(self.num_steps * dev.G * dev.A * dev.Zp, **f64) if self.snapshots == "psi" else None
+        self._psi_snap = torch.zeros(self.num_steps * dev.Gl * dev.A * dev.Zp, **f64) if self.snapshots == "psi" else None
         self._phi_snap = torch.zeros(self.num_steps * dev.G * dev.Zp, **f64)
         self._psi_host = self._phi_host = None
         st, outer, inner = dev.time_march(psi, self.num_steps, 1e-10, self._psi_snap, self._phi_snap)
@@ -110,9 +110,7 @@ class TimeUnit:
         _lib.check(st)
         g.phi.new = dev.cells_to_host(dev.phi)                          # R3
         g._psi_replay = None
-        last = dev.psi_to_host(psi)
-        for a, n in enumerate(dev.angles):
-            g.angle[n]._psi_midpoint = last[:, a, :].copy()             # time_unit.py:26-27
+        g._store_psi(dev, dev.psi_to_host(psi))                         # time_unit.py:26-27
 
     def calculate_one_step_flux(self, source, sigT=None, tolerance=1e-10):
         """time_unit.py:29-42 (+R3,R4): one step for an explicit per-angle source (Z,A,G).
@@ -132,9 +130,7 @@ class TimeUnit:
                                  else "Warning: source iteration did not converge")
         _lib.check(st)
         g.phi.new = dev.cells_to_host(dev.phi)
-        host = dev.psi_to_host(psi_out)
-        for a, n in enumerate(dev.angles):
-            g.angle[n]._psi_midpoint = host[:, a, :].copy()
+        g._store_psi(dev, dev.psi_to_host(psi_out))
         g._psi_replay = None
         return outer, inner
 
@@ -172,7 +168,7 @@ class TimeUnit:
             rows = [dev.psi_to_device(h[..., st]) for st in range(self.num_steps)]
             self._psi_snap = dev.torch.cat(rows)
         if self.snapshots == "psi" and self._psi_snap is not None:
-            snap, row_len, sharded = self._psi_snap, dev.G * dev.A * dev.Zp, True      # rows of this rank's angles
+            snap, row_len, sharded = self._psi_snap, dev.Gl * dev.A * dev.Zp, True     # rows of this rank's angles / groups
         else:
             snap, row_len, sharded = self._phi_snap, dev.G * dev.Zp, False            # phi is replicated on every rank
         if snap is None:
