@@ -9,6 +9,7 @@
 // step; it is done with FP64 tensor-core DMMA (mma.sync.m8n8k4.f64 -- tcgen05 has no FP64 kind)
 // and reduced deterministically.  The K x K symmetric and non-symmetric eigenproblems go to
 // cuSOLVER (plain library calls on tiny matrices).
+#include <cublas_v2.h>
 #include <cusolverDn.h>
 #include <math.h>
 #include <stdlib.h>
@@ -305,6 +306,65 @@ static int solver_ctx(cudaStream_t st, cusolverDnHandle_t *h, cusolverDnParams_t
         if (e_ != cudaSuccess) { status = cuda_fail(e_, #call, __FILE__, __LINE__); goto done; } \
     } while (0)
 
+// ---- windows wider than kGN snapshots --------------------------------------------------------------------------
+// The hand-written Gram and TSQR kernels keep one 128-column operand per CTA (registers / shared memory), which covers
+// the benchmark windows (K + 1 = 116 at 200 steps).  The reference takes any step count (time_unit.py:62-72); wider
+// windows go through plain library calls on the same data: the snapshot rows [n][ld] ARE the column-major len x n tall
+// matrix, so its R factor is cusolverDnDgeqrf on a scratch copy (blocked Householder, backward stable like the TSQR
+// kernel) and its Gram matrix one cublasDgemm.  Slower per column than the kernels; the answers obey the same tests.
+static thread_local cublasHandle_t t_blas = nullptr;
+static int blas_ctx(cudaStream_t st, cublasHandle_t *h)
+{
+    if (!t_blas && cublasCreate(&t_blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return AE_CUDA_ERROR; }
+    if (cublasSetStream(t_blas, st) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetStream failed"); return AE_CUDA_ERROR; }
+    *h = t_blas;
+    return AE_OK;
+}
+
+// upper triangle of a column-major m x n factored matrix (ld = lda) -> row-major n x n, zeros below the diagonal
+__global__ void extract_r_kernel(const double *__restrict__ a, int64_t lda, int n, int64_t rows, double *__restrict__ r)
+{
+    for (int idx = threadIdx.x + blockIdx.x * blockDim.x; idx < n * n; idx += blockDim.x * gridDim.x) {
+        const int i = idx / n, j = idx % n;
+        r[idx] = (j >= i && i < rows) ? a[(int64_t)j * lda + i] : 0.0;
+    }
+}
+
+// R factor of the column-major tall matrix `a` (len x n, leading dimension lda), which is overwritten.
+static int geqrf_r(double *a, int64_t lda, int64_t len, int n, double *r_out, cudaStream_t st)
+{
+    int status = AE_OK;
+    cusolverDnHandle_t h = nullptr;
+    cusolverDnParams_t params = nullptr;
+    double *tau = nullptr, *work = nullptr;
+    int *dinfo = nullptr, lwork = 0, info = 0;
+    if ((status = solver_ctx(st, &h, &params)) != AE_OK) return status;
+    if (len > 2147483647LL || lda > 2147483647LL) { set_error("ae_tsqr: window wider than %d snapshots needs fewer than 2^31 rows per rank", kGN); return AE_BAD_ARG; }
+    AE_CUDA_G(cudaMallocAsync((void **)&tau, sizeof(double) * n, st));
+    AE_CUDA_G(cudaMallocAsync((void **)&dinfo, sizeof(int), st));
+    AE_CUSOLVER(cusolverDnDgeqrf_bufferSize(h, (int)len, n, a, (int)lda, &lwork));
+    AE_CUDA_G(cudaMallocAsync((void **)&work, sizeof(double) * (size_t)lwork, st));
+    AE_CUSOLVER(cusolverDnDgeqrf(h, (int)len, n, a, (int)lda, tau, work, lwork, dinfo));
+    AE_CUDA_G(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AE_CUDA_G(cudaStreamSynchronize(st));
+    if (info != 0) { set_error("geqrf info=%d", info); status = AE_CUDA_ERROR; goto done; }
+    extract_r_kernel<<<64, 256, 0, st>>>(a, lda, n, len, r_out);
+    AE_CUDA_G(cudaGetLastError());
+done:
+    cudaFreeAsync(tau, st); cudaFreeAsync(work, st); cudaFreeAsync(dinfo, st);
+    return status;
+}
+
+// row-major [rows][n] -> column-major rows x n (the stacked triangles of a merge are row-major)
+__global__ void transpose_rows_kernel(const double *__restrict__ in, int64_t rows, int n, double *__restrict__ out)
+{
+    for (int64_t idx = threadIdx.x + (int64_t)blockIdx.x * blockDim.x; idx < rows * n; idx += (int64_t)blockDim.x * gridDim.x) {
+        const int64_t i = idx / n;
+        const int j = (int)(idx % n);
+        out[(int64_t)j * rows + i] = in[idx];
+    }
+}
+
 }  // namespace ae
 
 using namespace ae;
@@ -312,9 +372,17 @@ using namespace ae;
 extern "C" int ae_gram(const double *snap, int64_t ld, int64_t len, int32_t n, double *gram, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!snap || !gram || n < 1 || n > kGN || len < 1 || ld < len) {
-        set_error("ae_gram: bad argument (n=%d must be <= %d)", n, kGN);
-        return AE_BAD_ARG;
+    if (!snap || !gram || n < 1 || len < 1 || ld < len) { set_error("ae_gram: bad argument (n=%d)", n); return AE_BAD_ARG; }
+    if (n > kGN) {                                      // wide window: one library GEMM, G = B^T B with B = snap as len x n column-major
+        cublasHandle_t bh = nullptr;
+        AE_TRY(blas_ctx(st, &bh));
+        if (len > 2147483647LL || ld > 2147483647LL) { set_error("ae_gram: window wider than %d snapshots needs fewer than 2^31 rows per rank", kGN); return AE_BAD_ARG; }
+        const double one = 1.0, zero = 0.0;
+        if (cublasDgemm(bh, CUBLAS_OP_T, CUBLAS_OP_N, n, n, (int)len, &one, snap, (int)ld, snap, (int)ld, &zero, gram, n) != CUBLAS_STATUS_SUCCESS) {
+            set_error("cublasDgemm failed");
+            return AE_CUDA_ERROR;
+        }
+        return AE_OK;
     }
     int nparts = 148 * 2;
     int64_t cols = (len + nparts - 1) / nparts;
@@ -334,7 +402,7 @@ extern "C" int ae_dmd_from_gram(const double *gram_dev, int32_t K, double dt, do
                                 double *alpha_im, double *sigma_out, int32_t *rank, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!gram_dev || K < 1 || K + 1 > kGN || !alpha_re || !alpha_im || !rank) {
+    if (!gram_dev || K < 1 || !alpha_re || !alpha_im || !rank) {
         set_error("ae_dmd_from_gram: bad argument");
         return AE_BAD_ARG;
     }
@@ -436,7 +504,16 @@ static int tsqr_merge_tree(double *in, double *scratch, int count, int n, double
 extern "C" int ae_tsqr(const double *snap, int64_t ld, int64_t len, int32_t n, double *r_out, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!snap || !r_out || n < 1 || n > kGN || len < 1) { set_error("ae_tsqr: bad argument (n=%d)", n); return AE_BAD_ARG; }
+    if (!snap || !r_out || n < 1 || len < 1) { set_error("ae_tsqr: bad argument (n=%d)", n); return AE_BAD_ARG; }
+    if (n > kGN) {                                      // wide window: library QR on a scratch copy of the window
+        double *copy = nullptr;
+        AE_CUDA(cudaMallocAsync((void **)&copy, sizeof(double) * (size_t)len * n, st));
+        cudaError_t e = cudaMemcpy2DAsync(copy, sizeof(double) * len, snap, sizeof(double) * ld, sizeof(double) * len, n,
+                                          cudaMemcpyDeviceToDevice, st);
+        int rc = e == cudaSuccess ? geqrf_r(copy, len, len, n, r_out, st) : cuda_fail(e, "cudaMemcpy2DAsync", __FILE__, __LINE__);
+        cudaFreeAsync(copy, st);
+        return rc;
+    }
     int dev = 0, ncta = 148;
     AE_CUDA(cudaGetDevice(&dev));
     AE_CUDA(cudaDeviceGetAttribute(&ncta, cudaDevAttrMultiProcessorCount, dev));
@@ -455,7 +532,17 @@ extern "C" int ae_tsqr(const double *snap, int64_t ld, int64_t len, int32_t n, d
 extern "C" int ae_tsqr_merge(const double *r_stack, int32_t count, int32_t n, double *r_out, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!r_stack || !r_out || count < 1 || n < 1 || n > kGN) { set_error("ae_tsqr_merge: bad argument"); return AE_BAD_ARG; }
+    if (!r_stack || !r_out || count < 1 || n < 1) { set_error("ae_tsqr_merge: bad argument"); return AE_BAD_ARG; }
+    if (n > kGN) {                                      // wide window: QR of the stacked triangles through the library
+        const int64_t rows = (int64_t)count * n;
+        double *cm = nullptr;
+        AE_CUDA(cudaMallocAsync((void **)&cm, sizeof(double) * (size_t)rows * n, st));
+        transpose_rows_kernel<<<256, 256, 0, st>>>(r_stack, rows, n, cm);
+        cudaError_t e = cudaGetLastError();
+        int rc = e == cudaSuccess ? geqrf_r(cm, rows, rows, n, r_out, st) : cuda_fail(e, "transpose_rows_kernel", __FILE__, __LINE__);
+        cudaFreeAsync(cm, st);
+        return rc;
+    }
     return tsqr_launch(r_stack, n, (int64_t)count * n, n, true, (int64_t)count * n, 1, r_out, st);
 }
 
@@ -463,7 +550,7 @@ extern "C" int ae_dmd_from_r(const double *r_dev, int32_t K, double dt, double r
                              double *alpha_im, double *sigma_out, int32_t *rank, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!r_dev || K < 1 || K + 1 > kGN || !alpha_re || !alpha_im || !rank) { set_error("ae_dmd_from_r: bad argument"); return AE_BAD_ARG; }
+    if (!r_dev || K < 1 || !alpha_re || !alpha_im || !rank) { set_error("ae_dmd_from_r: bad argument"); return AE_BAD_ARG; }
     int status = AE_OK;
     const int n = K + 1;
     cusolverDnHandle_t h = nullptr;

@@ -76,6 +76,8 @@ class OneGroup:
         if self.material is None and hasattr(s, "assign_all"):
             draws = np.random.rand(Z, G) * 2        # == Z successive rand(G)*2 draws (zone.py:11, phi.py:8)
             mats, names, idx = s.assign_all(mid)
+            if np.any(idx < 0):                     # the reference leaves material = None there and fails at the first use
+                raise AttributeError("zone midpoint %r lies in no region of the slab" % float(mid[int(np.argmax(idx < 0))]))
             self.zone = _LazyZones(s, mid, mats, names, idx, draws)
         else:
             zones, mats, idx = [], [], np.empty(Z, dtype=np.int64)
@@ -129,9 +131,18 @@ class OneGroup:
     def _device(self, dt=None, s_ext=None):
         tabs = self._tables()
         sx = None if s_ext is None else np.asarray(s_ext, dtype=np.float64)
-        key = (dt, self.slab.hx, tuple(np.asarray(self.slab.mu)), tuple(a.tobytes() if a.size < 4096 else (a.shape, float(a.sum()), float((a * a).sum()))
-                                                                        for a in map(np.asarray, tabs)),
-               None if sx is None else (sx.shape, float(sx.sum()), float((sx * sx).sum())))
+        # the resident problem is reused only for IDENTICAL inputs: a digest over every byte of the tables, the source
+        # and the quadrature (sums would not notice a point source that moved or a permuted material map)
+        import hashlib
+        h = hashlib.blake2b(digest_size=16)
+        for a in (*tabs, sx, self.slab.mu, self.slab.weight):
+            if a is None:
+                h.update(b"-")
+            else:
+                a = np.ascontiguousarray(a)
+                h.update(str((a.shape, a.dtype.str)).encode())
+                h.update(a.tobytes())
+        key = (dt, self.slab.hx, h.hexdigest())
         hit = self._dev.get(dt)
         if hit is not None and hit[0] == key:
             return hit[1]

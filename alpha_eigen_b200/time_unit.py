@@ -103,14 +103,30 @@ class TimeUnit:
         st, outer, inner = dev.time_march(psi, self.num_steps, 1e-10, self._psi_snap, self._phi_snap)
         self.outer_iterations, self.inner_iterations = outer, inner
         if st == _lib.AE_NOT_CONVERGED:
-            failed = int(np.argmax(outer == 0)) if np.any(outer == 0) else len(outer) - 1
-            flux = outer[max(failed - 1, 0)] >= 99 if failed else outer[0] >= 99
-            raise AssertionError("Warning: time-dependent flux iteration did not converge" if flux
+            # the failing step is the last one with a recorded count (steps after it stay 0)
+            done = np.flatnonzero(outer != 0)
+            failed = int(done[-1]) if len(done) else 0
+            raise AssertionError("Warning: time-dependent flux iteration did not converge" if outer[failed] >= 99
                                  else "Warning: source iteration did not converge")
         _lib.check(st)
         g.phi.new = dev.cells_to_host(dev.phi)                          # R3
         g._psi_replay = None
         g._store_psi(dev, dev.psi_to_host(psi))                         # time_unit.py:26-27
+
+    def _check_sigT(self, sigT):
+        """The device problem carries sigT = total_xs + inv_speed/dt (time_unit.py:24).  A caller-supplied sigT must be
+        that very array (anything else would be silently ignored); returns cdt = inv_speed/dt shaped (Z,1,G), which must
+        be non-zero because the per-angle source is handed to the kernel as source/cdt."""
+        g, s = self.group, self.slab
+        inv = np.asarray(g.inv_speed, dtype=np.float64).reshape(s.num_zones, s.num_groups)
+        if sigT is not None:
+            want = np.asarray(g.total_xs, dtype=np.float64).reshape(s.num_zones, s.num_groups) + inv / self.dt
+            got = np.asarray(sigT, dtype=np.float64).reshape(s.num_zones, s.num_groups)
+            if not np.allclose(got, want, rtol=1e-13, atol=0.0):
+                raise ValueError("sigT must equal group.total_xs + group.inv_speed/dt (time_unit.py:24); set those instead")
+        if np.any(inv == 0.0):
+            raise ValueError("group.inv_speed has zeros: the time-dependent source psi*inv_speed/dt is undefined there")
+        return (inv / self.dt).reshape(s.num_zones, 1, s.num_groups)
 
     def calculate_one_step_flux(self, source, sigT=None, tolerance=1e-10):
         """time_unit.py:29-42 (+R3,R4): one step for an explicit per-angle source (Z,A,G).
@@ -120,8 +136,8 @@ class TimeUnit:
         g = self.group
         s = self.slab
         dev = g._device(dt=self.dt, s_ext=None)
+        cdt = self._check_sigT(sigT)
         # the kernel's angular source is q + cdt*psi_in: feed psi_in = source/cdt
-        cdt = (np.asarray(g.inv_speed, dtype=np.float64) / self.dt).reshape(s.num_zones, 1, s.num_groups)
         psi_in = dev.psi_to_device(np.asarray(source, dtype=np.float64).reshape(s.num_zones, s.num_angles, s.num_groups) / cdt)
         psi_out = dev.new_psi()
         st, outer, inner = dev.time_step(psi_in, psi_out, tolerance)
@@ -141,7 +157,7 @@ class TimeUnit:
         group.phi.new (the reference assigns it to an attribute of an ndarray and loses it)."""
         g, s = self.group, self.slab
         dev = g._device(dt=self.dt, s_ext=None)
-        cdt = (np.asarray(g.inv_speed, dtype=np.float64) / self.dt).reshape(s.num_zones, 1, s.num_groups)
+        cdt = self._check_sigT(sigT)
         psi_in = dev.psi_to_device(np.asarray(source, dtype=np.float64).reshape(s.num_zones, s.num_angles, s.num_groups) / cdt)
         zero = dev.torch.zeros(dev.G * dev.Zp, dtype=dev.torch.float64, device=dev.dev)
         st, iters = dev.source_iteration(zero, psi_in, 0.0, tolerance, 100)

@@ -97,7 +97,35 @@ def case_kp_alpha(out, cpm, A, steps, check_oracle=True):
     out(line)
 
 
-def case_c3_alpha(out, Z=100_000, A=64, G=70, steps=200):
+def well_posed(orc, snaps, steps, dev, R, gram, K, srt):
+    """The reference's rank rule (keep sigma_j while the tail sum exceeds 1e-13 of the total, time_unit.py:75-76) keeps
+    ~31 modes of the C3 window, down to sigma_j = 2e-13 sigma_1: the top of its spectrum is then complex noise pairs
+    (|Im alpha| ~ 4-5) that differ between ANY two factorizations, LAPACK's included.  Two comparisons that are
+    well posed: (1) the same routine with the rule's threshold at 1e-8 (modes above the Gram route's resolution),
+    (2) the largest REAL alpha -- the physical fundamental mode -- at the reference's own threshold."""
+    import numpy as np
+    out = {}
+    tol = 1e-8
+    skip = int(steps / 5); num_included = int(steps - skip - steps / 50); it = num_included - 1
+    X = np.ascontiguousarray(snaps[:, 2 * skip:skip + it]); Y = np.ascontiguousarray(snaps[:, 2 * skip + 1:skip + it + 1])
+    U, S, V = np.linalg.svd(X, full_matrices=False)
+    r = int(np.sum(1 - np.cumsum(S) / np.sum(S) > tol))
+    At = (U[:, :r].T @ Y) @ V[:r, :].T @ np.diag(1 / S[:r])
+    ref = srt((1 - 1.0 / np.linalg.eig(At)[0]) / 0.1)
+    a_t, _, r_t = dev.dmd_from_r(R, K, 0.1, tol)
+    a_g, _, r_g = dev.dmd_from_gram(gram, K, 0.1, tol)
+    a_t, a_g = srt(a_t), srt(a_g)
+    out["rank_tol_1e-8"] = {"host_rank": r, "tsqr_rank": int(r_t), "gram_rank": int(r_g),
+                            "host_alpha0": [float(ref[0].real), float(ref[0].imag)],
+                            "tsqr_alpha0": [float(a_t[0].real), float(a_t[0].imag)],
+                            "gram_alpha0": [float(a_g[0].real), float(a_g[0].imag)],
+                            "alpha0_rel_diff_tsqr": float(abs(a_t[0] - ref[0]) / abs(ref[0])),
+                            "alpha0_rel_diff_gram": float(abs(a_g[0] - ref[0]) / abs(ref[0])),
+                            "spectrum_max_rel_diff_tsqr": float(np.max(np.abs(a_t - ref) / np.abs(ref))) if r_t == r else None}
+    return out
+
+
+def case_c3_alpha(out, Z=100_000, A=64, G=70, steps=200, check_host=True):
     import torch
     from alpha_eigen_b200.device import SlabDevice
     from alpha_eigen_b200.synthetic import synthetic_problem
@@ -123,13 +151,37 @@ def case_c3_alpha(out, Z=100_000, A=64, G=70, steps=200):
     alg, sigg, rg = dev.dmd_from_gram(gram, K, 0.1)
     sync(); t3 = time.perf_counter()
     srt = lambda a: np.asarray(a)[np.lexsort((np.asarray(a).imag, -np.asarray(a).real))]
+    host = {}
+    if check_host:
+        # the reference routine's arithmetic (oracle.dmd_alpha, time_unit.py:61-92) on the
+        # DEVICE-produced snapshots copied to the host (storage order incl. padding zeros: row order does not matter)
+        from oracle import ae_oracle as orc
+        snaps = phi_snap.view(steps, dev.G * dev.Zp).cpu().numpy().T          # (M, steps) view, M = G * Zp
+        t0h = time.perf_counter()
+        ref, sv, rr = orc.dmd_alpha(snaps, steps, 0.1, return_rank_info=True)
+        th = time.perf_counter() - t0h
+        ref = srt(ref)
+        near = lambda a, x: complex(a[np.argmin(np.abs(a - x))])
+        real_top = lambda a: float(max([z.real for z in a if abs(z.imag) < 1e-9] or [float("nan")]))
+        host = {"host_dmd_s": th, "host_rank": int(rr), "host_alpha0": complex(ref[0]).real,
+                "host_alpha_top5": [[float(z.real), float(z.imag)] for z in ref[:5]],
+                "tsqr_alpha_top5": [[float(z.real), float(z.imag)] for z in srt(al)[:5]],
+                "gram_alpha_top5": [[float(z.real), float(z.imag)] for z in srt(alg)[:5]],
+                "largest_real_alpha": {"host": real_top(ref), "tsqr": real_top(srt(al)), "gram": real_top(srt(alg))},
+                "alpha0_rel_diff_tsqr": float(abs(srt(al)[0] - ref[0]) / abs(ref[0])),
+                "alpha0_rel_diff_gram": float(abs(srt(alg)[0] - ref[0]) / abs(ref[0])),
+                "gram_nearest_to_host_alpha0_rel": float(abs(near(srt(alg), ref[0]) - ref[0]) / abs(ref[0])),
+                "sigma_rel_err_tsqr": float(np.max(np.abs(sig[:len(sv)] - sv)) / sv[0]),
+                **well_posed(orc, snaps, steps, dev, R, gram, K, srt),
+                "host_sigma_rel_tail": [float(x) for x in (sv[[10, 17, 20, 25, 31, 40]] / sv[0])] if len(sv) > 40 else None}
+        del snaps
     sweeps = int(np.sum(inner)) + steps
     out({"case": "c3_alpha", "Z": Z, "A": A, "G": G, "steps": steps, "status": int(st), "snapshots": "phi",
          "outer_per_step": float(np.mean(outer)), "inner_per_step": float(np.mean(inner)), "sweep_sets": sweeps,
          "updates": float(sweeps) * Z * A * G, "gpu_march_s": t1 - t0, "updates_per_s": float(sweeps) * Z * A * G / (t1 - t0),
          "gpu_dmd_tsqr_s": t2 - t1, "gpu_dmd_gram_s": t3 - t2, "alpha0_tsqr": complex(srt(al)[0]).real,
          "alpha0_gram": complex(srt(alg)[0]).real, "rank_tsqr": int(r), "rank_gram": int(rg),
-         "sigma_rel": [float(x) for x in (sig[:8] / sig[0])]})
+         "sigma_rel": [float(x) for x in (sig[:8] / sig[0])], **host})
 
 
 def case_c5_sample(out, E=32, Z=2048, A=16, G=12, steps=200, concurrent=12):
@@ -191,7 +243,7 @@ def main():
         f.flush()
 
     if args.only_c3:
-        case_c3_alpha(out, steps=args.c3_steps)
+        case_c3_alpha(out, steps=args.c3_steps, check_host=args.c3_steps >= 50)
         f.close()
         return
     if args.only_c5:

@@ -186,10 +186,20 @@ elif mode == "dmd":
             col = V @ (np.array([1.0, 0.7, 0.5, 0.3, 1e-3]) * lam ** (st + 1))
             tu.psi[:, :, 0, st] = col.reshape(Z, A)
     else:
-        snap = np.load(sys.argv[7])["psi_snap"]           # (Z, A, 1, steps) from the repaired oracle march
+        snap = np.load(sys.argv[7])["psi_snap"]           # (Z, A, 1, steps) from the repaired oracle march (pinned bit
+                                                          # for bit to the reference's own sweeps by kp_march_repaired_*)
         tu.psi[...] = snap
     al = tu.compute_alpha_eigenvalues()
-    np.savez_compressed(out, Z=Z, A=A, steps=steps, dt=dt, psi=tu.psi, alphas=np.asarray(al, dtype=complex))
+    if kind == "march_small":
+        # large march: keep the answers, not the 11 MB of snapshots (the march itself is pinned elsewhere)
+        first = 2 * int(steps / 5)
+        K = int(steps - int(steps / 5) - steps / 50) - 1 - int(steps / 5)
+        sv = np.linalg.svd(np.asarray(tu.psi).reshape(Z * A, steps)[:, first:first + K], compute_uv=False)
+        np.savez_compressed(out, Z=Z, A=A, steps=steps, dt=dt, alphas=np.asarray(al, dtype=complex), sigma=sv,
+                            psi_last=np.asarray(tu.psi)[..., -1], phi_last=np.load(sys.argv[7])["phi_last"],
+                            outer=np.load(sys.argv[7])["outer"], inner=np.load(sys.argv[7])["inner"])
+    else:
+        np.savez_compressed(out, Z=Z, A=A, steps=steps, dt=dt, psi=tu.psi, alphas=np.asarray(al, dtype=complex))
 '''
 
 
@@ -234,6 +244,16 @@ def main():
         np.savez(tmp, psi_snap=res["psi_snap"])
         print("dmd golden (march)", cpm, A, steps, flush=True)
         run(["dmd", os.path.join(HERE, f"dmd_march_{cpm}_{A}_{steps}.npz"), "march", p["Z"], A, steps, tmp])
+    # the well-conditioned real march (the reference routine is reproducible to ~1e-9 on it): answers only
+    for cpm, A, steps in [(50, 16, 200)]:
+        p = kp_problem(9, cpm, A)
+        res = orc.time_march(p["mu"], p["weight"], p["hx"], p["tables"], np.zeros((p["Z"], 1)),
+                             kp_psi0(p), 0.1, steps)
+        assert res["status"] == 0
+        tmp = f"/tmp/ae_march_{cpm}_{A}_{steps}.npz"
+        np.savez(tmp, psi_snap=res["psi_snap"], phi_last=res["phi_last"], outer=res["outer"], inner=res["inner"])
+        print("dmd golden (march, answers only)", cpm, A, steps, flush=True)
+        run(["dmd", os.path.join(HERE, f"dmd_march_answers_{cpm}_{A}_{steps}.npz"), "march_small", p["Z"], A, steps, tmp])
 
 
 if __name__ == "__main__":

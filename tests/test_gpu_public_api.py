@@ -411,3 +411,39 @@ def test_cell_range_host_io_roundtrip():
     back = torch.empty(Z, G, dtype=torch.float64).pin_memory()
     dev.shard_to_host(rows, back)
     np.testing.assert_array_equal(back.numpy(), src.numpy())
+
+
+def test_device_problem_is_rebuilt_when_the_source_moves():
+    """OneGroup keeps the problem resident between calls; the cache key is a digest of every input byte, so a point
+    source moved to another cell (same sum, same sum of squares) must give the other answer, not the cached one."""
+    from alpha_eigen_modules.time_unit import TimeUnit
+    out = []
+    for cell in (30, 61):
+        s, g = _kp(10, 4)
+        tu = TimeUnit(slab=s, group=g, num_steps=2, dt=0.1)
+        g.source = np.zeros((s.num_zones, 1))
+        g.source[30, 0] = 1.0
+        tu.calculate_time_dependent_flux()                  # builds and caches the device problem
+        g.source = np.zeros((s.num_zones, 1))
+        g.source[cell, 0] = 1.0                             # same shape, sum and sum of squares
+        tu2 = TimeUnit(slab=s, group=g, num_steps=2, dt=0.1)
+        tu2.calculate_time_dependent_flux()
+        out.append(tu2.phi[:, 0, -1].copy())
+    assert not np.allclose(out[0], out[1])
+    assert int(np.argmax(out[1] - out[0])) in range(55, 68)     # the extra flux sits where the source went
+
+
+def test_explicit_sigT_must_match_the_device_problem():
+    """calculate_one_step_flux / time_dependent_source_iteration take sigT like the reference (time_unit.py:29,44); the
+    device problem already carries total_xs + inv_speed/dt, so any other array is refused instead of being ignored."""
+    from alpha_eigen_modules.time_unit import TimeUnit
+    s, g = _kp(10, 4)
+    tu = TimeUnit(slab=s, group=g, num_steps=1, dt=0.1)
+    src = np.ones((s.num_zones, s.num_angles, 1))
+    good = g.total_xs + g.inv_speed / 0.1
+    tu.calculate_one_step_flux(src, sigT=good)
+    with pytest.raises(ValueError):
+        tu.calculate_one_step_flux(src, sigT=good * 1.01)
+    g.inv_speed[5, 0] = 0.0
+    with pytest.raises(ValueError):
+        tu.time_dependent_source_iteration(sigT=None, source=src)

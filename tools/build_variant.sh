@@ -13,5 +13,5 @@ for f in ae_core ae_sweep ae_small ae_source ae_solver ae_dmd ae_comm; do
 done
 wait
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$root/alpha_eigen_b200/libae_$name.so" "$out"/*.o \
-    -L/usr/local/cuda/lib64 -lcusolver -ldl -Xlinker -rpath,/usr/local/cuda/lib64
+    -L/usr/local/cuda/lib64 -lcusolver -lcublas -ldl -Xlinker -rpath,/usr/local/cuda/lib64
 echo "built alpha_eigen_b200/libae_$name.so"
