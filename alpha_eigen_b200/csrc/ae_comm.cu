@@ -5,6 +5,7 @@
 // over ALL angles).  NCCL is resolved at run time from the copy torch already loaded (dlopen by
 // soname), so this library has no link-time NCCL dependency and loads on CPU-only hosts.
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 #include "ae_common.cuh"
 
@@ -36,6 +37,8 @@ struct Comm {
     int rank, nranks;
     double *pair_local;     // device [2]: this rank's (num, den) of a sharded norm
     double *pairs;          // device [nranks][2]: everybody's, after the all-gather
+    double *stage;          // device [nranks][block]: equal-sized blocks for the all-gather of unequal group ranges
+    size_t stage_elems;
 };
 
 static int load_nccl()
@@ -120,20 +123,48 @@ void group_range(int G, int nranks, int rank, int *g0, int *gl)
 }
 
 // Group-sharded ranks: rows[g][Zp], rank r owns the rows of its groups; every rank ends up with all rows.  The blocks
-// have unequal sizes (70 groups over 8 ranks: 9,9,9,9,9,9,8,8), so this is one broadcast per owner inside one NCCL
-// group (in place); optionally the (num, den) pairs of a sharded norm travel in the same group.
+// have unequal sizes (70 groups over 8 ranks: 9,9,9,9,9,9,8,8) and are not equally spaced, which ncclAllGather cannot
+// express.  One broadcast per owner inside an NCCL group does it in place but reached only ~210 GB/s per rank on
+// 8 B200 (2.3 ms for the 490 MB of C4); instead the own block is copied into an equal-sized slot of a staging buffer,
+// ONE ncclAllGather fills the other slots, and the foreign blocks are copied to their rows (device-to-device, a few
+// per cent of the collective).  Optionally the (num, den) pairs of a sharded norm travel in the same NCCL group.
 int comm_all_gather_groups(void *comm, double *rows, int G, int64_t Zp, int with_pairs, cudaStream_t st)
 {
     Comm *c = (Comm *)comm;
+    static const char *bc = getenv("AE_COMM_GROUPS_BROADCAST");            // "1": the grouped-broadcast variant (A/B)
+    const bool broadcast = bc && bc[0] == '1';
+    const int glmax = (G + c->nranks - 1) / c->nranks;
+    const size_t block = (size_t)glmax * Zp;
+    int g0 = 0, gl = 0;
+    group_range(G, c->nranks, c->rank, &g0, &gl);
+    if (rows && !broadcast) {
+        if (c->stage_elems < block * c->nranks) {
+            if (c->stage) AE_CUDA(cudaFree(c->stage));
+            c->stage = nullptr; c->stage_elems = 0;
+            AE_CUDA(cudaMalloc((void **)&c->stage, block * c->nranks * sizeof(double)));
+            c->stage_elems = block * c->nranks;
+        }
+        if (gl > 0)
+            AE_CUDA(cudaMemcpyAsync(c->stage + block * c->rank, rows + (int64_t)g0 * Zp, (size_t)gl * Zp * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, st));
+    }
     AE_NCCL(g_nccl.GroupStart());
-    for (int r = 0; r < c->nranks && rows; ++r) {
-        int g0, gl;
-        group_range(G, c->nranks, r, &g0, &gl);
-        double *blk = rows + (int64_t)g0 * Zp;
-        if (gl > 0) AE_NCCL(g_nccl.Broadcast(blk, blk, (size_t)gl * Zp, ncclFloat64, r, c->nccl, st));
+    if (rows && !broadcast) AE_NCCL(g_nccl.AllGather(c->stage + block * c->rank, c->stage, block, ncclFloat64, c->nccl, st));
+    for (int r = 0; r < c->nranks && rows && broadcast; ++r) {
+        int a, n;
+        group_range(G, c->nranks, r, &a, &n);
+        double *blk = rows + (int64_t)a * Zp;
+        if (n > 0) AE_NCCL(g_nccl.Broadcast(blk, blk, (size_t)n * Zp, ncclFloat64, r, c->nccl, st));
     }
     if (with_pairs) AE_NCCL(g_nccl.AllGather(c->pair_local, c->pairs, 2, ncclFloat64, c->nccl, st));
     AE_NCCL(g_nccl.GroupEnd());
+    for (int r = 0; r < c->nranks && rows && !broadcast; ++r) {
+        int a, n;
+        group_range(G, c->nranks, r, &a, &n);
+        if (r != c->rank && n > 0)
+            AE_CUDA(cudaMemcpyAsync(rows + (int64_t)a * Zp, c->stage + block * r, (size_t)n * Zp * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, st));
+    }
     return AE_OK;
 }
 
@@ -173,7 +204,7 @@ extern "C" int ae_comm_init(void **comm, int32_t rank, int32_t nranks, const voi
     ncclComm_t nc = nullptr;
     const int rc = g_nccl.CommInitRank(&nc, nranks, id, rank);
     if (rc) return nccl_fail(rc, "ncclCommInitRank");
-    Comm *c = new Comm{nc, rank, nranks, nullptr, nullptr};
+    Comm *c = new Comm{nc, rank, nranks, nullptr, nullptr, nullptr, 0};
     AE_CUDA(cudaMalloc((void **)&c->pair_local, 2 * sizeof(double)));
     AE_CUDA(cudaMalloc((void **)&c->pairs, 2 * sizeof(double) * nranks));
     *comm = c;
@@ -200,6 +231,7 @@ extern "C" int ae_comm_destroy(void *comm)
     const int rc = g_nccl.CommDestroy(c->nccl);
     cudaFree(c->pair_local);
     cudaFree(c->pairs);
+    cudaFree(c->stage);
     delete c;
     if (rc) return nccl_fail(rc, "ncclCommDestroy");
     return AE_OK;

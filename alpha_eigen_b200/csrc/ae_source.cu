@@ -277,53 +277,94 @@ __global__ void __launch_bounds__(32 * kSWarps, 2) scatter_source_kernel(const F
                 *reinterpret_cast<const double2 *>(p.phi + (int64_t)gp * p.Zp + s0 + 2 * c2);
         }
         __syncthreads();
-        for (int blk = gb; blk < gblocks; blk += blockDim.y) {
-            const int g0 = blk * kGB;
-            const int ng = min(kGB, p.G - g0);
-            if (g0 + ng <= p.g0 || g0 >= p.g0 + p.gl) continue;     // group-sharded: only this rank's output groups
-            double acc[4][kGB];
+        // output group blocks that overlap this rank's groups (all of them unless group-sharded)
+        const int b_lo = p.g0 / kGB, nb = (p.g0 + p.gl - 1) / kGB - b_lo + 1;
+        if (p.gl >= p.G) {
+            // a block of 8 output groups x 128 cells (4 per lane) per warp and step
+            for (int bi = gb; bi < nb; bi += blockDim.y) {
+                const int g0 = (b_lo + bi) * kGB;
+                const int ng = min(kGB, p.G - g0);
+                double acc[4][kGB];
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < 4; ++c)
 #pragma unroll
-                for (int j = 0; j < kGB; ++j) acc[c][j] = 0.0;
-            if (s_uniform) {
+                    for (int j = 0; j < kGB; ++j) acc[c][j] = 0.0;
+                if (s_uniform) {
 #pragma unroll 2
-                for (int gp = 0; gp < p.G; ++gp) {
-                    double x[4];
+                    for (int gp = 0; gp < p.G; ++gp) {
+                        double x[4];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) x[c] = phi[gp * kSC + 32 * c];
-                    const double2 *row = reinterpret_cast<const double2 *>(stab + gp * Gp + g0);
+                        for (int c = 0; c < 4; ++c) x[c] = phi[gp * kSC + 32 * c];
+                        const double2 *row = reinterpret_cast<const double2 *>(stab + gp * Gp + g0);
 #pragma unroll
-                    for (int j2 = 0; j2 < kGB / 2; ++j2) {
-                        const double2 t = row[j2];
+                        for (int j2 = 0; j2 < kGB / 2; ++j2) {
+                            const double2 t = row[j2];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            acc[c][2 * j2] = fma(x[c], t.x, acc[c][2 * j2]);
-                            acc[c][2 * j2 + 1] = fma(x[c], t.y, acc[c][2 * j2 + 1]);
+                            for (int c = 0; c < 4; ++c) {
+                                acc[c][2 * j2] = fma(x[c], t.x, acc[c][2 * j2]);
+                                acc[c][2 * j2 + 1] = fma(x[c], t.y, acc[c][2 * j2 + 1]);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const double *sc = p.scat + (size_t)p.mat[s0 + lane + 32 * c] * p.G * p.G + g0;
+                        for (int gp = 0; gp < p.G; ++gp) {
+                            const double x = phi[gp * kSC + 32 * c];
+#pragma unroll
+                            for (int j = 0; j < kGB; ++j)
+                                if (j < ng) acc[c][j] = fma(x, __ldg(sc + gp * p.G + j), acc[c][j]);
                         }
                     }
                 }
-            } else {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int j = 0; j < kGB; ++j)
+                    if (j < ng && g0 + j >= p.g0 && g0 + j < p.g0 + p.gl) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int64_t i = (int64_t)(g0 + j) * p.Zp + s0 + lane + 32 * c;
+                            p.q_next[i] = p.base[i] + 0.5 * acc[c][j];
+                        }
+                    }
+            }
+        } else {
+            // group-sharded rank: a warp takes (block, 32-cell column) items so that every warp of the CTA has work
+            // (whole blocks would leave most warps idle: 2 blocks for 10 warps at 8 ranks)
+            for (int it = gb; it < nb * 4; it += blockDim.y) {
+                const int g0 = (b_lo + it / 4) * kGB, c = it % 4;
+                const int ng = min(kGB, p.G - g0);
+                double acc[kGB];
+#pragma unroll
+                for (int j = 0; j < kGB; ++j) acc[j] = 0.0;
+                if (s_uniform) {
+#pragma unroll 4
+                    for (int gp = 0; gp < p.G; ++gp) {
+                        const double x = phi[gp * kSC + 32 * c];
+                        const double2 *row = reinterpret_cast<const double2 *>(stab + gp * Gp + g0);
+#pragma unroll
+                        for (int j2 = 0; j2 < kGB / 2; ++j2) {
+                            const double2 t = row[j2];
+                            acc[2 * j2] = fma(x, t.x, acc[2 * j2]);
+                            acc[2 * j2 + 1] = fma(x, t.y, acc[2 * j2 + 1]);
+                        }
+                    }
+                } else {
                     const double *sc = p.scat + (size_t)p.mat[s0 + lane + 32 * c] * p.G * p.G + g0;
                     for (int gp = 0; gp < p.G; ++gp) {
                         const double x = phi[gp * kSC + 32 * c];
 #pragma unroll
                         for (int j = 0; j < kGB; ++j)
-                            if (j < ng) acc[c][j] = fma(x, __ldg(sc + gp * p.G + j), acc[c][j]);
+                            if (j < ng) acc[j] = fma(x, __ldg(sc + gp * p.G + j), acc[j]);
                     }
                 }
-            }
 #pragma unroll
-            for (int j = 0; j < kGB; ++j)
-                if (j < ng && g0 + j >= p.g0 && g0 + j < p.g0 + p.gl) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                for (int j = 0; j < kGB; ++j)
+                    if (j < ng && g0 + j >= p.g0 && g0 + j < p.g0 + p.gl) {
                         const int64_t i = (int64_t)(g0 + j) * p.Zp + s0 + lane + 32 * c;
-                        p.q_next[i] = p.base[i] + 0.5 * acc[c][j];
+                        p.q_next[i] = p.base[i] + 0.5 * acc[j];
                     }
-                }
+            }
         }
     }
 }
