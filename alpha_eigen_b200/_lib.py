@@ -29,7 +29,7 @@ class AeSlab(C.Structure):
     _fields_ = [("Z", C.c_int64), ("Zp", C.c_int64), ("A", C.c_int32), ("n_neg", C.c_int32), ("G", C.c_int32),
                 ("M", C.c_int32), ("mu_ihx", C.c_void_p), ("wgt", C.c_void_p), ("mat", C.c_void_p),
                 ("scat", C.c_void_p), ("chi", C.c_void_p), ("nusf", C.c_void_p), ("hs", C.c_void_p),
-                ("cdt", C.c_void_p), ("s_ext", C.c_void_p), ("tile_info", C.c_void_p), ("g0", C.c_int32), ("gl", C.c_int32)]
+                ("cdt", C.c_void_p), ("s_ext", C.c_void_p), ("tile_info", C.c_void_p), ("inflow", C.c_void_p), ("g0", C.c_int32), ("gl", C.c_int32)]
 
 
 class AeWork(C.Structure):

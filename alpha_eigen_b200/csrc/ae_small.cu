@@ -42,7 +42,7 @@ namespace cg = cooperative_groups;
 namespace ae {
 
 struct SmallArgs {
-    const double *hs, *cdt, *mu_ihx, *wgt, *scat, *chi, *nusf, *s_ext;
+    const double *hs, *cdt, *mu_ihx, *wgt, *scat, *chi, *nusf, *s_ext, *inflow;
     const int32_t *mat;
     double *base, *q0, *q1, *phi0, *phi1, *phi_outer, *partial, *scratch;
     ae_ctrl *ctrl;
@@ -117,7 +117,7 @@ struct Small {
     // this CTA's row block
     int g, blk, nblk;
     bool neg;
-    double m, two_m, hw;
+    double m, two_m, hw, bc;                            // bc: flux entering this warp's row (0 = vacuum)
     int64_t goff, prow;
     double *part;
 
@@ -136,6 +136,7 @@ struct Small {
         const int a = a0 + (warp < nblk ? warp : 0);
         m = fabs(p.mu_ihx[a]); two_m = 2.0 * m;
         hw = warp < nblk ? 0.5 * p.wgt[a] : 0.0;
+        bc = (p.inflow && warp < nblk) ? p.inflow[(int64_t)g * p.A + a] : 0.0;     // one_direction.py:12
         goff = (int64_t)g * p.Zp + lane * 2;
         prow = ((int64_t)g * p.A + a) * p.Zp + lane * 2;
         part = p.partial + ((int64_t)blk * p.G + g) * p.Zp;
@@ -152,7 +153,7 @@ struct Small {
     __device__ void sweep(const double *q, const double *psi_in, double *psi_out)
     {
         const double *qc = q + goff;
-        double carry = 0.0;                             // vacuum boundary: group.py:48,54
+        double carry = bc;                              // vacuum boundary (group.py:48,54) unless a boundary_condition is set
         for (int64_t ti = 0; ti < nt; ++ti) {
             const int64_t off = (neg ? nt - 1 - ti : ti) * kTile;
             double ca[kL], cb[kL], f[kL];
@@ -456,7 +457,7 @@ static bool small_problem(const ae_slab *s, ae_work *w, SmallArgs &p, int &ac, i
     if (updates > (1 << 23) || s->Zp / kTile > 256) return false;       // big enough for the streaming kernels
     ac = block_angles(s->A, s->n_neg);
     p.hs = s->hs; p.cdt = s->cdt; p.mu_ihx = s->mu_ihx; p.wgt = s->wgt; p.scat = s->scat; p.chi = s->chi; p.nusf = s->nusf;
-    p.s_ext = s->s_ext; p.mat = s->mat; p.base = w->base; p.q0 = w->q0; p.q1 = w->q1; p.phi0 = w->phi; p.phi1 = w->phi_alt;
+    p.s_ext = s->s_ext; p.inflow = s->inflow; p.mat = s->mat; p.base = w->base; p.q0 = w->q0; p.q1 = w->q1; p.phi0 = w->phi; p.phi1 = w->phi_alt;
     p.phi_outer = w->phi_outer; p.partial = w->partial; p.scratch = w->norm_scratch; p.ctrl = w->ctrl;
     p.Z = s->Z; p.Zp = s->Zp; p.A = s->A; p.n_neg = s->n_neg; p.G = s->G;
     p.nb_neg = (s->n_neg + ac - 1) / ac;

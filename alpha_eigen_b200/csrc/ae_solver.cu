@@ -64,7 +64,11 @@ static int compute_fixed(const ae_slab *s, ae_work *w, const double *psi_in, cud
 {
     if (!w->phi_fixed) { set_error("time-dependent solve: ae_work.phi_fixed is missing"); return AE_BAD_ARG; }
     AE_CUDA(cudaMemsetAsync(w->q1, 0, (size_t)s->G * s->Zp * sizeof(double), st));        // q1 is free until the first update
-    AE_TRY(launch_sweep(s, w->q1, psi_in, nullptr, w->partial, w->sweep_sync, w->ctrl, 0, nullptr, st));
+    // with incident boundary fluxes the sweep is affine, not linear: they belong to the sweeps of q (every inner
+    // iteration carries them), so this one runs with vacuum boundaries
+    ae_slab vac = *s;
+    vac.inflow = nullptr;
+    AE_TRY(launch_sweep(&vac, w->q1, psi_in, nullptr, w->partial, w->sweep_sync, w->ctrl, 0, nullptr, st));
     AE_TRY(ae_reduce_partials(s, w->partial, w->P, w->phi_fixed, st));
     if (w->comm && s->gl <= 0) AE_TRY(comm_reduce_scatter_rows(w->comm, w->phi_fixed, s->G, s->Zp, st)); // valid on this rank's cell range
     return AE_OK;

@@ -46,6 +46,7 @@ constexpr int kTileBytes = kTile * 8;   // 2 KB
 struct SweepArgs {
     const double *hs, *cdt, *q, *mu_ihx, *wgt, *psi_in;
     const double *tinfo;                // [G][Zp/kTile][2] uniform-tile records (ae_tile_info) or NULL: general path only
+    const double *inflow;               // [G][A] incident boundary flux per row or NULL (vacuum)
     double *psi_out, *partial;
     SweepSync *sync;
     int64_t Z, Zp;
@@ -325,7 +326,8 @@ __global__ void __launch_bounds__(StageCfg<AC>::threads, AC == kACsmall ? 2 : 1)
             segs.get(k, rb, ti0, n);
             row_setup<AC>(p, unit_row(p, rb, mb), warp, c);
             double u_h = nan_v;                                             // the hs value uc was built for (NaN: none)
-            double carry = 0.0;                                             // vacuum boundary: group.py:48,54
+            // flux entering the row: vacuum (group.py:48,54) or the angle's boundary_condition (one_direction.py:12)
+            double carry = (p.inflow && ti0 == 0 && warp < c.nblk) ? p.inflow[c.row / p.Zp + warp] : 0.0;
             if (ti0 != 0) {                                                 // continue a row another CTA started
                 if (lane == 0 && warp < c.nblk) {
                     while (ld_acquire(&sy->flag[cta - p.gs][warp]) != stamp) {}    // same member of the previous gang
@@ -591,7 +593,8 @@ __global__ void __launch_bounds__(kPhiThreads, 1) phi_sweep_kernel(const SweepAr
             for (int r = 0; r < R; ++r) {
                 const int slot = warp + kPhiCW * r;
                 if (lane == 0) s_hw[slot] = slot < nblk ? 0.5 * p.wgt[a0 + slot] : 0.0;     // half weights (0: absent row)
-                cin[r] = 0.0;                                               // vacuum boundary: group.py:48,54
+                // vacuum boundary (group.py:48,54) or the angle's boundary_condition (one_direction.py:12)
+                cin[r] = (p.inflow && ti0 == 0 && slot < nblk) ? p.inflow[(int64_t)c.g * p.A + a0 + slot] : 0.0;
             }
             __syncwarp();
             if (ti0 != 0) {                                                 // continue rows another CTA started
@@ -876,6 +879,7 @@ int launch_sweep(const ae_slab *s, const double *q, const double *psi_in, double
     const int ac = shape_args(s->A, s->n_neg, G, s->Zp, p);
     p.hs = s->hs + goff; p.cdt = s->cdt ? s->cdt + goff : nullptr; p.q = q + goff; p.mu_ihx = s->mu_ihx; p.wgt = s->wgt;
     p.psi_in = psi_in; p.psi_out = psi_out; p.partial = partial; p.sync = (SweepSync *)sync;
+    p.inflow = s->inflow ? s->inflow + (s->gl > 0 ? (int64_t)s->g0 * s->A : 0) : nullptr;
     p.Z = s->Z;
     static const char *hints = getenv("AE_SWEEP_L2_HINTS");
     p.l2_hints = !(hints && hints[0] == '0');

@@ -178,10 +178,12 @@ class SlabDevice:
     total/chi/nusf/invspeed (M,G), scat (M,G,G) with scat[m][g'][g] = sigma_s(g'->g)
     dt ........... None for steady state; otherwise sigT = total + inv_speed/dt (time_unit.py:24)
     s_ext ........ (Z,G) fixed external source or None
+    inflow ....... (A_total, G) or (A_total,) flux entering the slab at each angle's upstream boundary
+                   (OneDirection.boundary_condition, one_direction.py:12); None = vacuum
     """
 
     def __init__(self, Z, hx, mu, weight, mat, total, scat, chi, nusf, invspeed, dt=None, s_ext=None,
-                 angles=None, comm: Comm | None = None, device=None, batch=None, flags=0, group_range_=None):
+                 angles=None, comm: Comm | None = None, device=None, batch=None, flags=0, group_range_=None, inflow=None):
         torch = _torch()
         self.torch = torch
         self.lib = _lib.load()
@@ -229,6 +231,11 @@ class SlabDevice:
         self.t_hs = self.cells_to_device(0.5 * sigT)                  # [G][Zp]
         self.t_cdt = self.cells_to_device(inv_cell / dt) if dt is not None else None
         self.t_sext = self.cells_to_device(s_ext) if s_ext is not None else None
+        self.t_inflow = None
+        if inflow is not None and np.any(np.asarray(inflow) != 0):
+            bc = np.asarray(inflow, dtype=np.float64).reshape(self.A_total, -1)
+            bc = np.broadcast_to(bc, (self.A_total, self.G))
+            self.t_inflow = up(np.ascontiguousarray(bc[self.angles].T))          # [G][A] local angles
         del sigT, inv_cell
         self.P = int(self.lib.ae_partial_count(self.A, self.n_neg))
         n = self.G * self.Zp
@@ -251,7 +258,8 @@ class SlabDevice:
                                 self.t_w.data_ptr(), self.t_mat.data_ptr(), self.t_scat.data_ptr(),
                                 self.t_chi.data_ptr(), self.t_nusf.data_ptr(), self.t_hs.data_ptr(),
                                 self.t_cdt.data_ptr() if self.t_cdt is not None else None,
-                                self.t_sext.data_ptr() if self.t_sext is not None else None, None, self.g0, self.gl)
+                                self.t_sext.data_ptr() if self.t_sext is not None else None, None,
+                                self.t_inflow.data_ptr() if self.t_inflow is not None else None, self.g0, self.gl)
         self._build_tile_info()
         self.work = _lib.AeWork(self._phi_bufs[0].data_ptr(), self._phi_bufs[1].data_ptr(), self.phi_outer.data_ptr(),
                                 self.base.data_ptr(), self.q0.data_ptr(), self.q1.data_ptr(), self.partial.data_ptr(),

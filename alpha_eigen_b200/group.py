@@ -135,7 +135,9 @@ class OneGroup:
         # and the quadrature (sums would not notice a point source that moved or a permuted material map)
         import hashlib
         h = hashlib.blake2b(digest_size=16)
-        for a in (*tabs, sx, self.slab.mu, self.slab.weight):
+        bc = np.array([np.broadcast_to(np.asarray(a.boundary_condition, dtype=np.float64), (self.slab.num_groups,))
+                       for a in self.angle])                         # one_direction.py:12, per angle (and group)
+        for a in (*tabs, sx, self.slab.mu, self.slab.weight, bc):
             if a is None:
                 h.update(b"-")
             else:
@@ -148,7 +150,8 @@ class OneGroup:
             return hit[1]
         comm = distributed.communicator()
         mu = np.asarray(self.slab.mu, dtype=np.float64)
-        dev = SlabDevice.sharded(self.slab.num_zones, self.slab.hx, mu, self.slab.weight, *tabs, comm=comm, dt=dt, s_ext=sx)
+        dev = SlabDevice.sharded(self.slab.num_zones, self.slab.hx, mu, self.slab.weight, *tabs, comm=comm, dt=dt, s_ext=sx,
+                                 inflow=bc if np.any(bc != 0) else None)
         self._dev[dt] = (key, dev)
         return dev
 

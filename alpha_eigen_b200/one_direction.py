@@ -3,6 +3,11 @@
 The reference also builds a dense (Z+1)^2 "coefficient matrix" per angle (one_direction.py:34-39)
 that is never used and costs 80 GB per angle at 1e5 cells; it is not reproduced.  psi_midpoint is
 fetched from the device on first access after a solve instead of being written by every sweep.
+
+`boundary_condition` (one_direction.py:12) is the flux entering the slab at this angle's upstream boundary: the reference
+puts it into the first / last entry of the right-hand side it builds in set_positive / set_negative_boundary_condition
+(one_direction.py:24-31) and never sets it to anything but 0 (vacuum, which its live sweep hard-codes, group.py:48,54).
+Here a non-zero value (scalar, or one per group) is honoured by every sweep: it is the initial value of the recurrence.
 """
 import numpy as np
 

@@ -68,6 +68,9 @@ typedef struct ae_slab {
     const double *tile_info; /* [G][Zp/AE_TILE][2] records written by ae_tile_info for THESE hs / cdt arrays, or NULL.
                                 Lets the sweep skip the per-cell reciprocals in tiles whose cells share one sigT
                                 (material regions, slab.py:33-56); results are bit-identical with and without it */
+    const double *inflow;    /* [G][A] flux entering the slab at each row's upstream boundary (x = 0 for mu > 0, x = L for mu < 0):
+                                OneDirection.boundary_condition (one_direction.py:12,24-31).  NULL = vacuum, which is what the
+                                reference always runs with (group.py:48,54) */
     int32_t g0, gl;          /* group-sharded ranks (several GPUs, G >= 2 ranks): this rank sweeps groups [g0, g0+gl) with ALL
                                 angles and psi / partial hold only those groups ([gl][A][Zp], [P][gl][Zp]); every other array
                                 keeps all G rows.  A group's flux is then complete on its owner: no reduction, one all-gather

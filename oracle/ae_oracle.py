@@ -97,6 +97,18 @@ def sweep(mu, hx, source, sigT):
     return psi
 
 
+_inflow_keep = None
+
+
+def set_inflow(inflow):
+    """Incident boundary fluxes (A, G) used by every sweep set from now on (OneDirection.boundary_condition,
+    one_direction.py:12,24-31), or None for vacuum (what the reference always runs with)."""
+    global _inflow_keep
+    _inflow_keep = None if inflow is None else _f64(inflow)
+    lib().aeo_set_inflow.restype = None
+    lib().aeo_set_inflow(_d(_inflow_keep))
+
+
 def sweep_set(mu, w, hx, q, sigT, want_psi=False):
     """All angles x groups with isotropic source q (Z,G); returns phi (Z,G) [, psi (Z,A,G)]."""
     q, sigT, mu, w = _f64(q), _f64(sigT), _f64(mu), _f64(w)

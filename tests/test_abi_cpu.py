@@ -25,7 +25,7 @@ def test_header_symbols_exported():
 def test_struct_sizes_match_header():
     import ctypes as C
     assert C.sizeof(_lib.AeCtrl) == 64
-    assert C.sizeof(_lib.AeSlab) == 16 + 16 + 10 * 8 + 8
+    assert C.sizeof(_lib.AeSlab) == 16 + 16 + 11 * 8 + 8
     assert C.sizeof(_lib.AeWork) == 14 * 8 + 16
 
 

@@ -65,7 +65,21 @@ def test_dmd_fixtures(golden_dir):
     assert len(files) >= 3
     for f in files:
         g = np.load(f)
-        al = orc.dmd_alpha_from_psi(g["psi"], int(g["steps"]), float(g["dt"]))
+        if "psi" in g.files:
+            psi = g["psi"]
+        else:
+            # answers-only fixture of a long march: its snapshots are the oracle's own (repaired) march, regenerated here
+            # (K-P 50 cells/mfp S16: Z = 450); iteration counts and the last flux are part of the fixture
+            cpm = int(g["Z"]) // 9
+            p = kp_problem(9, cpm, int(g["A"]))
+            res = orc.time_march(p["mu"], p["weight"], p["hx"], p["tables"], np.zeros((p["Z"], 1)), kp_psi0(p),
+                                 float(g["dt"]), int(g["steps"]))
+            assert res["status"] == 0
+            np.testing.assert_array_equal(res["outer"], g["outer"])
+            np.testing.assert_array_equal(res["inner"], g["inner"])
+            np.testing.assert_array_equal(res["phi_last"], g["phi_last"])
+            psi = res["psi_snap"]
+        al = orc.dmd_alpha_from_psi(psi, int(g["steps"]), float(g["dt"]))
         ref = g["alphas"]
         assert len(al) == len(ref)                                      # same rank decision (time_unit.py:75-76)
         # same LAPACK, same memory layout as time_unit.py:68-72 -> identical to rounding
@@ -139,3 +153,28 @@ def test_not_converged_status():
     st, phi, it = orc.source_iteration(p["mu"], p["weight"], p["hx"], p["tables"], np.ones((p["Z"], 1)),
                                        max_iterations=5)
     assert st == 1 and it == 4          # `assert iteration < max_iterations` (group.py:72): 4 iterations run
+
+
+def test_incident_boundary_flux_analytic():
+    """OneDirection.boundary_condition (one_direction.py:12,24-31): with no source, the flux entering a uniform
+    absorber is multiplied by a = (m - s/2)/(m + s/2) per cell of the diamond-difference recurrence (group.py:50), so
+    the cell-centre fluxes are psi0 a^i (1 + a)/2 -- in both directions."""
+    from oracle import ae_oracle as orc
+    Z, hx, sig, psi0 = 40, 0.1, 1.3, 2.5
+    lib = orc.lib()
+    for mu in (0.7, -0.3):
+        m = abs(mu) / hx
+        a = (m - 0.5 * sig) / (m + 0.5 * sig)
+        psi = np.empty(Z)
+        src, s = np.zeros(Z), np.full(Z, sig)
+        import ctypes
+        lib.aeo_sweep_in.restype = None
+        lib.aeo_sweep_in(ctypes.c_int64(Z), ctypes.c_double(mu), ctypes.c_double(1 / hx), orc._d(src), ctypes.c_int64(1), orc._d(s),
+                         ctypes.c_int64(1), orc._d(psi), ctypes.c_int64(1), ctypes.c_double(psi0))
+        want = psi0 * a ** np.arange(Z) * (1 + a) / 2
+        if mu < 0:
+            want = want[::-1]
+        np.testing.assert_allclose(psi, want, rtol=1e-13)
+    # vacuum is the zero-inflow case of the same routine
+    psi_v = orc.sweep(0.7, hx, np.ones(Z), np.full(Z, sig))
+    assert psi_v[0] == 0.5 * (0 + 1 / (0.7 / hx + 0.5 * sig))
