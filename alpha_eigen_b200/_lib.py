@@ -63,6 +63,7 @@ SYMBOLS = {
                                   C.c_int64]),
     "ae_reduce_partials": (C.c_int, [C.POINTER(AeSlab), _P, C.c_int32, _P, _P]),
     "ae_flux_update": (C.c_int, [C.POINTER(AeSlab), C.POINTER(AeWork), _P, C.c_int32, _P, C.c_double, C.c_int32, _P]),
+    "ae_sweep_and_update": (C.c_int, [C.POINTER(AeSlab), C.POINTER(AeWork), _P, _P, _P, _P, C.c_double, C.c_int32, _P]),
     "ae_exchange_partials": (C.c_int, [C.POINTER(AeSlab), C.POINTER(AeWork), _P]),
     "ae_pack_cells": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, _P]),
     "ae_unpack_cells": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, _P]),

@@ -39,7 +39,10 @@ struct Comm {
     double *pairs;          // device [nranks][2]: everybody's, after the all-gather
     double *stage;          // device [nranks][block]: equal-sized blocks for the all-gather of unequal group ranges
     size_t stage_elems;
+    cudaStream_t aux;       // second stream: flux assembly + all-gather of a group chunk while the next chunk is swept
+    cudaEvent_t ev[4];      // main -> aux (chunk swept), aux -> main (exchange done)
 };
+constexpr int kPairSlots = 4;                  // (num, den) pairs per rank: one per group chunk
 
 static int load_nccl()
 {
@@ -83,6 +86,8 @@ int comm_rank(const void *comm) { return comm ? ((const Comm *)comm)->rank : 0; 
 int comm_size(const void *comm) { return comm ? ((const Comm *)comm)->nranks : 1; }
 double *comm_pair_local(void *comm) { return ((Comm *)comm)->pair_local; }
 double *comm_pairs(void *comm) { return ((Comm *)comm)->pairs; }
+cudaStream_t comm_aux_stream(void *comm) { return ((Comm *)comm)->aux; }
+cudaEvent_t comm_event(void *comm, int i) { return ((Comm *)comm)->ev[i]; }
 
 // rows[g][Zp]: sum over ranks of every row, rank r keeping cells [r*Zs, (r+1)*Zs) of each row (in place).
 int comm_reduce_scatter_rows(void *comm, double *rows, int G, int64_t Zp, cudaStream_t st)
@@ -109,7 +114,7 @@ int comm_all_gather_rows(void *comm, double *rows, int G, int64_t Zp, int with_p
         double *row = rows + (int64_t)g * Zp;
         AE_NCCL(g_nccl.AllGather(row + c->rank * Zs, row, (size_t)Zs, ncclFloat64, c->nccl, st));
     }
-    if (with_pairs) AE_NCCL(g_nccl.AllGather(c->pair_local, c->pairs, 2, ncclFloat64, c->nccl, st));
+    if (with_pairs) AE_NCCL(g_nccl.AllGather(c->pair_local, c->pairs, 2 * kPairSlots, ncclFloat64, c->nccl, st));
     AE_NCCL(g_nccl.GroupEnd());
     return AE_OK;
 }
@@ -128,6 +133,55 @@ void group_range(int G, int nranks, int rank, int *g0, int *gl)
 // 8 B200 (2.3 ms for the 490 MB of C4); instead the own block is copied into an equal-sized slot of a staging buffer,
 // ONE ncclAllGather fills the other slots, and the foreign blocks are copied to their rows (device-to-device, a few
 // per cent of the collective).  Optionally the (num, den) pairs of a sharded norm travel in the same NCCL group.
+// A rank's groups are exchanged in up to two chunks so that the first can travel while the second is swept: the last
+// `tail` groups form chunk 1, the rest chunk 0 (ranks with fewer than 3 groups have one chunk: count = 1 for everybody).
+int group_chunks(int G, int nranks) { return G / nranks >= 3 ? 2 : 1; }
+void group_chunk_range(int gl, int count, int chunk, int *off, int *len)
+{
+    const int tail = count == 2 ? 2 : 0;
+    if (chunk == 0) { *off = 0; *len = gl - tail; }
+    else { *off = gl - tail; *len = tail; }
+}
+
+// All-gather of chunk `chunk` (of `count`) of every rank's groups; chunk < 0: whole blocks.
+int comm_all_gather_group_chunk(void *comm, double *rows, int G, int64_t Zp, int count, int chunk, int with_pairs, cudaStream_t st)
+{
+    Comm *c = (Comm *)comm;
+    const int glmax = (G + c->nranks - 1) / c->nranks;
+    int lmax = glmax;
+    if (chunk >= 0) { int o; group_chunk_range(glmax, count, chunk, &o, &lmax); }
+    const size_t block = (size_t)lmax * Zp;
+    if (c->stage_elems < (size_t)glmax * Zp * c->nranks) {
+        if (c->stage) AE_CUDA(cudaFree(c->stage));
+        c->stage = nullptr; c->stage_elems = 0;
+        AE_CUDA(cudaMalloc((void **)&c->stage, (size_t)glmax * Zp * c->nranks * sizeof(double)));
+        c->stage_elems = (size_t)glmax * Zp * c->nranks;
+    }
+    auto range_of = [&](int r, int *a, int *n) {
+        int g0, gl;
+        group_range(G, c->nranks, r, &g0, &gl);
+        int off = 0, len = gl;
+        if (chunk >= 0) group_chunk_range(gl, count, chunk, &off, &len);
+        *a = g0 + off; *n = len;
+    };
+    int a, n;
+    range_of(c->rank, &a, &n);
+    if (n > 0)
+        AE_CUDA(cudaMemcpyAsync(c->stage + block * c->rank, rows + (int64_t)a * Zp, (size_t)n * Zp * sizeof(double),
+                                cudaMemcpyDeviceToDevice, st));
+    AE_NCCL(g_nccl.GroupStart());
+    AE_NCCL(g_nccl.AllGather(c->stage + block * c->rank, c->stage, block, ncclFloat64, c->nccl, st));
+    if (with_pairs) AE_NCCL(g_nccl.AllGather(c->pair_local, c->pairs, 2 * kPairSlots, ncclFloat64, c->nccl, st));
+    AE_NCCL(g_nccl.GroupEnd());
+    for (int r = 0; r < c->nranks; ++r) {
+        range_of(r, &a, &n);
+        if (r != c->rank && n > 0)
+            AE_CUDA(cudaMemcpyAsync(rows + (int64_t)a * Zp, c->stage + block * r, (size_t)n * Zp * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, st));
+    }
+    return AE_OK;
+}
+
 int comm_all_gather_groups(void *comm, double *rows, int G, int64_t Zp, int with_pairs, cudaStream_t st)
 {
     Comm *c = (Comm *)comm;
@@ -156,7 +210,7 @@ int comm_all_gather_groups(void *comm, double *rows, int G, int64_t Zp, int with
         double *blk = rows + (int64_t)a * Zp;
         if (n > 0) AE_NCCL(g_nccl.Broadcast(blk, blk, (size_t)n * Zp, ncclFloat64, r, c->nccl, st));
     }
-    if (with_pairs) AE_NCCL(g_nccl.AllGather(c->pair_local, c->pairs, 2, ncclFloat64, c->nccl, st));
+    if (with_pairs) AE_NCCL(g_nccl.AllGather(c->pair_local, c->pairs, 2 * kPairSlots, ncclFloat64, c->nccl, st));
     AE_NCCL(g_nccl.GroupEnd());
     for (int r = 0; r < c->nranks && rows && !broadcast; ++r) {
         int a, n;
@@ -204,9 +258,13 @@ extern "C" int ae_comm_init(void **comm, int32_t rank, int32_t nranks, const voi
     ncclComm_t nc = nullptr;
     const int rc = g_nccl.CommInitRank(&nc, nranks, id, rank);
     if (rc) return nccl_fail(rc, "ncclCommInitRank");
-    Comm *c = new Comm{nc, rank, nranks, nullptr, nullptr, nullptr, 0};
-    AE_CUDA(cudaMalloc((void **)&c->pair_local, 2 * sizeof(double)));
-    AE_CUDA(cudaMalloc((void **)&c->pairs, 2 * sizeof(double) * nranks));
+    Comm *c = new Comm{nc, rank, nranks, nullptr, nullptr, nullptr, 0, nullptr, {nullptr, nullptr, nullptr, nullptr}};
+    AE_CUDA(cudaMalloc((void **)&c->pair_local, 2 * kPairSlots * sizeof(double)));
+    AE_CUDA(cudaMalloc((void **)&c->pairs, 2 * kPairSlots * sizeof(double) * nranks));
+    AE_CUDA(cudaMemset(c->pair_local, 0, 2 * kPairSlots * sizeof(double)));
+    AE_CUDA(cudaMemset(c->pairs, 0, 2 * kPairSlots * sizeof(double) * nranks));
+    AE_CUDA(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) AE_CUDA(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
     *comm = c;
     return AE_OK;
 }
@@ -232,6 +290,8 @@ extern "C" int ae_comm_destroy(void *comm)
     cudaFree(c->pair_local);
     cudaFree(c->pairs);
     cudaFree(c->stage);
+    if (c->aux) cudaStreamDestroy(c->aux);
+    for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
     if (rc) return nccl_fail(rc, "ncclCommDestroy");
     return AE_OK;

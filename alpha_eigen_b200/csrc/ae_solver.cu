@@ -29,6 +29,17 @@ static int exchange_partials(const ae_slab *s, ae_work *w, int P, cudaStream_t s
     return comm_reduce_scatter_rows(w->comm, w->reduced, s->G, s->Zp, st);
 }
 int launch_k_update(const ae_slab *s, ae_work *w, double tol, int iteration, cudaStream_t st);
+int launch_assemble_rows(const ae_slab *s, ae_work *w, const double *partial, int P, const double *fixed, const double *phi_in,
+                         double *phi_out, int g0, int gl, int slot, cudaStream_t st);
+int launch_norm_and_scatter(const ae_slab *s, ae_work *w, const double *phi, double *q_next, int nslots, double tol, int iteration,
+                            cudaStream_t st);
+int comm_all_gather_group_chunk(void *comm, double *rows, int G, int64_t Zp, int count, int chunk, int with_pairs, cudaStream_t st);
+int group_chunks(int G, int nranks);
+void group_chunk_range(int gl, int count, int chunk, int *off, int *len);
+int comm_size(const void *comm);
+cudaStream_t comm_aux_stream(void *comm);
+cudaEvent_t comm_event(void *comm, int i);
+void sweep_reserve_sms(int n);
 int launch_outer_check(const ae_slab *s, ae_work *w, cudaStream_t st);
 int launch_ctrl_init(ae_work *w, cudaStream_t st);
 
@@ -155,6 +166,62 @@ extern "C" int ae_flux_update(const ae_slab *s, ae_work *w, const double *partia
     if (!partial || !q_next || P < 1) { set_error("ae_flux_update: bad argument"); return AE_BAD_ARG; }
     AE_TRY(launch_finalize(s, w, partial, P, nullptr, w->phi, w->phi_alt, q_next, 0, 0.0, tol, iteration, 0, (cudaStream_t)stream));
     double *t = w->phi; w->phi = w->phi_alt; w->phi_alt = t;      // w->phi is always the newest iterate
+    return AE_OK;
+}
+
+// One sweep set + flux update as ONE call (what a time-dependent source iteration consists of).  Group-sharded ranks
+// run it in two chunks of their groups: while the second chunk is swept (on a few SMs less), the first chunk's flux is
+// assembled and all-gathered on a second stream, so only the second, small chunk's exchange is exposed.
+extern "C" int ae_sweep_and_update(const ae_slab *s, ae_work *w, const double *q, const double *psi_in, double *psi_out,
+                                   double *q_next, double tol, int32_t iteration, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    AE_TRY(check_work(s, w, "ae_sweep_and_update"));
+    if (!q || !q_next) { set_error("ae_sweep_and_update: bad argument"); return AE_BAD_ARG; }
+    // Overlap pays when the exchange of the head chunk fits behind the sweep of the two-group tail chunk: from 4 ranks on
+    // (measured at 2 ranks: the head's 4 GB of partial sums and the tail's sweep fight for HBM, 29.8 against 28.5 ms per step).
+    // AE_EXCHANGE_OVERLAP = 0 / 1 forces it off / on.
+    static const char *force = getenv("AE_EXCHANGE_OVERLAP");
+    const bool overlap = force ? force[0] == '1' : (w->comm && comm_size(w->comm) >= 4);
+    const int chunks = (w->comm && s->gl > 0 && overlap) ? group_chunks(s->G, comm_size(w->comm)) : 1;
+    if (chunks < 2) {
+        AE_TRY(launch_sweep(s, q, psi_in, psi_out, w->partial, w->sweep_sync, w->ctrl, 0, nullptr, st));
+        if (w->comm && s->gl <= 0) {
+            AE_TRY(exchange_partials(s, w, w->P, st));
+            AE_TRY(launch_finalize(s, w, w->reduced, 1, nullptr, w->phi, w->phi_alt, q_next, 0, 0.0, tol, iteration, 0, st));
+        } else {
+            AE_TRY(launch_finalize(s, w, w->partial, w->P, nullptr, w->phi, w->phi_alt, q_next, 0, 0.0, tol, iteration, 0, st));
+        }
+    } else {
+        static const char *res = getenv("AE_EXCHANGE_RESERVE_SMS");
+        const int reserve = res ? atoi(res) : 16;
+        cudaStream_t aux = comm_aux_stream(w->comm);
+        const size_t row = (size_t)s->A * s->Zp;                                // psi elements per group
+        size_t part_off = 0;
+        AE_CUDA(cudaEventRecord(comm_event(w->comm, 3), st));                   // aux starts after everything queued so far
+        AE_CUDA(cudaStreamWaitEvent(aux, comm_event(w->comm, 3), 0));
+        for (int c = 0; c < chunks; ++c) {
+            int off, len;
+            group_chunk_range(s->gl, chunks, c, &off, &len);
+            ae_slab view = *s;
+            view.g0 = s->g0 + off; view.gl = len;
+            double *part = w->partial + part_off;                               // this chunk's own [P][len][Zp] region
+            sweep_reserve_sms(c > 0 ? reserve : 0);                             // the first chunk has the device to itself
+            const int rc = launch_sweep(&view, q, psi_in ? psi_in + off * row : nullptr, psi_out ? psi_out + off * row : nullptr,
+                                        part, w->sweep_sync, w->ctrl, 0, nullptr, st);
+            sweep_reserve_sms(0);
+            AE_TRY(rc);
+            AE_CUDA(cudaEventRecord(comm_event(w->comm, c), st));
+            AE_CUDA(cudaStreamWaitEvent(aux, comm_event(w->comm, c), 0));
+            AE_TRY(launch_assemble_rows(s, w, part, w->P, nullptr, w->phi, w->phi_alt, view.g0, len, c, aux));
+            AE_TRY(comm_all_gather_group_chunk(w->comm, w->phi_alt, s->G, s->Zp, chunks, c, c == chunks - 1, aux));
+            part_off += (size_t)w->P * len * s->Zp;
+        }
+        AE_CUDA(cudaEventRecord(comm_event(w->comm, 2), aux));
+        AE_CUDA(cudaStreamWaitEvent(st, comm_event(w->comm, 2), 0));
+        AE_TRY(launch_norm_and_scatter(s, w, w->phi_alt, q_next, chunks, tol, iteration, st));
+    }
+    double *t = w->phi; w->phi = w->phi_alt; w->phi_alt = t;                   // w->phi is always the newest iterate
     return AE_OK;
 }
 

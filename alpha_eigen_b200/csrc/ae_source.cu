@@ -90,12 +90,14 @@ __device__ __forceinline__ void grid_sum2(double num, double den, const NormOut 
 }
 
 // Sharded norms: combine the ranks' pairs in rank order (identical on every rank).
-__global__ void norm_finalize_kernel(const double *pairs, int nranks, int mode, ae_ctrl *ctrl, double tol, int iteration,
-                                     int gate)
+constexpr int kPairSlots = 4;       // (num, den) pairs per rank: one per group chunk (ae_comm.cu)
+__global__ void norm_finalize_kernel(const double *pairs, int nranks, int nslots, int mode, ae_ctrl *ctrl, double tol,
+                                     int iteration, int gate)
 {
     if (gate && ctrl->inner_done) return;
     double a = 0.0, b = 0.0;
-    for (int r = 0; r < nranks; ++r) { a += pairs[2 * r]; b += pairs[2 * r + 1]; }
+    for (int r = 0; r < nranks; ++r)
+        for (int c = 0; c < nslots; ++c) { a += pairs[2 * (r * kPairSlots + c)]; b += pairs[2 * (r * kPairSlots + c) + 1]; }
     apply_norm(mode, a, b, ctrl, tol, iteration);
 }
 
@@ -479,7 +481,7 @@ static int finish_sharded_norm(const ae_slab *s, ae_work *w, double *rows, int m
 {
     if (s->gl > 0) AE_TRY(comm_all_gather_groups(w->comm, rows, s->G, s->Zp, 1, st));
     else AE_TRY(comm_all_gather_rows(w->comm, rows, s->G, s->Zp, 1, st));
-    norm_finalize_kernel<<<1, 1, 0, st>>>(comm_pairs(w->comm), comm_size(w->comm), mode, w->ctrl, tol, iteration, gate);
+    norm_finalize_kernel<<<1, 1, 0, st>>>(comm_pairs(w->comm), comm_size(w->comm), 1, mode, w->ctrl, tol, iteration, gate);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
 }
@@ -530,6 +532,50 @@ int launch_finalize(const ae_slab *s, ae_work *w, const double *partial, int P, 
         if (init) AE_TRY(comm_all_gather_rows(w->comm, q_next, s->G, s->Zp, 0, st));
         else AE_TRY(finish_sharded_norm(s, w, q_next, kNormInner, tol, iteration, gate, st));
     }
+    return AE_OK;
+}
+
+// ---- pieces of the overlapped group-sharded step (ae_sweep_and_update) --------------------------------------------
+// flux assembly of group rows [g0, g0+gl) from `partial` ([P][gl][Zp]); the (num, den) pair goes to slot `slot`
+int launch_assemble_rows(const ae_slab *s, ae_work *w, const double *partial, int P, const double *fixed, const double *phi_in,
+                         double *phi_out, int g0, int gl, int slot, cudaStream_t st)
+{
+    FinArgs p;
+    p.partial = partial; p.base = w->base; p.fixed = fixed; p.mat = s->mat; p.scat = s->scat; p.phi_in = phi_in; p.phi = phi_out;
+    p.q_next = nullptr; p.norm = norm_out(w, kNormInner, 0.0, 0);
+    p.norm.pair_local = comm_pair_local(w->comm) + 2 * slot;
+    p.Z = s->Z; p.Zp = s->Zp; p.c0 = 0; p.cn = s->Zp; p.g0 = g0; p.gl = gl; p.P = P; p.G = s->G; p.M = s->M;
+    p.init = 0; p.gate = 0; p.cold = 0.0;
+    int64_t bx = (s->Zp / 2 + 255) / 256;
+    const int64_t cap = (2 * (int64_t)per_cell_blocks(s->Zp)) / s->G;
+    if (bx > cap) bx = cap;
+    if (bx > (148 * 48 + gl - 1) / gl) bx = (148 * 48 + gl - 1) / gl;
+    if (bx < 1) bx = 1;
+    flux_assemble_kernel<<<dim3((unsigned)bx, gl), 256, 0, st>>>(p);
+    AE_CUDA(cudaGetLastError());
+    return AE_OK;
+}
+
+// after the chunks' pairs have been all-gathered: the norm, then the scatter source of this rank's groups
+int launch_norm_and_scatter(const ae_slab *s, ae_work *w, const double *phi, double *q_next, int nslots, double tol, int iteration,
+                            cudaStream_t st)
+{
+    norm_finalize_kernel<<<1, 1, 0, st>>>(comm_pairs(w->comm), comm_size(w->comm), nslots, kNormInner, w->ctrl, tol, iteration, 0);
+    AE_CUDA(cudaGetLastError());
+    FinArgs p;
+    p.partial = nullptr; p.base = w->base; p.fixed = nullptr; p.mat = s->mat; p.scat = s->scat; p.phi_in = nullptr;
+    p.phi = const_cast<double *>(phi); p.q_next = q_next; p.norm = norm_out(w, kNormInner, tol, iteration);
+    p.Z = s->Z; p.Zp = s->Zp; p.c0 = 0; p.cn = s->Zp; p.g0 = s->g0; p.gl = s->gl; p.P = 0; p.G = s->G; p.M = s->M;
+    p.init = 0; p.gate = 0; p.cold = 0.0;
+    const int gblocks = (s->G + kGB - 1) / kGB;
+    const size_t smem = (size_t)s->G * (gblocks * kGB + kSC) * sizeof(double);
+    if (smem > 220 * 1024) { set_error("flux update: scatter matrix of G=%d does not fit in shared memory", s->G); return AE_BAD_ARG; }
+    if (smem > 48 * 1024)
+        AE_CUDA(cudaFuncSetAttribute((const void *)scatter_source_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t sgrid = s->Zp / kSC;
+    if (sgrid > 148 * 2) sgrid = 148 * 2;
+    scatter_source_kernel<<<(unsigned)sgrid, dim3(32, gblocks < kSWarps ? gblocks : kSWarps), smem, st>>>(p);
+    AE_CUDA(cudaGetLastError());
     return AE_OK;
 }
 

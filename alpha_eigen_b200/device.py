@@ -432,6 +432,12 @@ class SlabDevice:
         _lib.check(self.lib.ae_flux_update(C.byref(self.slab), C.byref(self.work), partial.data_ptr(), P,
                                            q_next.data_ptr(), tol, iteration, self.stream))
 
+    def sweep_and_update(self, q, psi_in, psi_out, q_next, tol=0.0, iteration=0):
+        """ae_sweep_and_update: one sweep set + flux update (group-sharded ranks overlap the flux exchange with the sweep)."""
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        _lib.check(self.lib.ae_sweep_and_update(C.byref(self.slab), C.byref(self.work), q.data_ptr(), ptr(psi_in), ptr(psi_out),
+                                                q_next.data_ptr(), tol, iteration, self.stream))
+
     def read_ctrl(self):
         """Copy the device control block to the host (synchronises the stream)."""
         self.ctrl_host.copy_(self.ctrl, non_blocking=True)

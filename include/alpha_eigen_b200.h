@@ -153,6 +153,13 @@ int ae_reduce_partials(const ae_slab *s, const double *partial, int32_t P, doubl
 int ae_flux_update(const ae_slab *s, ae_work *w, const double *partial, int32_t P, double *q_next,
                    double tol, int32_t iteration, void *stream);
 
+/* ae_sweep_set followed by ae_flux_update as one call: the unit a time-dependent source iteration repeats (the sweep's
+ * partials go to w->partial).  Group-sharded ranks (ae_slab.gl > 0) overlap the flux exchange with the sweep: their
+ * groups are swept in two chunks and the first chunk's flux is assembled and all-gathered on a second stream while the
+ * second chunk is swept.  Same results as the two calls (the norm's sum is taken chunk by chunk). */
+int ae_sweep_and_update(const ae_slab *s, ae_work *w, const double *q, const double *psi_in, double *psi_out,
+                        double *q_next, double tol, int32_t iteration, void *stream);
+
 /* Multi-GPU only: w->reduced := sum of the local angle-block partials, then reduce-scattered by rows over
  * the ranks so that this rank holds the rank-summed flux of its own cell range [r*Zp/N, (r+1)*Zp/N).
  * Follow with ae_flux_update(s, w, w->reduced, 1, ...), which updates that range and all-gathers the

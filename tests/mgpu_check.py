@@ -90,6 +90,30 @@ def main():
     assert st == 0 and list(outer) == list(rm["outer"]) and list(inner) == list(rm["inner"])
     assert rel(dgt.cells_to_host(dgt.phi), rm["phi_last"]) < 1e-10
     assert rel(dgt.psi_to_host(pg), rm["psi_last"][:, dgt.angles, :][..., dgt.groups]) < 1e-10
+    # the overlapped step (two group chunks, exchange of the first behind the sweep of the second) against the two plain calls
+    if dgt.gl > 0:
+        qa = torch.rand(dgt.G * dgt.Zp, dtype=torch.float64, device=dgt.dev, generator=torch.Generator(device=dgt.dev).manual_seed(3))
+        dgt.base.zero_()
+        outs = []
+        import os
+        os.environ["AE_EXCHANGE_OVERLAP"] = "1"                         # also at 2 ranks, where it is off by default
+        for fused in (False, True):
+            pa = dgt.psi_to_device(psi0)
+            qn = torch.zeros_like(qa)
+            for b in dgt._phi_bufs:                                     # same previous iterate for both runs
+                b.fill_(0.25)
+            if fused:
+                dgt.sweep_and_update(qa, pa, pa, qn, 0.0, 1)
+            else:
+                import ctypes as C
+                from alpha_eigen_b200 import _lib
+                _lib.check(dgt.lib.ae_sweep_set(C.byref(dgt.slab), qa.data_ptr(), pa.data_ptr(), pa.data_ptr(),
+                                                dgt.partial.data_ptr(), dgt.sync.data_ptr(), dgt.stream))
+                dgt.flux_update(dgt.partial, dgt.P, qn, 0.0, 1)
+            torch.cuda.synchronize()
+            outs.append((dgt.phi.clone(), qn.clone(), pa.clone(), dgt.read_ctrl().change))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+        assert abs(outs[0][3] - outs[1][3]) < 1e-13 * abs(outs[0][3])
     gfirst, gK = dmd_window(gsteps)
     Rg = dgt.tsqr(gsnap, n_pg, gfirst, gK + 1)                       # rows of this rank's groups; factors merged across ranks
     alg, sigg, rkg = dgt.dmd_from_r(Rg, gK, 0.1)
