@@ -28,10 +28,11 @@ __device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, dou
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// Each CTA (8 warps) owns a contiguous range of columns and accumulates the full n x n Gram of it.
-// Warp w computes output rows [16w, 16w+16) x all 128 columns as 2 x 16 DMMA tiles of 8x8
-// (64 accumulator doubles per lane).  The A fragment (row i0+lane/4, k0+lane%4) and the B fragment
-// (col j0+lane/4, k0+lane%4) are the same access pattern on the staged tile, because B = S^T.
+// Each CTA (8 warps) owns a contiguous range of columns and accumulates the Gram matrix of it -- its UPPER block
+// triangle only (the matrix is symmetric): the 16 strips of 8 rows have 16, 15, ..., 1 tiles of 8 x 8 on or above the
+// diagonal, so warp w takes strips w and 15 - w, 17 tiles, the same for every warp (the full square would be 32).
+// The A fragment (row i0+lane/4, k0+lane%4) and the B fragment (col j0+lane/4, k0+lane%4) are the same access pattern
+// on the staged tile, because B = S^T.
 __global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ snap, int64_t ld, int64_t len, int n,
                                                    int64_t cols_per_cta, double *__restrict__ partial)
 {
@@ -39,7 +40,8 @@ __global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ sn
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t c_begin = (int64_t)blockIdx.x * cols_per_cta;
     const int64_t c_end = min(len, c_begin + cols_per_cta);
-    double acc[2][16][2];
+    const int s0 = warp, s1 = 15 - warp;                // this warp's two row strips (s0 < s1)
+    double acc[2][16][2];                               // [strip][column tile]: tiles b >= strip are live
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -56,24 +58,27 @@ __global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ sn
         __syncthreads();
 #pragma unroll
         for (int k0 = 0; k0 < kGK; k0 += 4) {
-            double af[2];
-#pragma unroll
-            for (int a = 0; a < 2; ++a) af[a] = tile[(warp * 16 + a * 8 + (lane >> 2)) * kGStride + k0 + (lane & 3)];
+            const double a0 = tile[(s0 * 8 + (lane >> 2)) * kGStride + k0 + (lane & 3)];
+            const double a1 = tile[(s1 * 8 + (lane >> 2)) * kGStride + k0 + (lane & 3)];
 #pragma unroll
             for (int b = 0; b < 16; ++b) {
-                const double bf = tile[(b * 8 + (lane >> 2)) * kGStride + k0 + (lane & 3)];
-#pragma unroll
-                for (int a = 0; a < 2; ++a) dmma_8x8x4(acc[a][b][0], acc[a][b][1], af[a], bf);
+                if (b >= s0) {                          // warp-uniform
+                    const double bf = tile[(b * 8 + (lane >> 2)) * kGStride + k0 + (lane & 3)];
+                    dmma_8x8x4(acc[0][b][0], acc[0][b][1], a0, bf);
+                    if (b >= s1) dmma_8x8x4(acc[1][b][0], acc[1][b][1], a1, bf);
+                }
             }
         }
     }
-    // C fragment: row = lane/4, cols = 2*(lane%4) + {0,1}
+    // C fragment: row = lane/4, cols = 2*(lane%4) + {0,1}; only the live tiles are written (the reduction mirrors them)
     double *out = partial + (size_t)blockIdx.x * kGN * kGN;
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
-            const int r = warp * 16 + a * 8 + (lane >> 2), c = b * 8 + 2 * (lane & 3);
+            const int strip = a ? s1 : s0;
+            if (b < strip) continue;
+            const int r = strip * 8 + (lane >> 2), c = b * 8 + 2 * (lane & 3);
             out[r * kGN + c] = acc[a][b][0];
             out[r * kGN + c + 1] = acc[a][b][1];
         }
@@ -83,7 +88,8 @@ __global__ void gram_reduce_kernel(const double *__restrict__ partial, int npart
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * n) return;
-    const int r = idx / n, c = idx % n;
+    int r = idx / n, c = idx % n;
+    if ((r >> 3) > (c >> 3)) { const int t = r; r = c; c = t; }     // lower block triangle: the mirror tile
     double s = 0.0;
     for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * kGN * kGN + r * kGN + c];
     gram[idx] = s;
