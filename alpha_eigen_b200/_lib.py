@@ -89,6 +89,7 @@ SYMBOLS = {
     "ae_comm_allreduce_sum": (C.c_int, [_P, _P, C.c_int64, _P]),
     "ae_comm_gather_rows": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P]),
     "ae_comm_gather_groups": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P]),
+    "ae_comm_exchange_mode": (C.c_int32, [_P]),
     "ae_group_range": (None, [C.c_int32, C.c_int32, C.c_int32, c_ip, c_ip]),
     "ae_comm_destroy": (C.c_int, [_P]),
 }

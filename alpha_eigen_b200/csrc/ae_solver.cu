@@ -39,7 +39,7 @@ void group_chunk_range(int gl, int count, int chunk, int *off, int *len);
 int comm_size(const void *comm);
 cudaStream_t comm_aux_stream(void *comm);
 cudaEvent_t comm_event(void *comm, int i);
-void sweep_reserve_sms(int n);
+bool comm_peer_exchange_ready(void *comm, int G, int64_t Zp, cudaStream_t st);
 int launch_outer_check(const ae_slab *s, ae_work *w, cudaStream_t st);
 int launch_ctrl_init(ae_work *w, cudaStream_t st);
 
@@ -169,21 +169,23 @@ extern "C" int ae_flux_update(const ae_slab *s, ae_work *w, const double *partia
     return AE_OK;
 }
 
-// One sweep set + flux update as ONE call (what a time-dependent source iteration consists of).  Group-sharded ranks
-// run it in two chunks of their groups: while the second chunk is swept (on a few SMs less), the first chunk's flux is
-// assembled and all-gathered on a second stream, so only the second, small chunk's exchange is exposed.
+// One sweep set + flux update as ONE call (what a time-dependent source iteration consists of).
+// AE_EXCHANGE_OVERLAP=1 (group-sharded ranks with the peer exchange of ae_comm.cu, which needs no SM) runs it in two
+// chunks of the rank's groups: the first chunk's flux is assembled right after its sweep and travels on a second stream
+// while the second, two-group chunk is swept.  It is NOT the default: the exchange does hide, but a sweep of two groups
+// has too few rows for the wavefront over cell segments that keeps the SMs busy, and loses more than the exchange costs
+// (C4 on 2 GPUs: 30.6 ms per step split, 28.0 ms unsplit; with NCCL on the second stream and 16 SMs held back for it,
+// 8 GPUs: 10.1 against 8.35 ms).
 extern "C" int ae_sweep_and_update(const ae_slab *s, ae_work *w, const double *q, const double *psi_in, double *psi_out,
                                    double *q_next, double tol, int32_t iteration, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     AE_TRY(check_work(s, w, "ae_sweep_and_update"));
     if (!q || !q_next) { set_error("ae_sweep_and_update: bad argument"); return AE_BAD_ARG; }
-    // Overlap pays when the exchange of the head chunk fits behind the sweep of the two-group tail chunk: from 4 ranks on
-    // (measured at 2 ranks: the head's 4 GB of partial sums and the tail's sweep fight for HBM, 29.8 against 28.5 ms per step).
-    // AE_EXCHANGE_OVERLAP = 0 / 1 forces it off / on.
     static const char *force = getenv("AE_EXCHANGE_OVERLAP");
-    const bool overlap = force ? force[0] == '1' : (w->comm && comm_size(w->comm) >= 4);
-    const int chunks = (w->comm && s->gl > 0 && overlap) ? group_chunks(s->G, comm_size(w->comm)) : 1;
+    int chunks = 1;
+    if (w->comm && s->gl > 0 && force && force[0] == '1' && comm_peer_exchange_ready(w->comm, s->G, s->Zp, st))
+        chunks = group_chunks(s->G, comm_size(w->comm));
     if (chunks < 2) {
         AE_TRY(launch_sweep(s, q, psi_in, psi_out, w->partial, w->sweep_sync, w->ctrl, 0, nullptr, st));
         if (w->comm && s->gl <= 0) {
@@ -193,8 +195,6 @@ extern "C" int ae_sweep_and_update(const ae_slab *s, ae_work *w, const double *q
             AE_TRY(launch_finalize(s, w, w->partial, w->P, nullptr, w->phi, w->phi_alt, q_next, 0, 0.0, tol, iteration, 0, st));
         }
     } else {
-        static const char *res = getenv("AE_EXCHANGE_RESERVE_SMS");
-        const int reserve = res ? atoi(res) : 16;
         cudaStream_t aux = comm_aux_stream(w->comm);
         const size_t row = (size_t)s->A * s->Zp;                                // psi elements per group
         size_t part_off = 0;
@@ -206,14 +206,11 @@ extern "C" int ae_sweep_and_update(const ae_slab *s, ae_work *w, const double *q
             ae_slab view = *s;
             view.g0 = s->g0 + off; view.gl = len;
             double *part = w->partial + part_off;                               // this chunk's own [P][len][Zp] region
-            sweep_reserve_sms(c > 0 ? reserve : 0);                             // the first chunk has the device to itself
-            const int rc = launch_sweep(&view, q, psi_in ? psi_in + off * row : nullptr, psi_out ? psi_out + off * row : nullptr,
-                                        part, w->sweep_sync, w->ctrl, 0, nullptr, st);
-            sweep_reserve_sms(0);
-            AE_TRY(rc);
+            AE_TRY(launch_sweep(&view, q, psi_in ? psi_in + off * row : nullptr, psi_out ? psi_out + off * row : nullptr,
+                                part, w->sweep_sync, w->ctrl, 0, nullptr, st));
+            AE_TRY(launch_assemble_rows(s, w, part, w->P, nullptr, w->phi, w->phi_alt, view.g0, len, c, st));
             AE_CUDA(cudaEventRecord(comm_event(w->comm, c), st));
             AE_CUDA(cudaStreamWaitEvent(aux, comm_event(w->comm, c), 0));
-            AE_TRY(launch_assemble_rows(s, w, part, w->P, nullptr, w->phi, w->phi_alt, view.g0, len, c, aux));
             AE_TRY(comm_all_gather_group_chunk(w->comm, w->phi_alt, s->G, s->Zp, chunks, c, c == chunks - 1, aux));
             part_off += (size_t)w->P * len * s->Zp;
         }

@@ -779,11 +779,6 @@ static int64_t plan_grid(SweepArgs &p, int64_t resident)
     return grid;
 }
 
-// SMs the next sweep launches of this host thread leave free (the overlapped multi-GPU step keeps a few for the
-// collective's kernels, which cannot share an SM with a sweep CTA: it fills the shared memory and the register file)
-static thread_local int t_reserve_sms = 0;
-void sweep_reserve_sms(int n) { t_reserve_sms = n > 0 ? n : 0; }
-
 template <int AC, bool RD, bool WR>
 static int launch_variant(const SweepArgs &p_in, const ae_ctrl *ctrl, int gate, cudaStream_t st)
 {
@@ -803,8 +798,7 @@ static int launch_variant(const SweepArgs &p_in, const ae_ctrl *ctrl, int gate, 
     int dev = 0, sms = 0;
     AE_CUDA(cudaGetDevice(&dev));
     AE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int free_sms = sms - t_reserve_sms > sms / 2 ? sms - t_reserve_sms : sms / 2;
-    const int64_t grid = plan_grid(p, (int64_t)free_sms * ctas_per_sm);
+    const int64_t grid = plan_grid(p, (int64_t)sms * ctas_per_sm);
     sweep_kernel<AC, RD, WR><<<(unsigned)grid, threads, smem, st>>>(p, ctrl, gate);
     AE_CUDA(cudaGetLastError());
     return AE_OK;
@@ -830,8 +824,7 @@ static int launch_phi(const SweepArgs &p_in, const ae_ctrl *ctrl, int gate, int 
         AE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         ctas_per_sm = n;
     }
-    const int free_sms = sms - t_reserve_sms > sms / 2 ? sms - t_reserve_sms : sms / 2;
-    const int64_t grid = plan_grid(p, (int64_t)free_sms * ctas_per_sm);
+    const int64_t grid = plan_grid(p, (int64_t)sms * ctas_per_sm);
     phi_sweep_kernel<<<(unsigned)grid, kPhiThreads, smem, st>>>(p, ctrl, gate);
     AE_CUDA(cudaGetLastError());
     *P_out = p.nbg;

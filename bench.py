@@ -386,6 +386,13 @@ def main():
         ms_total, phase = float(t[0]), [float(x) for x in t[1:]]
     sweep_ms = phase[0]
     sweep_ms_source = "CUDA events around the sweep launches of the timed steps"
+    exchange_mode = None
+    if group_mode and world > 1:
+        peer = dev.lib.ae_comm_exchange_mode(dev.comm.handle) == 1          # what the library actually did
+        split = peer and os.environ.get("AE_EXCHANGE_OVERLAP", "0") == "1" and G // world >= 3
+        exchange_mode = (("copy engines over NVLink into IPC-shared peer buffers, flags by stream memory operations (no SM)"
+                          if peer else "ncclAllGather through a staging buffer") +
+                         ("; two group chunks, the first travels while the second is swept" if split else "; one chunk after the sweep"))
     if group_mode:
         # the overlapped step cannot be cut into phases from outside: the sweep kernel is timed alone right after the
         # timed region (same launch, whole grid), the remainder of a step is exchange + update that the sweep did not hide
@@ -402,7 +409,21 @@ def main():
             t = torch.tensor([sweep_ms], dtype=torch.float64, device=dev.dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sweep_ms = float(t[0])
-        sweep_ms_source = "5 sweep-only launches timed right after the timed region (the overlapped step has no phase boundaries)"
+        sweep_ms_source = "5 sweep-only launches timed right after the timed region (the step is one C call)"
+        exchange_ms = None
+        if world > 1:
+            # the flux exchange alone (all-gather of the group rows of phi), ranks aligned by a barrier first
+            dist.barrier()
+            fence()
+            xev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            xev[0].record()
+            for k in range(5):
+                _lib.check(dev.lib.ae_comm_gather_groups(dev.comm.handle, dev.phi.data_ptr(), G, dev.Zp, dev.stream))
+            xev[1].record()
+            fence()
+            t = torch.tensor([xev[0].elapsed_time(xev[1]) / 5], dtype=torch.float64, device=dev.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            exchange_ms = float(t[0])
     ms_per_step = ms_total / args.steps
     value = updates_per_step / (ms_per_step * 1e-3)
     gpu_launches = launches
@@ -521,8 +542,10 @@ def main():
                          "sweep_share_of_step": sweep_ms / ms_per_step},
             "roofline_inner": inner,
             "breakdown_ms": ({"sweep_alone": sweep_ms, "exposed_exchange_and_update": ms_per_step - sweep_ms,
-                              "what": "group-sharded overlapped step: sweep kernel timed alone; the rest of the step is what the "
-                                      "sweep did not hide (second chunk's assembly + all-gather, norm, scatter source)"}
+                              "exchange_alone": exchange_ms, "exchange": exchange_mode,
+                              "what": "group-sharded step: the whole-range sweep kernel timed alone; the rest of the step is what "
+                                      "the sweep did not hide (flux assembly, the exposed part of the flux exchange, norm, scatter "
+                                      "source, and what splitting the sweep in two launches costs)"}
                              if group_mode else
                              {"sweep": phase[0], "exchange_reduce_scatter": phase[1], "flux_update_and_allgather": phase[2]}),
             "parity_check": parity,

@@ -261,6 +261,10 @@ int ae_comm_allreduce_sum(void *comm, double *buf, int64_t count, void *stream);
 /* Group-sharded ranks: rows [G][Zp], rank r contributes rows [g0_r, g0_r + gl_r) of the balanced contiguous
  * partition of the G groups (ae_group_range), in place. */
 int ae_comm_gather_groups(void *comm, double *rows, int32_t G, int64_t Zp, void *stream);
+/* How the group-sharded flux exchange of this communicator travels: 1 = copy engines over NVLink into IPC-shared peer
+ * buffers, signalled by stream memory operations (no SM, overlaps the sweep); 0 = NCCL all-gather (peer mapping was
+ * not possible, or AE_COMM_PEER_COPY=0); -1 = not decided yet (no exchange has run). */
+int32_t ae_comm_exchange_mode(void *comm);
 void ae_group_range(int32_t G, int32_t nranks, int32_t rank, int32_t *g0, int32_t *gl);
 /* rows [G][Zp]: every rank contributes its cell range of every row, in place (all-gather). */
 int ae_comm_gather_rows(void *comm, double *rows, int32_t G, int64_t Zp, void *stream);

@@ -96,7 +96,7 @@ def main():
         dgt.base.zero_()
         outs = []
         import os
-        os.environ["AE_EXCHANGE_OVERLAP"] = "1"                         # also at 2 ranks, where it is off by default
+        os.environ["AE_EXCHANGE_OVERLAP"] = "1"                         # the two-chunk step is opt-in
         for fused in (False, True):
             pa = dgt.psi_to_device(psi0)
             qn = torch.zeros_like(qa)
@@ -114,6 +114,11 @@ def main():
             outs.append((dgt.phi.clone(), qn.clone(), pa.clone(), dgt.read_ctrl().change))
         assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
         assert abs(outs[0][3] - outs[1][3]) < 1e-13 * abs(outs[0][3])
+        xmode = dgt.lib.ae_comm_exchange_mode(dgt.comm.handle)
+        want = 0 if os.environ.get("AE_COMM_PEER_COPY") == "0" else 1
+        assert xmode == want, f"flux exchange mode {xmode}, expected {want} (1 = peer copies, 0 = NCCL)"
+        if rank == 0:
+            print(f"group-sharded flux exchange: {'peer copies (copy engines + stream memory operations)' if xmode == 1 else 'NCCL all-gather'}")
     gfirst, gK = dmd_window(gsteps)
     Rg = dgt.tsqr(gsnap, n_pg, gfirst, gK + 1)                       # rows of this rank's groups; factors merged across ranks
     alg, sigg, rkg = dgt.dmd_from_r(Rg, gK, 0.1)
