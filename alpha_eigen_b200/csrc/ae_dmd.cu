@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "ae_common.cuh"
+#include "ae_dmd_small.cuh"
 
 namespace ae {
 
@@ -552,11 +553,125 @@ extern "C" int ae_tsqr_merge(const double *r_stack, int32_t count, int32_t n, do
     return tsqr_launch(r_stack, n, (int64_t)count * n, n, true, (int64_t)count * n, 1, r_out, st);
 }
 
+// ---- the small dense part as ONE block per window (ae_dmd_small.cuh) ----------------------------------------------
+struct BlockTeam {
+    __device__ int lane() const { return threadIdx.x & 31; }
+    __device__ int lanes() const { return 32; }
+    __device__ int warp() const { return threadIdx.x >> 5; }
+    __device__ int warps() const { return blockDim.x >> 5; }
+    __device__ double sum(double x) const
+    {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);   // butterfly: every lane gets the same bits
+        return x;
+    }
+    __device__ void count(int *c) const { atomicAdd(c, 1); }
+    __device__ void sync_warp() const { __syncwarp(); }
+    __device__ void sync_block() const { __syncthreads(); }
+};
+
+constexpr int kSmallThreads = 512;
+
+__global__ void __launch_bounds__(kSmallThreads, 1)
+dmd_small_kernel(const double *__restrict__ r_stack, int K, double dt, double rank_tol, double *__restrict__ at_scratch,
+                 double *__restrict__ alpha_re, double *__restrict__ alpha_im, double *__restrict__ sigma,
+                 int *__restrict__ rank, int *__restrict__ info)
+{
+    extern __shared__ double small_smem[];
+    const int n = K + 1;
+    const size_t b = blockIdx.x;
+    double *A = small_smem, *B = A + (size_t)n * K, *sig = B + (size_t)n * K, *eigw = sig + K;
+    int *ord = (int *)(eigw + 3 * K), *counter = ord + K;
+    BlockTeam t;
+    const int st = ae_dmd_small::dmd_window(t, r_stack + b * n * n, K, dt, rank_tol, A, B, sig, eigw, ord, counter,
+                                            at_scratch + b * n * n, alpha_re + b * K, alpha_im + b * K, sigma + b * K, rank + b);
+    if (threadIdx.x == 0) info[b] = st;
+}
+
+static bool small_fits(int K) { return K >= 1 && ae_dmd_small::dmd_window_smem_bytes(K) <= 227 * 1024; }
+
+// `count` windows, r_stack [count][K+1][K+1] (device); host outputs [count][K] / [count]
+static int dmd_small_batched(const double *r_stack, int count, int K, double dt, double rank_tol, double *alpha_re,
+                             double *alpha_im, double *sigma_out, int32_t *rank, int32_t *info, cudaStream_t st)
+{
+    int status = AE_OK;
+    const int n = K + 1;
+    const size_t smem = ae_dmd_small::dmd_window_smem_bytes(K);
+    double *dAt = nullptr, *dOut = nullptr;
+    int *dInt = nullptr;
+    const size_t per = (size_t)count * K;
+    double *hOut = (double *)malloc(sizeof(double) * 3 * per);
+    int *hInt = (int *)malloc(sizeof(int) * 2 * count);
+    AE_CUDA_G(cudaFuncSetAttribute((const void *)dmd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AE_CUDA_G(cudaMallocAsync((void **)&dAt, sizeof(double) * (size_t)count * n * n, st));
+    AE_CUDA_G(cudaMallocAsync((void **)&dOut, sizeof(double) * 3 * per, st));
+    AE_CUDA_G(cudaMallocAsync((void **)&dInt, sizeof(int) * 2 * count, st));
+    AE_CUDA_G(cudaMemsetAsync(dOut, 0, sizeof(double) * 3 * per, st));
+    dmd_small_kernel<<<count, kSmallThreads, smem, st>>>(r_stack, K, dt, rank_tol, dAt, dOut, dOut + per, dOut + 2 * per, dInt, dInt + count);
+    AE_CUDA_G(cudaGetLastError());
+    AE_CUDA_G(cudaMemcpyAsync(hOut, dOut, sizeof(double) * 3 * per, cudaMemcpyDeviceToHost, st));
+    AE_CUDA_G(cudaMemcpyAsync(hInt, dInt, sizeof(int) * 2 * count, cudaMemcpyDeviceToHost, st));
+    AE_CUDA_G(cudaStreamSynchronize(st));
+    memcpy(alpha_re, hOut, sizeof(double) * per);
+    memcpy(alpha_im, hOut + per, sizeof(double) * per);
+    if (sigma_out) memcpy(sigma_out, hOut + 2 * per, sizeof(double) * per);
+    for (int m = 0; m < count; ++m) { rank[m] = hInt[m]; info[m] = hInt[count + m]; }
+done:
+    cudaFreeAsync(dAt, st); cudaFreeAsync(dOut, st); cudaFreeAsync(dInt, st);
+    free(hOut); free(hInt);
+    return status;
+}
+
+static int small_info_to_status(int info, const char *who)
+{
+    if (info == ae_dmd_small::kOk) return AE_OK;
+    if (info == ae_dmd_small::kNoRank) { set_error("%s: no singular value survives the rank rule", who); return AE_BAD_ARG; }
+    set_error("%s: %s did not converge", who, info == ae_dmd_small::kSvdNotConverged ? "Jacobi SVD" : "QR eigenvalue iteration");
+    return AE_CUDA_ERROR;
+}
+
+static int dmd_from_r_cusolver(const double *r_dev, int32_t K, double dt, double rank_tol, double *alpha_re, double *alpha_im,
+                               double *sigma_out, int32_t *rank, cudaStream_t st);
+
+// Windows that fit one block's shared memory (K <= 118) take the block kernel; AE_DMD_CUSOLVER=1 keeps them on the library (A/B).
+static bool use_small_kernel(int K)
+{
+    const char *env = getenv("AE_DMD_CUSOLVER");              // read per call: the tests flip it
+    return small_fits(K) && !(env && env[0] == '1');
+}
+
 extern "C" int ae_dmd_from_r(const double *r_dev, int32_t K, double dt, double rank_tol, double *alpha_re,
                              double *alpha_im, double *sigma_out, int32_t *rank, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (!r_dev || K < 1 || !alpha_re || !alpha_im || !rank) { set_error("ae_dmd_from_r: bad argument"); return AE_BAD_ARG; }
+    if (!use_small_kernel(K)) return dmd_from_r_cusolver(r_dev, K, dt, rank_tol, alpha_re, alpha_im, sigma_out, rank, st);
+    int32_t info = 0;
+    AE_TRY(dmd_small_batched(r_dev, 1, K, dt, rank_tol, alpha_re, alpha_im, sigma_out, rank, &info, st));
+    return small_info_to_status(info, "ae_dmd_from_r");
+}
+
+extern "C" int ae_dmd_from_r_batched(const double *r_stack, int32_t count, int32_t K, double dt, double rank_tol,
+                                     double *alpha_re, double *alpha_im, double *sigma_out, int32_t *rank, int32_t *status,
+                                     void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!r_stack || count < 1 || K < 1 || !alpha_re || !alpha_im || !rank || !status) { set_error("ae_dmd_from_r_batched: bad argument"); return AE_BAD_ARG; }
+    if (use_small_kernel(K)) {
+        AE_TRY(dmd_small_batched(r_stack, count, K, dt, rank_tol, alpha_re, alpha_im, sigma_out, rank, status, st));
+        for (int m = 0; m < count; ++m) status[m] = small_info_to_status(status[m], "ae_dmd_from_r_batched");
+        return AE_OK;
+    }
+    const size_t n = (size_t)K + 1;
+    for (int m = 0; m < count; ++m)
+        status[m] = dmd_from_r_cusolver(r_stack + m * n * n, K, dt, rank_tol, alpha_re + (size_t)m * K, alpha_im + (size_t)m * K,
+                                        sigma_out ? sigma_out + (size_t)m * K : nullptr, rank + m, st);
+    return AE_OK;
+}
+
+static int dmd_from_r_cusolver(const double *r_dev, int32_t K, double dt, double rank_tol, double *alpha_re,
+                               double *alpha_im, double *sigma_out, int32_t *rank, cudaStream_t st)
+{
     int status = AE_OK;
     const int n = K + 1;
     cusolverDnHandle_t h = nullptr;

@@ -521,6 +521,16 @@ class SlabDevice:
         n = rk.value
         return np.array(are[:n]) + 1j * np.array(aim[:n]), np.array(sig[:]), n
 
+    def dmd_from_r_batched(self, r_stack, count, K, dt, rank_tol=1e-13):
+        """ae_dmd_from_r_batched: `count` triangular factors [count][K+1][K+1] (device) -> list of (alphas, sigma, rank)
+        or the status code of a window that failed."""
+        are, aim, sig = (np.zeros((count, K)) for _ in range(3))
+        rk, st = np.zeros(count, dtype=np.int32), np.zeros(count, dtype=np.int32)
+        _lib.check(self.lib.ae_dmd_from_r_batched(r_stack.data_ptr(), count, K, dt, rank_tol, are.ctypes.data, aim.ctypes.data,
+                                                  sig.ctypes.data, rk.ctypes.data, st.ctypes.data, self.stream))
+        return [(are[m, :rk[m]] + 1j * aim[m, :rk[m]], sig[m].copy(), int(rk[m])) if st[m] == 0 else int(st[m])
+                for m in range(count)]
+
     def dmd_from_gram(self, gram, K, dt, rank_tol=1e-13):
         are, aim, sig = (C.c_double * K)(), (C.c_double * K)(), (C.c_double * K)()
         r = C.c_int32(0)

@@ -101,7 +101,7 @@ def march_batched(devs, psis, psi_snaps, phi_snaps, num_steps, tol=1e-10):
 
 
 def solve_members_batched(members, dt, num_steps, tol=1e-10, rank_tol=1e-13, keep_snapshots=False, snapshots="psi",
-                          memory_fraction=0.6, timings=None, dmd_threads=8):
+                          memory_fraction=0.6, timings=None):
     """March a list of same-shape members with the batched kernel (in chunks that fit HBM), then their DMDs.
     `timings` (dict, optional) receives wall seconds of the setup / march / dmd phases."""
     import time
@@ -134,24 +134,29 @@ def solve_members_batched(members, dt, num_steps, tol=1e-10, rank_tol=1e-13, kee
         status, outer, inner, teams = march_batched(devs, psis, snaps if snapshots == "psi" else None,
                                                     snaps if snapshots == "phi" else None, num_steps, tol)
         t0 = lap("march", t0)
-        def finish(j):
-            # the small dense part of a DMD is latency bound (cuSOLVER gesvd / geev on ~116 x 115): members overlap on
-            # their own streams, one host thread each (the solver context is per thread)
-            dev = devs[j]
+        # DMDs: one TSQR per member (each fills the GPU), then the small dense parts of ALL members in one launch
+        # (ae_dmd_from_r_batched: one thread block per window)
+        first, K = dmd_window(num_steps)
+        ok = [j for j in range(len(devs)) if status[j] == 0]
+        dmds = {}
+        if ok:
+            d0 = devs[0]
+            r_stack = torch.empty(len(ok) * (K + 1) * (K + 1), dtype=torch.float64, device=d0.dev)
+            for i, j in enumerate(ok):
+                r_stack[i * (K + 1) * (K + 1):(i + 1) * (K + 1) * (K + 1)] = devs[j].tsqr(snaps[j], rows, first, K + 1)
+            for j, res in zip(ok, d0.dmd_from_r_batched(r_stack, len(ok), K, dt, rank_tol)):
+                if isinstance(res, int):
+                    raise RuntimeError(f"DMD of member {c0 + j} failed with status {res}")
+                alphas, sigma, r = res
+                order = np.lexsort((alphas.imag, -alphas.real))
+                dmds[j] = (alphas[order], sigma, r)
+        for j, dev in enumerate(devs):
             out = dict(status=int(status[j]), outer=outer[j], inner=inner[j], in_flight=teams)
-            stream = torch.cuda.Stream(device=dev.dev)
-            with torch.cuda.stream(stream):
-                if status[j] == 0:
-                    alphas, sigma, r = member_dmd(dev, snaps[j], rows, num_steps, dt, rank_tol)
-                    out.update(alphas=alphas, sigma=sigma, rank=r)
-                if keep_snapshots:
-                    out.update(psi_last=dev.psi_to_host(psis[j]), angles=dev.angles, snap=snaps[j], dev=dev)
-                stream.synchronize()
-            return out
-
-        torch.cuda.synchronize()
-        with ThreadPoolExecutor(max_workers=max(1, int(dmd_threads))) as pool:
-            results.extend(pool.map(finish, range(len(devs))))
+            if j in dmds:
+                out.update(alphas=dmds[j][0], sigma=dmds[j][1], rank=dmds[j][2])
+            if keep_snapshots:
+                out.update(psi_last=dev.psi_to_host(psis[j]), angles=dev.angles, snap=snaps[j], dev=dev)
+            results.append(out)
         lap("dmd", t0)
         del devs, psis, snaps
     if timings is not None:

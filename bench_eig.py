@@ -222,6 +222,40 @@ def case_c5_batched(out, E=128, Z=2048, A=16, G=12, steps=200, snapshots="psi"):
          "ranks": [int(res[0]["rank"]), int(res[-1]["rank"])]})
 
 
+def case_c5_member_validation(out, Z=2048, A=16, G=12, steps=200):
+    """One ensemble member's DMD three ways on the SAME device snapshots: the block kernel (default), the cuSOLVER route
+    (AE_DMD_CUSOLVER=1) and the reference routine's arithmetic on the host (oracle.dmd_alpha: LAPACK SVD of the full
+    snapshot matrix), plus the host routine on snapshots perturbed by 1e-15 relative: the window's own sensitivity."""
+    from alpha_eigen_b200.ensemble import solve_member, synthetic_ensemble, member_dmd
+    from oracle import ae_oracle as orc
+    p = synthetic_ensemble(1024, Z, A, G)[0]
+    os.environ.pop("AE_DMD_CUSOLVER", None)
+    res = solve_member(p, 0.1, steps, keep_snapshots=True)
+    dev, snap = res["dev"], res["snap"]
+    rows = snap.numel() // steps
+    t0 = time.perf_counter(); al_k, sig_k, r_k = member_dmd(dev, snap, rows, steps, 0.1); sync(); t_k = time.perf_counter() - t0
+    os.environ["AE_DMD_CUSOLVER"] = "1"
+    t0 = time.perf_counter(); al_l, sig_l, r_l = member_dmd(dev, snap, rows, steps, 0.1); sync(); t_l = time.perf_counter() - t0
+    os.environ.pop("AE_DMD_CUSOLVER", None)
+    X = snap.cpu().numpy().reshape(steps, rows).T
+    t0 = time.perf_counter(); al_h, sig_h, r_h = orc.dmd_alpha(X, steps, 0.1, return_rank_info=True); t_h = time.perf_counter() - t0
+    srt = lambda z: np.asarray(z)[np.lexsort((np.asarray(z).imag, -np.asarray(z).real))]
+    rs = np.random.RandomState(1)
+    al_p = orc.dmd_alpha(X * (1 + 1e-15 * rs.randn(*X.shape)), steps, 0.1)
+    a_h = srt(al_h)[0]
+    rel = lambda z: float(abs(srt(z)[0] - a_h) / abs(a_h))
+    m = min(len(sig_h), len(sig_k))
+    out({"case": "c5_member_dmd_validation", "rows": int(rows), "steps": steps,
+         "alpha0_host": [float(a_h.real), float(a_h.imag)], "rank_host": int(r_h), "host_s": t_h,
+         "alpha0_block_kernel": float(srt(al_k)[0].real), "rank_block_kernel": int(r_k), "block_kernel_rel_diff": rel(al_k),
+         "block_kernel_member_dmd_s": t_k,
+         "alpha0_cusolver": float(srt(al_l)[0].real), "rank_cusolver": int(r_l), "cusolver_rel_diff": rel(al_l),
+         "cusolver_member_dmd_s": t_l,
+         "host_perturbed_1e-15_rel_diff": rel(al_p),
+         "sigma_rel_err_block_kernel": float(np.max(np.abs(sig_k[:m] - sig_h[:m])) / sig_h[0]),
+         "sigma_rel_err_cusolver": float(np.max(np.abs(sig_l[:m] - sig_h[:m])) / sig_h[0])})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "eig_bench.jsonl"))
@@ -250,6 +284,7 @@ def main():
         case_c5_batched(out, E=args.c5_members)
         case_c5_batched(out, E=args.c5_members, snapshots="phi")
         case_c5_sample(out, E=min(32, args.c5_members))
+        case_c5_member_validation(out)
         f.close()
         return
     case_kp_k(out)
@@ -262,6 +297,7 @@ def main():
     if not args.skip_c5:
         case_c5_batched(out, E=args.c5_members)
         case_c5_sample(out)
+        case_c5_member_validation(out)
     f.close()
 
 

@@ -250,9 +250,16 @@ int ae_tsqr(const double *snap, int64_t ld, int64_t len, int32_t n, double *r, v
  * allgather of the per-rank factors of a row-sharded snapshot matrix. */
 int ae_tsqr_merge(const double *r_stack, int32_t count, int32_t n, double *r, void *stream);
 /* As ae_dmd_from_gram, from the triangular factor r [K+1][K+1] (device): thin SVD of r[:, 0:K]
- * (cuSOLVER gesvd) gives sigma and V of X; Atilde = U_r^T r[:, 1:K+1] V S^-1. */
+ * gives sigma and V of X; Atilde = U_r^T r[:, 1:K+1] V S^-1; eigenvalues of Atilde. */
 int ae_dmd_from_r(const double *r, int32_t K, double dt, double rank_tol,
                   double *alpha_re, double *alpha_im, double *sigma, int32_t *rank, void *stream);
+/* The same for `count` windows at once (an ensemble's members): r_stack [count][K+1][K+1] (device); host outputs
+ * alpha_re / alpha_im / sigma [count][K], rank / status [count] (status[m] is the code ae_dmd_from_r would have
+ * returned for window m).  Windows of K <= 118 columns run as one thread block each of ONE launch (one-sided Jacobi
+ * SVD, rank rule, Atilde, balanced Hessenberg-QR eigenvalues in shared memory; ae_dmd_from_r takes the same kernel);
+ * wider ones go through cuSOLVER one by one. */
+int ae_dmd_from_r_batched(const double *r_stack, int32_t count, int32_t K, double dt, double rank_tol,
+                          double *alpha_re, double *alpha_im, double *sigma, int32_t *rank, int32_t *status, void *stream);
 
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink ---------------------------------- */
 int ae_comm_unique_id(void *id128);                                     /* host, 128 bytes */
@@ -262,8 +269,8 @@ int ae_comm_allreduce_sum(void *comm, double *buf, int64_t count, void *stream);
  * partition of the G groups (ae_group_range), in place. */
 int ae_comm_gather_groups(void *comm, double *rows, int32_t G, int64_t Zp, void *stream);
 /* How the group-sharded flux exchange of this communicator travels: 1 = copy engines over NVLink into IPC-shared peer
- * buffers, signalled by stream memory operations (no SM, overlaps the sweep); 0 = NCCL all-gather (peer mapping was
- * not possible, or AE_COMM_PEER_COPY=0); -1 = not decided yet (no exchange has run). */
+ * buffers, signalled by stream memory operations (no SM; opt-in with AE_COMM_PEER_COPY=1); 0 = NCCL all-gather (the
+ * default, and the fallback when the peers cannot be mapped); -1 = not decided yet (no exchange has run). */
 int32_t ae_comm_exchange_mode(void *comm);
 void ae_group_range(int32_t G, int32_t nranks, int32_t rank, int32_t *g0, int32_t *gl);
 /* rows [G][Zp]: every rank contributes its cell range of every row, in place (all-gather). */

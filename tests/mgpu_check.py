@@ -115,7 +115,7 @@ def main():
         assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
         assert abs(outs[0][3] - outs[1][3]) < 1e-13 * abs(outs[0][3])
         xmode = dgt.lib.ae_comm_exchange_mode(dgt.comm.handle)
-        want = 0 if os.environ.get("AE_COMM_PEER_COPY") == "0" else 1
+        want = 1 if os.environ.get("AE_COMM_PEER_COPY") == "1" else 0
         assert xmode == want, f"flux exchange mode {xmode}, expected {want} (1 = peer copies, 0 = NCCL)"
         if rank == 0:
             print(f"group-sharded flux exchange: {'peer copies (copy engines + stream memory operations)' if xmode == 1 else 'NCCL all-gather'}")

@@ -740,3 +740,44 @@ def test_boundary_condition_attribute_through_the_public_classes():
     g.source_iteration_for_scalar_flux()
     lit = np.asarray(g.phi.new)
     assert np.all(lit > base) and lit[0, 0] - base[0, 0] > 0.5      # an isotropic unit inflow adds ~1 at the faces
+
+
+# ---------------------------------------------------------- the block kernel of the small dense part ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", FIXTURES)
+def test_dmd_block_kernel_against_the_library_route(golden_dir, name, monkeypatch):
+    """ae_dmd_from_r runs a window as one thread block (Jacobi SVD + rank rule + Atilde + Hessenberg-QR in shared memory,
+    csrc/ae_dmd_small.cuh); AE_DMD_CUSOLVER=1 keeps the cuSOLVER gesvd / Xgeev route.  Same rank, singular values to
+    rounding, same spectrum (to the conditioning of the window)."""
+    g0 = np.load(os.path.join(golden_dir, name + ".npz"))
+    psi, steps, dt = g0["psi"], int(g0["steps"]), float(g0["dt"])
+    monkeypatch.delenv("AE_DMD_CUSOLVER", raising=False)
+    (al, sigma, r), R, (first, K) = _device_dmd(psi, steps, dt)
+    monkeypatch.setenv("AE_DMD_CUSOLVER", "1")
+    (al_l, sigma_l, r_l), _, _ = _device_dmd(psi, steps, dt)
+    assert r == r_l == len(g0["alphas"])
+    assert np.max(np.abs(sigma - sigma_l)) < 5e-15 * sigma_l[0]
+    dom, dom_l = _sorted_c(al)[0], _sorted_c(al_l)[0]
+    assert abs(dom - dom_l) < (1e-5 if "march" in name else 1e-10) * abs(dom_l)
+
+
+@pytest.mark.gpu
+def test_dmd_batched_windows_equal_single_calls(golden_dir):
+    """ae_dmd_from_r_batched: every window of a stack gets exactly what its own ae_dmd_from_r call returns (same kernel,
+    one block per window), and a window without a surviving singular value reports its status alone."""
+    from alpha_eigen_b200 import _lib
+    g0 = np.load(os.path.join(golden_dir, "dmd_modes_64_4_50.npz"))
+    psi, steps, dt = g0["psi"], int(g0["steps"]), float(g0["dt"])
+    (al0, sig0, r0), R, (first, K) = _device_dmd(psi, steps, dt)
+    (al1, sig1, r1), R1, _ = _device_dmd(psi[::-1].copy() * 3.0, steps, dt)
+    from alpha_eigen_b200.device import SlabDevice
+    one = np.ones((1, 1))
+    dev = SlabDevice(8, 1.0, *np.polynomial.legendre.leggauss(2), np.zeros(8, dtype=np.int64), one, one.reshape(1, 1, 1), one, one, one)
+    stack = dev.torch.tensor(np.concatenate([R.ravel(), np.zeros((K + 1) ** 2), R1.ravel(), R.ravel()]), dtype=dev.torch.float64,
+                             device=dev.dev)
+    out = dev.dmd_from_r_batched(stack, 4, K, dt)
+    assert out[1] == _lib.AE_BAD_ARG                                    # all-zero window: no singular value survives
+    for got, (al, sig, r) in ((out[0], (al0, sig0, r0)), (out[2], (al1, sig1, r1)), (out[3], (al0, sig0, r0))):
+        assert got[2] == r
+        np.testing.assert_array_equal(got[1], sig)
+        np.testing.assert_array_equal(got[0], al)

@@ -10,7 +10,7 @@ from alpha_eigen_b200.ensemble import solve_members_batched, synthetic_ensemble 
 from alpha_eigen_b200.time_unit import dmd_window  # noqa: E402
 
 members = synthetic_ensemble(1024, 2048, 16, 12)[::512][:2]
-res = solve_members_batched(members, 0.1, 200, keep_snapshots=True, dmd_threads=1)
+res = solve_members_batched(members, 0.1, 200, keep_snapshots=True)
 r = res[0]
 dev, snap = r["dev"], r["snap"]
 rows = dev.G * dev.A * dev.Zp
