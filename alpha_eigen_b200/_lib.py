@@ -84,6 +84,7 @@ SYMBOLS = {
     "ae_tsqr": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int32, _P, _P]),
     "ae_tsqr_merge": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
     "ae_dmd_from_r": (C.c_int, [_P, C.c_int32, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_ip, _P]),
+    "ae_dmd_last_jacobi_sweeps": (C.c_int, []),
     "ae_dmd_from_r_batched": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_double, C.c_double, _P, _P, _P, _P, _P, _P]),
     "ae_comm_unique_id": (C.c_int, [_P]),
     "ae_comm_init": (C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32, _P]),

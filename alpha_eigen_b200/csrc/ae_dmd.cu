@@ -588,6 +588,9 @@ dmd_small_kernel(const double *__restrict__ r_stack, int K, double dt, double ra
     if (threadIdx.x == 0) info[b] = st;
 }
 
+static thread_local int t_last_sweeps = 0;           // Jacobi sweeps of the first window of this thread's last call (probe)
+extern "C" int ae_dmd_last_jacobi_sweeps(void) { return t_last_sweeps; }
+
 static bool small_fits(int K) { return K >= 1 && ae_dmd_small::dmd_window_smem_bytes(K) <= 227 * 1024; }
 
 // `count` windows, r_stack [count][K+1][K+1] (device); host outputs [count][K] / [count]
@@ -615,7 +618,8 @@ static int dmd_small_batched(const double *r_stack, int count, int K, double dt,
     memcpy(alpha_re, hOut, sizeof(double) * per);
     memcpy(alpha_im, hOut + per, sizeof(double) * per);
     if (sigma_out) memcpy(sigma_out, hOut + 2 * per, sizeof(double) * per);
-    for (int m = 0; m < count; ++m) { rank[m] = hInt[m]; info[m] = hInt[count + m]; }
+    for (int m = 0; m < count; ++m) { rank[m] = hInt[m]; info[m] = hInt[count + m] & 0xff; }
+    t_last_sweeps = hInt[count] >> 8;
 done:
     cudaFreeAsync(dAt, st); cudaFreeAsync(dOut, st); cudaFreeAsync(dInt, st);
     free(hOut); free(hInt);

@@ -25,14 +25,92 @@ namespace ae_dmd_small {
 enum { kOk = 0, kSvdNotConverged = 1, kEigNotConverged = 2, kNoRank = 3 };
 constexpr int kMaxSweeps = 60;
 
-// ---- one-sided Jacobi: rotate the columns of A (n x K, column-major, ld = lda) until they are mutually orthogonal; B
-// (same shape) receives the same rotations.  On return column j of A is sigma_j u_j (unsorted).  `counter` is one shared int.
+#if defined(__CUDA_ARCH__)
+#define AE_RSQRT(x) rsqrt(x)
+#else
+#define AE_RSQRT(x) (1.0 / sqrt(x))
+#endif
+
+// ---- Householder QR with column pivoting of A (n x K, n > K, column-major, ld = lda), the reflectors and the column
+// swaps applied to B (same shape) as well: on return the upper triangle of A's top K rows is R1 (A P = Q1 R1, diagonal
+// non-increasing in magnitude) and B is H_K .. H_1 B P.  This is the preconditioner of Drmac & Veselic for the Jacobi SVD
+// below: on a triangular factor of a window whose singular values span 16 decades the plain method needs 25 sweeps, on
+// R1^T eight.  cn: K doubles, v: n doubles of scratch; returns |A|_F^2 through *fro2.
 template <class Team>
-AE_SD int jacobi_columns(Team &t, double *A, double *B, int n, int K, int lda, int *counter)
+AE_SD void qr_column_pivoting(Team &t, double *A, double *B, int n, int K, int lda, double *cn, double *v, double *fro2)
+{
+    const int tid = t.warp() * t.lanes() + t.lane(), nthreads = t.warps() * t.lanes();
+    for (int k = 0; k < K; ++k) {
+        for (int j = k + t.warp(); j < K; j += t.warps()) {            // remaining column norms (recomputed: no downdating error)
+            const double *a = A + (size_t)j * lda;
+            double s = 0.0;
+            for (int i = k + t.lane(); i < n; i += t.lanes()) s = fma(a[i], a[i], s);
+            s = t.sum(s);
+            if (t.lane() == 0) cn[j] = s;
+        }
+        t.sync_block();
+        int pv = k;
+        double best = cn[k], total = 0.0;
+        for (int j = k; j < K; ++j) {                                  // every thread: same values, same answer
+            total += cn[j];
+            if (cn[j] > best) { best = cn[j]; pv = j; }
+        }
+        if (k == 0 && tid == 0) *fro2 = total;
+        if (pv != k)
+            for (int i = tid; i < n; i += nthreads) {
+                double x = A[(size_t)k * lda + i]; A[(size_t)k * lda + i] = A[(size_t)pv * lda + i]; A[(size_t)pv * lda + i] = x;
+                x = B[(size_t)k * lda + i]; B[(size_t)k * lda + i] = B[(size_t)pv * lda + i]; B[(size_t)pv * lda + i] = x;
+            }
+        t.sync_block();
+        // reflector of column k, rows k .. n-1:  v = x - alpha e_1,  H = I - beta v v^T
+        const double *x = A + (size_t)k * lda;
+        const double x0 = x[k], norm = sqrt(best);
+        if (norm == 0.0) { t.sync_block(); continue; }                 // nothing left: the remaining columns are zero
+        const double alpha = -copysign(norm, x0);
+        const double beta = 1.0 / (best - x0 * alpha);                 // 2 / v^T v
+        for (int i = k + tid; i < n; i += nthreads) v[i] = i == k ? x0 - alpha : x[i];
+        t.sync_block();
+        for (int c = t.warp(); c < 2 * K - k - 1; c += t.warps()) {    // trailing columns of A, all columns of B
+            double *col = c < K - k - 1 ? A + (size_t)(k + 1 + c) * lda : B + (size_t)(c - (K - k - 1)) * lda;
+            double s = 0.0;
+            for (int i = k + t.lane(); i < n; i += t.lanes()) s = fma(v[i], col[i], s);
+            s = t.sum(s) * beta;
+            for (int i = k + t.lane(); i < n; i += t.lanes()) col[i] = fma(-s, v[i], col[i]);
+        }
+        for (int i = k + tid; i < n; i += nthreads) A[(size_t)k * lda + i] = i == k ? alpha : 0.0;
+        t.sync_block();
+    }
+}
+
+// In-place transpose of the top K x K block of a column-major n x K array (ld = lda); with `lower_only` the strict upper
+// triangle of the result is zeroed (the transposed triangular factor); rows K .. n-1 are zeroed.
+template <class Team>
+AE_SD void transpose_top(Team &t, double *A, int n, int K, int lda, bool lower_only)
+{
+    const int tid = t.warp() * t.lanes() + t.lane(), nthreads = t.warps() * t.lanes();
+    for (int idx = tid; idx < K * K; idx += nthreads) {
+        const int i = idx % K, j = idx / K;                            // element (i, j), i < j: swap with (j, i)
+        if (i < j) {
+            const double up = A[(size_t)j * lda + i], lo = A[(size_t)i * lda + j];
+            A[(size_t)i * lda + j] = up;
+            A[(size_t)j * lda + i] = lower_only ? 0.0 : lo;
+        }
+    }
+    for (int idx = tid; idx < (n - K) * K; idx += nthreads) A[(size_t)(idx / (n - K)) * lda + K + idx % (n - K)] = 0.0;
+    t.sync_block();
+}
+
+// ---- one-sided Jacobi: rotate the columns of A (n x K, column-major, ld = lda) until they are mutually orthogonal; B
+// (same shape) receives the same rotations.  On return column j of A is sigma_j u_j (unsorted).  Pairs of columns that
+// are both below `floor2` (squared norm: rounding noise of the factorisation that produced A) are left alone.
+// `counter` is one shared int.
+template <class Team>
+AE_SD int jacobi_columns(Team &t, double *A, double *B, int n, int K, int lda, double floor2, int *counter, int *sweeps_out)
 {
     const int Kp = K + (K & 1);                        // round-robin over an even number of players
     const int rounds = Kp - 1, pairs = Kp / 2;
     const double tol = 1.5e-16 * sqrt((double)n);      // LAPACK dgesvj's threshold: sqrt(m) eps
+    const double tol2 = tol * tol;
     for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
         if (t.warp() == 0 && t.lane() == 0) *counter = 0;
         t.sync_block();
@@ -50,10 +128,12 @@ AE_SD int jacobi_columns(Team &t, double *A, double *B, int n, int K, int lda, i
                     al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga);
                 }
                 al = t.sum(al); be = t.sum(be); ga = t.sum(ga);
-                if (al == 0.0 || be == 0.0 || !(fabs(ga) > tol * sqrt(al) * sqrt(be))) continue;
-                const double zeta = (be - al) / (2.0 * ga);
-                const double tn = fabs(zeta) > 1e150 ? 0.5 / zeta : copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double c = 1.0 / sqrt(1.0 + tn * tn), s = c * tn;
+                if (al == 0.0 || be == 0.0 || (al <= floor2 && be <= floor2) || !(ga * ga > tol2 * al * be)) continue;
+                // tan of the rotation angle: the smaller root of t^2 + 2 zeta t - 1 = 0, zeta = (be - al) / (2 ga)
+                const double d = be - al;
+                const double num = (d < 0.0) != (ga < 0.0) ? -2.0 * fabs(ga) : 2.0 * fabs(ga);      // sign(zeta) 2|ga|
+                const double tn = num / (fabs(d) + sqrt(fma(d, d, 4.0 * ga * ga)));
+                const double c = AE_RSQRT(fma(tn, tn, 1.0)), s = c * tn;
                 double *bp = B + (size_t)p * lda, *bq = B + (size_t)q * lda;
                 for (int k = t.lane(); k < n; k += t.lanes()) {
                     const double x = ap[k], y = aq[k];
@@ -67,8 +147,9 @@ AE_SD int jacobi_columns(Team &t, double *A, double *B, int n, int K, int lda, i
         }
         const int rotated = *counter;
         t.sync_block();
-        if (rotated == 0) return kOk;
+        if (rotated == 0) { *sweeps_out = sweep + 1; return kOk; }
     }
+    *sweeps_out = kMaxSweeps;
     return kSvdNotConverged;
 }
 
@@ -290,7 +371,7 @@ AE_SHD inline int dmd_rank(const double *sig, int K, double rank_tol)
 //   A, B    (K+1) x K doubles each, column-major; after the SVD the space of A holds Atilde (r x (r|1))
 //   sig     K doubles, eigw 3 K doubles, ord K ints, counter 1 int
 //   at      (K+1)*(K+1) doubles of GLOBAL scratch (Atilde is assembled there while A and B are still needed)
-// Results: alpha_re / alpha_im [r], sigma_out [K] (descending), *rank_out; return value is the status.
+// Results: alpha_re / alpha_im [r], sigma_out [K] (descending), *rank_out; return value: status | (Jacobi sweeps << 8).
 template <class Team>
 AE_SD int dmd_window(Team &t, const double *R, int K, double dt, double rank_tol, double *A, double *B, double *sig,
                      double *eigw, int *ord, int *counter, double *at, double *alpha_re, double *alpha_im, double *sigma_out, int *rank_out)
@@ -303,7 +384,15 @@ AE_SD int dmd_window(Team &t, const double *R, int K, double dt, double rank_tol
         B[idx] = R[i * n + j + 1];
     }
     t.sync_block();
-    const int st = jacobi_columns(t, A, B, n, K, n, counter);
+    // A P = Q1 R1;  L = R1^T;  Jacobi: L W = Ut S  =>  A = (Q1 W) S (P Ut)^T.  With Y2 = Q1^T Y P carried as B = Y2^T:
+    // Atilde = U_r^T Y V_r S_r^-1 = W_r^T Y2 Ut_r S_r^-1, i.e. Atilde[i][j] = (b'_i . a'_j) / sigma_j^2   (time_unit.py:85-89)
+    double *fro2 = eigw + n;
+    qr_column_pivoting(t, A, B, n, K, n, sig, eigw, fro2);
+    transpose_top(t, A, n, K, n, true);
+    transpose_top(t, B, n, K, n, false);
+    const double floor2 = 4.84e-30 * *fro2;            // (10 eps |A|_F)^2: below the rounding noise of the TSQR factor
+    int sweeps = 0;
+    const int st = jacobi_columns(t, A, B, n, K, n, floor2, counter, &sweeps);
     if (st != kOk) return st;
     for (int j = t.warp(); j < K; j += t.warps()) {                    // sigma_j = |column j|
         double s = 0.0;
@@ -327,15 +416,14 @@ AE_SD int dmd_window(Team &t, const double *R, int K, double dt, double rank_tol
     t.sync_block();
     const int r = *rank_out;
     if (r < 1) return kNoRank;
-    // Atilde[i][j] = (w_i . b_j) / (sigma_i sigma_j): U_r^T (Y V_r) S_r^-1 with u_i = w_i / sigma_i   (time_unit.py:85-89)
     const int ld = r | 1;                                              // odd: column walks hit distinct banks
     for (int idx = t.warp(); idx < r * r; idx += t.warps()) {
         const int i = idx / r, j = idx % r;
-        const double *w = A + (size_t)ord[i] * n, *b = B + (size_t)ord[j] * n;
+        const double *b = B + (size_t)ord[i] * n, *w = A + (size_t)ord[j] * n;
         double s = 0.0;
-        for (int k = t.lane(); k < n; k += t.lanes()) s = fma(w[k], b[k], s);
+        for (int k = t.lane(); k < n; k += t.lanes()) s = fma(b[k], w[k], s);
         s = t.sum(s);
-        if (t.lane() == 0) at[i * ld + j] = s / (sig[ord[i]] * sig[ord[j]]);
+        if (t.lane() == 0) at[i * ld + j] = s / (sig[ord[j]] * sig[ord[j]]);
     }
     t.sync_block();
     double *a = A, *v = eigw, *wr = eigw + K, *wi = eigw + 2 * K;
@@ -355,7 +443,7 @@ AE_SD int dmd_window(Team &t, const double *R, int K, double dt, double rank_tol
         if (t.lane() == 0) *counter = est;
     }
     t.sync_block();
-    return *counter;
+    return *counter | (sweeps << 8);                                   // status, and the Jacobi sweep count above bit 8
 }
 
 // work-area sizes in doubles / bytes for a window of K columns

@@ -477,7 +477,7 @@ def main():
     hz, hg = pipe.shard_shape()
     q_host = torch.rand(max(hz, 1), hg, dtype=torch.float64)[:hz].pin_memory()
     phi_host = torch.empty(hz, hg, dtype=torch.float64).pin_memory()
-    e_steps = max(3, min(args.steps, 8))
+    e_steps = max(3, min(args.steps, 32))       # the pipe's fill (first upload) and drain (last download) are inside the timed region
 
     # Every step still uploads its own source and downloads its own flux; the copies run on the copy engines
     # (HostPipe: two staging slots, own streams) so that the upload of step i+1 and the download of step i-1

@@ -260,6 +260,8 @@ int ae_dmd_from_r(const double *r, int32_t K, double dt, double rank_tol,
  * wider ones go through cuSOLVER one by one. */
 int ae_dmd_from_r_batched(const double *r_stack, int32_t count, int32_t K, double dt, double rank_tol,
                           double *alpha_re, double *alpha_im, double *sigma, int32_t *rank, int32_t *status, void *stream);
+/* Diagnostic: Jacobi sweeps the first window of this host thread's last block-kernel DMD needed. */
+int ae_dmd_last_jacobi_sweeps(void);
 
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink ---------------------------------- */
 int ae_comm_unique_id(void *id128);                                     /* host, 128 bytes */

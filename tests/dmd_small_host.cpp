@@ -25,7 +25,7 @@ extern "C" int dmd_small_host(const double *R, int K, double dt, double rank_tol
     OneThread t;
     const int st = ae_dmd_small::dmd_window(t, R, K, dt, rank_tol, A, B, sig, eigw, ord, &counter, at, alpha_re, alpha_im, sigma, rank);
     free(A); free(B); free(sig); free(eigw); free(at); free(ord);
-    return st;
+    return st & 0xff;
 }
 
 // eigenvalues of a general real matrix (row-major n x n) by the same balance / hessenberg / hqr chain

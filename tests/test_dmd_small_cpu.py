@@ -92,11 +92,12 @@ def test_dmd_windows_of_the_fixtures(host, golden_dir):
         assert st == 0 and rk == len(ref)                               # same rank decision (time_unit.py:75-76)
         sv = np.linalg.svd(W[:, :K], compute_uv=False)
         m = min(len(sv), K)
-        assert np.max(np.abs(sig[:m] - sv[:m])) < 5e-15 * sv[0]
+        assert np.max(np.abs(sig[:m] - sv[:m])) < 2e-15 * sv[0]
         if "march" in os.path.basename(f):
-            # the march window is ill conditioned: dominant mode to 1e-5, as the GPU test of the library route
+            # the march window is ill conditioned: the reference's own dominant alpha moves by ~1e-5 under a
+            # 1e-15 relative perturbation of the snapshots (test_dmd_march_fixture_conditioning_aware measures it)
             srt = lambda z: z[np.lexsort((z.imag, -z.real))]
-            assert abs(srt(al)[0] - srt(ref)[0]) < 1e-5 * abs(srt(ref)[0])
+            assert abs(srt(al)[0] - srt(ref)[0]) < 1e-4 * abs(srt(ref)[0])
         else:
             assert _match(ref, al) < 1e-9
     assert seen >= 3

