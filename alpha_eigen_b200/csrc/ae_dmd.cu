@@ -37,7 +37,7 @@ __device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, dou
 __global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ snap, int64_t ld, int64_t len, int n,
                                                    int64_t cols_per_cta, double *__restrict__ partial)
 {
-    __shared__ double tile[kGN * kGStride];
+    extern __shared__ double gram_tiles[];              // two stages of kGN x kGStride: the next one loads while this one is used
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t c_begin = (int64_t)blockIdx.x * cols_per_cta;
     const int64_t c_end = min(len, c_begin + cols_per_cta);
@@ -48,15 +48,31 @@ __global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ sn
 #pragma unroll
         for (int b = 0; b < 16; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    for (int64_t c0 = c_begin; c0 < c_end; c0 += kGK) {
-        __syncthreads();
-        // stage rows 0..127 x kGK columns (zero beyond n / c_end); 32 consecutive doubles per row
+    // stage rows 0..127 x kGK columns (zero beyond n / c_end) with 8-byte asynchronous copies: 32 consecutive doubles per row
+    auto stage = [&](int buf, int64_t c0) {
+        double *tile = gram_tiles + buf * (kGN * kGStride);
         for (int idx = tid; idx < kGN * kGK; idx += 256) {
             const int r = idx / kGK, k = idx % kGK;
             const int64_t c = c0 + k;
-            tile[r * kGStride + k] = (r < n && c < c_end) ? snap[(int64_t)r * ld + c] : 0.0;
+            const bool live = r < n && c < c_end;
+            const double *src = live ? snap + (int64_t)r * ld + c : snap;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + r * kGStride + k);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(live ? 8 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (c_begin < c_end) stage(0, c_begin);
+    int it = 0;
+    for (int64_t c0 = c_begin; c0 < c_end; c0 += kGK, ++it) {
+        const bool more = c0 + kGK < c_end;
+        if (more) {
+            stage((it + 1) & 1, c0 + kGK);              // its previous user finished at the barrier that ended iteration it-1
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
+        const double *tile = gram_tiles + (it & 1) * (kGN * kGStride);
 #pragma unroll
         for (int k0 = 0; k0 < kGK; k0 += 4) {
             const double a0 = tile[(s0 * 8 + (lane >> 2)) * kGStride + k0 + (lane & 3)];
@@ -70,6 +86,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ sn
                 }
             }
         }
+        __syncthreads();
     }
     // C fragment: row = lane/4, cols = 2*(lane%4) + {0,1}; only the live tiles are written (the reduction mirrors them)
     double *out = partial + (size_t)blockIdx.x * kGN * kGN;
@@ -395,9 +412,15 @@ extern "C" int ae_gram(const double *snap, int64_t ld, int64_t len, int32_t n, d
     int64_t cols = (len + nparts - 1) / nparts;
     cols = (cols + kGK - 1) / kGK * kGK;
     nparts = (int)((len + cols - 1) / cols);
+    constexpr int gram_smem = 2 * kGN * kGStride * (int)sizeof(double);
+    static bool gram_attr = false;
+    if (!gram_attr) {
+        AE_CUDA(cudaFuncSetAttribute((const void *)gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem));
+        gram_attr = true;
+    }
     double *partial = nullptr;
     AE_CUDA(cudaMallocAsync((void **)&partial, (size_t)nparts * kGN * kGN * sizeof(double), st));
-    gram_kernel<<<nparts, 256, 0, st>>>(snap, ld, len, n, cols, partial);
+    gram_kernel<<<nparts, 256, gram_smem, st>>>(snap, ld, len, n, cols, partial);
     gram_reduce_kernel<<<(n * n + 255) / 256, 256, 0, st>>>(partial, nparts, n, gram);
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(partial, st);
@@ -554,15 +577,20 @@ extern "C" int ae_tsqr_merge(const double *r_stack, int32_t count, int32_t n, do
 }
 
 // ---- the small dense part as ONE block per window (ae_dmd_small.cuh) ----------------------------------------------
-struct BlockTeam {
-    __device__ int lane() const { return threadIdx.x & 31; }
-    __device__ int lanes() const { return 32; }
-    __device__ int warp() const { return threadIdx.x >> 5; }
-    __device__ int warps() const { return blockDim.x >> 5; }
+// A thread block seen as groups of L lanes (L = 32: warps).  A group plays the "warp" of ae_dmd_small.cuh: it owns one
+// column pair of a Jacobi round, so with L = 8 one warp instruction works on four pairs (the FP64 pipe issues a warp
+// instruction in two cycles whatever the number of active lanes, and the rotation scalars are computed by every lane).
+template <int L>
+struct GroupTeam {
+    __device__ int lane() const { return threadIdx.x & (L - 1); }
+    __device__ int lanes() const { return L; }
+    __device__ int warp() const { return threadIdx.x / L; }
+    __device__ int warps() const { return blockDim.x / L; }
     __device__ double sum(double x) const
     {
+        const unsigned mask = L == 32 ? 0xffffffffu : ((1u << L) - 1u) << (threadIdx.x & 31 & ~(L - 1));
 #pragma unroll
-        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);   // butterfly: every lane gets the same bits
+        for (int o = L / 2; o; o >>= 1) x += __shfl_xor_sync(mask, x, o);       // butterfly: every lane gets the same bits
         return x;
     }
     __device__ void count(int *c) const { atomicAdd(c, 1); }
@@ -582,8 +610,9 @@ dmd_small_kernel(const double *__restrict__ r_stack, int K, double dt, double ra
     const size_t b = blockIdx.x;
     double *A = small_smem, *B = A + (size_t)n * K, *sig = B + (size_t)n * K, *eigw = sig + K;
     int *ord = (int *)(eigw + 3 * K), *counter = ord + K;
-    BlockTeam t;
-    const int st = ae_dmd_small::dmd_window(t, r_stack + b * n * n, K, dt, rank_tol, A, B, sig, eigw, ord, counter,
+    GroupTeam<8> t;
+    GroupTeam<32> te;
+    const int st = ae_dmd_small::dmd_window(t, te, r_stack + b * n * n, K, dt, rank_tol, A, B, sig, eigw, ord, counter,
                                             at_scratch + b * n * n, alpha_re + b * K, alpha_im + b * K, sigma + b * K, rank + b);
     if (threadIdx.x == 0) info[b] = st;
 }

@@ -367,13 +367,14 @@ AE_SHD inline int dmd_rank(const double *sig, int K, double rank_tol)
     return r;
 }
 
-// ---- the whole window.  R: (K+1) x (K+1) row-major triangular factor (global).  Work areas (shared memory on the GPU):
+// ---- the whole window.  `t` is the team of the SVD stage (its "warps" take column pairs: on the GPU groups of 8 lanes, so
+// that a warp instruction carries four pairs), `te` the team of the eigenvalue stage (one full warp).  R: (K+1) x (K+1) row-major triangular factor (global).  Work areas (shared memory on the GPU):
 //   A, B    (K+1) x K doubles each, column-major; after the SVD the space of A holds Atilde (r x (r|1))
 //   sig     K doubles, eigw 3 K doubles, ord K ints, counter 1 int
 //   at      (K+1)*(K+1) doubles of GLOBAL scratch (Atilde is assembled there while A and B are still needed)
 // Results: alpha_re / alpha_im [r], sigma_out [K] (descending), *rank_out; return value: status | (Jacobi sweeps << 8).
-template <class Team>
-AE_SD int dmd_window(Team &t, const double *R, int K, double dt, double rank_tol, double *A, double *B, double *sig,
+template <class Team, class EigTeam>
+AE_SD int dmd_window(Team &t, EigTeam &te, const double *R, int K, double dt, double rank_tol, double *A, double *B, double *sig,
                      double *eigw, int *ord, int *counter, double *at, double *alpha_re, double *alpha_im, double *sigma_out, int *rank_out)
 {
     const int n = K + 1;
@@ -430,17 +431,17 @@ AE_SD int dmd_window(Team &t, const double *R, int K, double dt, double rank_tol
     for (int idx = tid; idx < r * ld; idx += nthreads) a[idx] = (idx % ld) < r ? at[idx] : 0.0;
     t.sync_block();
     int est = kOk;
-    if (t.warp() == 0) {
-        balance(t, a, r, ld);
-        hessenberg(t, a, r, ld, v);
-        est = hqr(t, a, r, ld, wr, wi);
+    if (te.warp() == 0) {
+        balance(te, a, r, ld);
+        hessenberg(te, a, r, ld, v);
+        est = hqr(te, a, r, ld, wr, wi);
         if (est == kOk)
-            for (int j = t.lane(); j < r; j += t.lanes()) {            // alpha = (1 - 1/lambda)/dt  (time_unit.py:91)
+            for (int j = te.lane(); j < r; j += te.lanes()) {          // alpha = (1 - 1/lambda)/dt  (time_unit.py:91)
                 const double re = wr[j], im = wi[j], d = re * re + im * im;
                 alpha_re[j] = (1.0 - re / d) / dt;
                 alpha_im[j] = (im / d) / dt;
             }
-        if (t.lane() == 0) *counter = est;
+        if (te.lane() == 0) *counter = est;
     }
     t.sync_block();
     return *counter | (sweeps << 8);                                   // status, and the Jacobi sweep count above bit 8

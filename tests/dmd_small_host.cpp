@@ -23,7 +23,7 @@ extern "C" int dmd_small_host(const double *R, int K, double dt, double rank_tol
     double *at = (double *)malloc(sizeof(double) * n * n);
     int *ord = (int *)malloc(sizeof(int) * K), counter = 0;
     OneThread t;
-    const int st = ae_dmd_small::dmd_window(t, R, K, dt, rank_tol, A, B, sig, eigw, ord, &counter, at, alpha_re, alpha_im, sigma, rank);
+    const int st = ae_dmd_small::dmd_window(t, t, R, K, dt, rank_tol, A, B, sig, eigw, ord, &counter, at, alpha_re, alpha_im, sigma, rank);
     free(A); free(B); free(sig); free(eigw); free(at); free(ord);
     return st & 0xff;
 }
