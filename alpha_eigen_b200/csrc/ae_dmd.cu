@@ -199,10 +199,13 @@ __global__ void __launch_bounds__(kTsqrThreads, 1) tsqr_kernel(const double *__r
                     if (ss == 0.0) {
                         hh[0] = 0.0; hh[1] = 0.0;
                     } else {
-                        const double beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
-                        hh[0] = (beta - alpha) / beta;
-                        hh[1] = 1.0 / (alpha - beta);
-                        R[k * ldw + k] = beta;
+                        // dlarfg's beta = -sign(alpha) |(alpha, x)|, tau = (beta - alpha)/beta = 1 + |alpha|/norm and
+                        // 1/(alpha - beta) = sign(alpha)/(|alpha| + norm) from one rsqrt and one reciprocal: this scalar
+                        // chain is what the other 15 warps wait for at the barrier of every step
+                        const double n2 = fma(alpha, alpha, ss), ri = rsqrt(n2), nrm = n2 * ri, aa = fabs(alpha);
+                        hh[0] = fma(aa, ri, 1.0);
+                        hh[1] = copysign(__drcp_rn(aa + nrm), alpha);
+                        R[k * ldw + k] = -copysign(nrm, alpha);
                     }
                 }
             }
