@@ -106,3 +106,53 @@ def test_dmd_windows_of_the_fixtures(host, golden_dir):
 def test_no_singular_value_survives(host):
     st, _, _, rk = _window(host, np.zeros((5, 5)), 4, 0.1)
     assert st == 3 and rk == 0                                          # kNoRank
+
+
+def _reference_window(W, K, dt, tol):
+    """time_unit.py:72-91 on a window W (M, K+1) with LAPACK: the arithmetic the block kernel replaces."""
+    U, S, Vt = np.linalg.svd(W[:, :K], full_matrices=False)
+    r = int(np.sum(1 - np.cumsum(S) / np.sum(S) > tol))
+    At = U[:, :r].T @ W[:, 1:K + 1] @ Vt[:r].T @ np.diag(1 / S[:r])
+    return (1 - 1 / np.linalg.eigvals(At)) / dt, r
+
+
+@pytest.mark.parametrize("K", [9, 28, 57, 115])
+def test_known_linear_dynamics(host, K):
+    """Snapshots of a linear system with five strong modes (one complex pair) and a weak sixth: the reference's rule keeps
+    five (it always drops the last mode before an exactly zero tail), and their alphas are (1 - 1/lambda)/dt
+    (time_unit.py:91) up to the weak mode's leakage; against LAPACK on the same window the spectrum agrees to rounding."""
+    rs = np.random.RandomState(K)
+    lam = np.array([0.999, 0.97, 0.9 + 0.2j, 0.9 - 0.2j, 0.8])
+    M, dt = 400, 0.1
+    v = rs.randn(M, 4)
+    v_re, v_im = rs.randn(M), rs.randn(M)
+    amp = rs.rand(4) + 0.5
+    W = np.zeros((M, K + 1))
+    for s in range(K + 1):
+        pair = (lam[2] ** s) * (v_re + 1j * v_im)
+        W[:, s] = (amp[0] * 0.999 ** s * v[:, 0] + amp[1] * 0.97 ** s * v[:, 1] + 2 * amp[2] * pair.real
+                   + amp[3] * 0.8 ** s * v[:, 2] + 1e-7 * 0.5 ** s * v[:, 3])
+    Rr = np.linalg.qr(W, mode="r")
+    R = np.zeros((K + 1, K + 1))
+    R[:Rr.shape[0]] = Rr
+    st, al, sig, rk = _window(host, R, K, dt, tol=1e-10)
+    ref, r_ref = _reference_window(W, K, dt, 1e-10)
+    assert st == 0 and rk == r_ref and rk in (4, 5)                      # the 9-column window is too short for the fifth
+    assert _match(ref, al) < 1e-8
+    if rk == 5:
+        assert _match((1 - 1 / lam) / dt, al) < 1e-4
+
+
+def test_rank_deficient_wide_window(host):
+    """More columns than rows (K > M, as in the 40-cell fixture): exact zero singular values, rank from the rule."""
+    rs = np.random.RandomState(5)
+    M, K = 30, 60
+    W = rs.randn(M, 3) @ rs.randn(3, K + 1)
+    Rr = np.linalg.qr(W, mode="r")
+    R = np.zeros((K + 1, K + 1))
+    R[:Rr.shape[0]] = Rr
+    st, al, sig, rk = _window(host, R, K, 0.1, tol=1e-10)
+    ref, r_ref = _reference_window(W, K, 0.1, 1e-10)
+    assert st == 0 and rk == r_ref
+    sv = np.linalg.svd(W[:, :K], compute_uv=False)
+    assert np.max(np.abs(sig[:3] - sv[:3])) < 1e-14 * sv[0] and np.all(sig[3:] < 1e-13 * sv[0])
