@@ -113,10 +113,11 @@ def test_time_dependent_sweep_set_matches_oracle():
     assert _rel(dev.psi_to_host(psi), psi_o[:, dev.angles, :]) < 1e-13
 
 
-@pytest.mark.parametrize("Z,A,G", [(8000, 64, 37), (5000, 96, 26)])
+@pytest.mark.parametrize("Z,A,G", [(8000, 64, 37), (5000, 96, 26), (20000, 256, 70)])
 def test_ganged_sweep_matches_oracle(Z, A, G):
     """Shapes with several angle blocks per direction and enough tiles to fill the persistent grid: the kernel
-    runs its CTAs in gangs (ae_sweep_plan says so) with row hand-offs between gangs.  Steady and time-dependent
+    runs its CTAs in gangs (ae_sweep_plan says so) with row hand-offs between gangs.  The last shape is the benchmark
+    problem's own angle and group counts (S256, 70 groups: 16 angle blocks per group, 16 partial flux slabs) on 20 000 cells.  Steady and time-dependent
     (in place) sweep sets against the oracle, bit-for-bit against a second launch (determinism)."""
     import ctypes as C
     from oracle import ae_oracle as orc
