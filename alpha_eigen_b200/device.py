@@ -433,7 +433,8 @@ class SlabDevice:
                                            q_next.data_ptr(), tol, iteration, self.stream))
 
     def sweep_and_update(self, q, psi_in, psi_out, q_next, tol=0.0, iteration=0):
-        """ae_sweep_and_update: one sweep set + flux update (group-sharded ranks overlap the flux exchange with the sweep)."""
+        """ae_sweep_and_update: one sweep set + flux update as one C call (with AE_COMM_PEER_COPY=1 and AE_EXCHANGE_OVERLAP=1
+        group-sharded ranks split it in two group chunks and exchange the first behind the sweep of the second)."""
         ptr = lambda t: t.data_ptr() if t is not None else None
         _lib.check(self.lib.ae_sweep_and_update(C.byref(self.slab), C.byref(self.work), q.data_ptr(), ptr(psi_in), ptr(psi_out),
                                                 q_next.data_ptr(), tol, iteration, self.stream))

@@ -394,7 +394,7 @@ def main():
                           if peer else "ncclAllGather through a staging buffer") +
                          ("; two group chunks, the first travels while the second is swept" if split else "; one chunk after the sweep"))
     if group_mode:
-        # the overlapped step cannot be cut into phases from outside: the sweep kernel is timed alone right after the
+        # the step is ONE C call (ae_sweep_and_update) with no phase boundaries visible here: the sweep kernel is timed alone right after the
         # timed region (same launch, whole grid), the remainder of a step is exchange + update that the sweep did not hide
         fence()
         sev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]

@@ -90,7 +90,8 @@ def main():
     assert st == 0 and list(outer) == list(rm["outer"]) and list(inner) == list(rm["inner"])
     assert rel(dgt.cells_to_host(dgt.phi), rm["phi_last"]) < 1e-10
     assert rel(dgt.psi_to_host(pg), rm["psi_last"][:, dgt.angles, :][..., dgt.groups]) < 1e-10
-    # the overlapped step (two group chunks, exchange of the first behind the sweep of the second) against the two plain calls
+    # ae_sweep_and_update against the two plain calls; with the peer-copy exchange (AE_COMM_PEER_COPY=1) it runs as two
+    # group chunks, the exchange of the first behind the sweep of the second
     if dgt.gl > 0:
         qa = torch.rand(dgt.G * dgt.Zp, dtype=torch.float64, device=dgt.dev, generator=torch.Generator(device=dgt.dev).manual_seed(3))
         dgt.base.zero_()
