@@ -109,6 +109,13 @@ def set_inflow(inflow):
     lib().aeo_set_inflow(_d(_inflow_keep))
 
 
+def set_reflect_left(on: bool):
+    """Reflective LEFT boundary (symmetry plane at x = 0) for every sweep set from now on: a direction mu > 0 enters with
+    the flux its mirror direction left with in the same sweep set.  False = the reference's vacuum."""
+    lib().aeo_set_reflect_left.restype = None
+    lib().aeo_set_reflect_left(1 if on else 0)
+
+
 def sweep_set(mu, w, hx, q, sigT, want_psi=False):
     """All angles x groups with isotropic source q (Z,G); returns phi (Z,G) [, psi (Z,A,G)]."""
     q, sigT, mu, w = _f64(q), _f64(sigT), _f64(mu), _f64(w)

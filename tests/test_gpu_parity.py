@@ -783,3 +783,57 @@ def test_dmd_batched_windows_equal_single_calls(golden_dir):
         assert got[2] == r
         np.testing.assert_array_equal(got[1], sig)
         np.testing.assert_array_equal(got[0], al)
+
+
+# ---------------------------------------------------------- reflective left boundary (method of images) ----
+@pytest.mark.gpu
+def test_reflective_half_slab_power_iteration_reproduces_golden_k():
+    """alpha_eigen_b200.reflect.ReflectedSlabDevice on the right half of the symmetric K-P slab: the reference's golden k of
+    the whole slab (tests/test_short_kornreich_parsons.py:39), the oracle's TRUE reflective solve (aeo_set_reflect_left),
+    same iteration history."""
+    from alpha_eigen_b200.reflect import ReflectedSlabDevice
+    from oracle import ae_oracle as orc
+    from tests.kp import kp_problem
+    p = kp_problem(9, 50, 4)
+    h, t = p["Z"] // 2, p["tables"]
+    dev = ReflectedSlabDevice(h, p["hx"], p["mu"], p["weight"], t.mat[h:], t.total, t.scat, t.chi, t.nusf, t.invspeed)
+    r = dev.power_iteration(p["phi0"][h:])
+    orc.set_reflect_left(True)
+    try:
+        ro = orc.power_iteration(p["mu"], p["weight"], p["hx"], orc.Tables(t.mat[h:], t.total, t.scat, t.chi, t.nusf, t.invspeed),
+                                 p["phi0"][h:])
+    finally:
+        orc.set_reflect_left(False)
+    assert r["status"] == 0 and ro["status"] == 0
+    assert abs(r["k_new"] - 0.9358157950764868) < 1e-12 and abs(r["k_new"] - ro["k_new"]) < 1e-13
+    assert list(r["si_hist"]) == list(ro["si_hist"])
+    assert _rel(r["phi_new"], ro["phi_new"]) < 1e-12
+
+
+@pytest.mark.gpu
+def test_reflective_multigroup_source_iteration_and_march():
+    """Three groups, two materials, random source and initial angular flux on the half slab: source iteration and a 3-step
+    march of the mirrored device solve against the oracle's true reflection (iteration counts, phi, psi)."""
+    from alpha_eigen_b200.reflect import ReflectedSlabDevice
+    from oracle import ae_oracle as orc
+    p = _mg_problem(300, 6, 3, M=2, seed=12)
+    t = p["tables"]
+    args = (p["Z"], p["hx"], p["mu"], p["weight"], t.mat, t.total, t.scat, t.chi, t.nusf, t.invspeed)
+    src = p["rs"].rand(p["Z"], 3) + 0.1
+    psi0 = p["rs"].rand(p["Z"], 6, 3)
+    dev = ReflectedSlabDevice(*args)
+    st, phi, it = dev.source_iteration(src)
+    devt = ReflectedSlabDevice(*args, dt=0.1, s_ext=src)
+    rm = devt.time_march(psi0, 3)
+    orc.set_reflect_left(True)
+    try:
+        st_o, phi_o, it_o = orc.source_iteration(p["mu"], p["weight"], p["hx"], t, src)
+        ro = orc.time_march(p["mu"], p["weight"], p["hx"], t, src, psi0, 0.1, 3)
+    finally:
+        orc.set_reflect_left(False)
+    assert st == 0 and st_o == 0 and it == it_o
+    assert _rel(phi, phi_o) < 1e-12
+    assert rm["status"] == 0 and ro["status"] == 0
+    assert list(rm["outer"]) == list(ro["outer"]) and list(rm["inner"]) == list(ro["inner"])
+    assert _rel(rm["phi_last"], ro["phi_last"]) < 1e-10
+    assert _rel(rm["psi_last"], ro["psi_last"]) < 1e-10

@@ -178,3 +178,56 @@ def test_incident_boundary_flux_analytic():
     # vacuum is the zero-inflow case of the same routine
     psi_v = orc.sweep(0.7, hx, np.ones(Z), np.full(Z, sig))
     assert psi_v[0] == 0.5 * (0 + 1 / (0.7 / hx + 0.5 * sig))
+
+
+# ------------------------------------------------------------------ reflective left boundary ----
+@pytest.mark.parametrize("cpm,A", [(50, 4), (100, 16)])
+def test_reflective_half_slab_reproduces_reference_golden_k(cpm, A):
+    """The reference has no reflective boundary, but its K-P slab is symmetric about its centre (slab.py:41-56; phi0 =
+    half + half[::-1], phi.py:10-11): the right half with a TRUE reflective left face (oracle: aeo_set_reflect_left, a
+    direction enters with what its mirror left with) must reproduce the reference's golden k of the whole slab, with the
+    same iteration history."""
+    p = kp_problem(9, cpm, A)
+    h = p["Z"] // 2
+    t = p["tables"]
+    full = orc.power_iteration(p["mu"], p["weight"], p["hx"], t, p["phi0"])
+    half = orc.Tables(t.mat[h:], t.total, t.scat, t.chi, t.nusf, t.invspeed)
+    orc.set_reflect_left(True)
+    try:
+        r = orc.power_iteration(p["mu"], p["weight"], p["hx"], half, p["phi0"][h:])
+    finally:
+        orc.set_reflect_left(False)
+    assert r["status"] == 0
+    assert abs(r["k_new"] - REF_GOLDEN_K[(cpm, A)]) < 1e-13
+    assert list(r["si_hist"]) == list(full["si_hist"])
+    np.testing.assert_allclose(r["phi_new"], full["phi_new"][h:], rtol=1e-13)
+
+
+def test_reflective_march_equals_mirrored_march():
+    """Time-dependent multigroup form of the same statement: the reflective half-slab march equals the right half of the
+    march of the mirrored slab (psi(-x, mu) = psi(x, -mu) initially), iteration counts included."""
+    rs = np.random.RandomState(11)
+    Z, A, G, M, steps = 60, 6, 3, 2, 3
+    mu, w = np.polynomial.legendre.leggauss(A)
+    mat = (np.arange(Z) * M) // Z
+    total = 0.5 + rs.rand(M, G)
+    scat = 0.3 * rs.rand(M, G, G) * total[:, :, None] / G
+    chi = np.tile(rs.dirichlet(np.ones(G)), (M, 1))
+    nusf = 0.05 * rs.rand(M, G)
+    inv = 0.5 + rs.rand(M, G)
+    half = orc.Tables(mat, total, scat, chi, nusf, inv)
+    mirror = lambda a: np.concatenate([a[::-1], a], axis=0)
+    full = orc.Tables(mirror(mat), total, scat, chi, nusf, inv)
+    psi0 = rs.rand(Z, A, G)
+    S = rs.rand(Z, G)
+    anti = np.array([int(np.argmin(np.abs(mu + m))) for m in mu])
+    rf = orc.time_march(mu, w, 0.1, full, mirror(S), np.concatenate([psi0[::-1][:, anti, :], psi0], axis=0), 0.1, steps)
+    orc.set_reflect_left(True)
+    try:
+        rh = orc.time_march(mu, w, 0.1, half, S, psi0, 0.1, steps)
+    finally:
+        orc.set_reflect_left(False)
+    assert rf["status"] == 0 and rh["status"] == 0
+    assert list(rf["outer"]) == list(rh["outer"]) and list(rf["inner"]) == list(rh["inner"])
+    np.testing.assert_allclose(rh["psi_last"], rf["psi_last"][Z:], rtol=1e-12)
+    np.testing.assert_allclose(rh["phi_last"], rf["phi_last"][Z:], rtol=1e-12)
